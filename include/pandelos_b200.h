@@ -1,0 +1,136 @@
+/* pandelos_b200 — C ABI of the B200-native PanDelos `Pangenes` similarity engine.
+ *
+ * This is the drop-in boundary for ONE path of Guilucand/PanDelos: everything the reference's JNI library
+ * `ig/native/library.cpp` does behind its two entry points (citations relative to the reference tree):
+ *
+ *   Java_infoasys_cli_pangenes_PangeneNative_preprocessSequences   ig/native/pangene_native.h:16-17, library.cpp:189-371
+ *   Java_infoasys_cli_pangenes_PangeneNative_computeScores         ig/native/pangene_native.h:24-25, library.cpp:529-604
+ *
+ * `libnative.so` (csrc/jni_shim.cpp) exports exactly those two JNI symbols and forwards to the functions below;
+ * the native `pangenes` CLI, the Python/ctypes binding and bench.py call them directly.  Plain pointers and sizes
+ * only.  All work runs in hand-written sm_100a CUDA kernels; there is no CPU implementation behind this ABI —
+ * without a CUDA device every entry point fails with PD_ERR_NO_DEVICE.
+ *
+ * Results are bit-identical to the reference: same k-mer ranks and counts, same candidate cells, same float32
+ * score/perc/tr_perc bit patterns, same best-hit maxima.  The ORDER of the returned cells is unspecified (the
+ * reference's consumers, Pangenes.java:98-176, only take max/min/set-insert over them).
+ */
+#ifndef PANDELOS_B200_H
+#define PANDELOS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PD_OK 0
+#define PD_ERR_INVALID (-1)     /* bad argument (k <= 0, null pointer, unknown genome, offsets not ascending) */
+#define PD_ERR_UNSUPPORTED (-2) /* base^k >= 2^63 (the reference's Rabin-hash fallback, library.cpp:81-86,103-119),
+                                   >= 2^31 k-mers (the reference's own int limit, library.cpp:174,281,300),
+                                   or a gene of 2^20 or more residues */
+#define PD_ERR_CUDA (-3)        /* a CUDA call or kernel failed */
+#define PD_ERR_NO_DEVICE (-4)   /* no usable CUDA device */
+#define PD_ERR_NOMEM (-5)
+
+typedef struct pd_index pd_index; /* the device-resident index: replaces `pair_info global_info` (library.cpp:56-73) */
+
+typedef struct pd_options {
+    int32_t device;          /* CUDA ordinal; -1 = the calling thread's current device */
+    int32_t verbose;         /* 1 = print the reference's cost report (library.cpp:347-370) to stdout */
+    int32_t contexts;        /* concurrent pd_compute_scores calls served without blocking (0 = default 2) */
+    int32_t hash_log2;       /* log2 slots of the per-row shared-memory accumulator (0 = default 12) */
+    uint64_t cell_capacity;  /* initial per-call cell buffer, in cells (0 = automatic) */
+    int32_t keep_sorted;     /* 1 = keep the sorted k-mer keys so pd_entries can return ranks (tests) */
+    int32_t reserved;
+} pd_options;
+
+typedef struct pd_index_info {
+    uint32_t S;            /* genes */
+    uint32_t G;            /* genomes = max genome id + 1 (library.cpp:242) */
+    int32_t k;
+    uint32_t base;         /* alphabet size = distinct bytes present (library.cpp:96-100) */
+    uint32_t rank_bits;    /* bits of a k-mer rank */
+    uint32_t seq_bits;     /* bits of a gene id in the 64-bit sort key */
+    uint64_t N;            /* k-mer occurrences */
+    uint64_t U;            /* unique (k-mer, gene) entries = posting entries */
+    uint64_t groups;       /* rank groups after the tail merge (library.cpp:300-306) */
+    uint64_t R;            /* forward entries: (gene, shared k-mer) pairs */
+    uint64_t lookups;      /* the reference's "Total cost: N lookups" (library.cpp:349) */
+    uint32_t max_kseq;     /* longest gene, in k-mers */
+    uint32_t reserved;
+    double build_ms[8];    /* device time: histogram, encode, sort, groups, forward index, total, h2d, unused */
+} pd_index_info;
+
+/* Flat image of infoasys.cli.pangenes.Scores (ig/infoasys/cli/pangenes/Scores.java:3-35), one computeScores call.
+ * All arrays are pinned host memory owned by the library until pd_scores_release. */
+typedef struct pd_scores {
+    int32_t scoresCount;
+    int32_t S;                   /* length of scoresMaxMappings / max_genome_score_col */
+    int32_t rows;                /* genes of this genome = rows of max_genome_score */
+    int32_t G;
+    float* scores;               /* Jaccard = sum(min)/sum(max), float32 (library.cpp:501) */
+    float* percs;                /* library.cpp:497 */
+    float* tr_percs;             /* library.cpp:498 */
+    int32_t* row;
+    int32_t* column;
+    int32_t* first_seq_genome;
+    int32_t* second_seq_genome;
+    float* max_genome_score;     /* rows x G row-major: best score of the row against each genome (library.cpp:513-514) */
+    float* max_genome_score_col; /* S: best score of each column against this genome's rows (library.cpp:515) */
+    int32_t* scoresMaxMappings;  /* S: gene -> row index within this genome, INT32_MAX elsewhere (library.cpp:428-432) */
+    void* owner;                 /* private */
+} pd_scores;
+
+/* Device-side timing/volume of the last scoring call on a context or of pd_score_partition_device. */
+typedef struct pd_score_stats {
+    uint64_t rows;
+    uint64_t lookups;        /* posting entries visited */
+    uint64_t pairs;          /* candidate (row, col != row) cells evaluated (finalize evaluations, library.cpp:493) */
+    uint64_t cells;          /* non-zero cells emitted */
+    uint64_t fallback_rows;  /* rows that overflowed the shared-memory accumulator and took the dense global path */
+    uint64_t launches;       /* kernels launched */
+    double kernel_ms;        /* CUDA-event time of the scoring kernels */
+    double total_ms;         /* CUDA-event time of the whole call on its stream (memsets, kernels, copies) */
+} pd_score_stats;
+
+const char* pd_last_error(void);  /* message of the calling thread's last failure */
+int pd_device_count(void);
+
+/* preprocessSequences.  residues: concatenated sequence bytes (Latin-1 / ASCII, as `jchar < 256` in library.cpp:223);
+ * offsets[S+1] ascending with offsets[0] == 0; genome_of[S].  Host pointers. */
+int pd_build(const uint8_t* residues, const uint64_t* offsets, const uint32_t* genome_of, uint32_t S, int32_t k,
+             const pd_options* opt, pd_index** out);
+/* Same, with `residues` already in device memory (offsets / genome_of stay host pointers: O(S) metadata). */
+int pd_build_device(const uint8_t* d_residues, const uint64_t* offsets, const uint32_t* genome_of, uint32_t S, int32_t k,
+                    const pd_options* opt, pd_index** out);
+void pd_free(pd_index* ix);
+
+int pd_info(const pd_index* ix, pd_index_info* out);
+/* per gene: kseq_lengths (library.cpp:250-262) and computation_costs[].total_visited (library.cpp:327); either may be NULL */
+int pd_gene_stats(const pd_index* ix, uint32_t* kseq_len, uint64_t* total_visited);
+/* the sorted, count-deduplicated entry list (library.cpp:280-287) and each entry's group (start, len); any may be NULL.
+ * `rank` needs pd_options.keep_sorted. */
+int pd_entries(const pd_index* ix, uint64_t* rank, uint32_t* seq, uint32_t* count, uint32_t* group_start, uint32_t* group_len);
+
+/* computeScores(genome).  Thread-safe; blocks while all contexts are in use. */
+int pd_compute_scores(pd_index* ix, uint32_t genome, pd_scores* out);
+void pd_scores_release(pd_index* ix, pd_scores* s);
+int pd_last_score_stats(const pd_scores* s, pd_score_stats* out);
+
+/* Device-resident scoring of the gene range [row_begin, row_end) (multi-GPU partitions, bench `value`):
+ * cells stay in the context's HBM buffers; d_best_hit (device, (row_end-row_begin) x G floats, may be NULL)
+ * receives BH[r][h] = best score of gene r against genome h.  Rows are processed in blocks of `rows_per_launch`
+ * genes (0 = automatic), each block's cells overwriting the previous block's. */
+int pd_score_partition_device(pd_index* ix, uint32_t row_begin, uint32_t row_end, uint32_t rows_per_launch,
+                              float* d_best_hit, pd_score_stats* stats);
+
+/* Splits [0, S) into `parts` contiguous gene ranges of near-equal total_visited (query partitioning by
+ * posting-list volume); bounds[parts+1].  snap_to_genomes != 0 moves boundaries to genome boundaries. */
+int pd_partition_rows(const pd_index* ix, uint32_t parts, int32_t snap_to_genomes, uint32_t* bounds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,721 @@
+// Host orchestration of the B200 Pangenes engine: index build (preprocessSequences, reference
+// ig/native/library.cpp:189-371) and scoring calls (computeScores, library.cpp:409-604).  All arithmetic runs in
+// the kernels of index_kernels.cuh / score_kernels.cuh / prims.cuh; this file sizes buffers, orders launches on one
+// stream per context and moves results.  There is no CPU implementation of any step.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#include "index_kernels.cuh"
+#include "prims.cuh"
+#include "score_kernels.cuh"
+
+namespace pd {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+const std::string& last_error() { return g_last_error; }
+
+namespace {
+
+inline unsigned blocks_for(uint64_t n, unsigned per = 256) { return (unsigned)((n + per - 1) / per); }
+inline int bits_for(uint64_t v) {  // bits needed to represent values 0..v
+    int b = 0;
+    while (v) {
+        b++;
+        v >>= 1;
+    }
+    return b;
+}
+
+struct Timer {
+    rt::event_t a, b;
+    rt::stream_t st;
+    explicit Timer(rt::stream_t s) : st(s) {
+        a = rt::event_create();
+        b = rt::event_create();
+    }
+    ~Timer() {
+        rt::event_destroy(a);
+        rt::event_destroy(b);
+    }
+    void start() { rt::event_record(a, st); }
+    void stop() { rt::event_record(b, st); }
+    double ms() { return rt::event_ms(a, b); }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ contexts
+
+struct ScoreContext {
+    Index* ix = nullptr;
+    rt::stream_t st;
+    rt::event_t ev_call0, ev_call1, ev_k0, ev_k1;
+    // cell buffers (device, SoA in the layout of Scores.java) and their host mirrors
+    uint64_t cap = 0;
+    rt::DevBuf<float> d_score, d_perc, d_trperc;
+    rt::DevBuf<int32_t> d_row, d_col, d_g1, d_g2;
+    rt::DevBuf<uint32_t> d_bh, d_colmax;
+    rt::DevBuf<unsigned long long> d_counters;  // 8
+    rt::DevBuf<uint32_t> d_cursors;             // 16
+    rt::DevBuf<uint2> d_rows, d_ovf;
+    rt::DevBuf<uint32_t> d_dense;
+    rt::PinBuf<unsigned long long> h_counters;
+    rt::PinBuf<uint2> h_rows;
+    rt::PinBuf<float> h_score, h_perc, h_trperc, h_bh, h_colmax;
+    rt::PinBuf<int32_t> h_row, h_col, h_g1, h_g2, h_map;
+    pd_score_stats stats;
+
+    explicit ScoreContext(Index* i) : ix(i) {
+        st = rt::stream_create();
+        ev_call0 = rt::event_create();
+        ev_call1 = rt::event_create();
+        ev_k0 = rt::event_create();
+        ev_k1 = rt::event_create();
+        d_counters.alloc(8);
+        d_cursors.alloc(16);
+        h_counters.ensure(8);
+        memset(&stats, 0, sizeof(stats));
+    }
+    ~ScoreContext() {
+        rt::event_destroy(ev_call0);
+        rt::event_destroy(ev_call1);
+        rt::event_destroy(ev_k0);
+        rt::event_destroy(ev_k1);
+        rt::stream_destroy(st);
+    }
+    void ensure_cells(uint64_t n) {
+        if (n <= cap) return;
+        d_score.alloc(n); d_perc.alloc(n); d_trperc.alloc(n);
+        d_row.alloc(n); d_col.alloc(n); d_g1.alloc(n); d_g2.alloc(n);
+        cap = n;
+    }
+};
+
+Index::~Index() {
+    for (ScoreContext* c : all_ctx) delete c;
+}
+
+ScoreContext* Index::acquire() {
+    std::unique_lock<std::mutex> lk(mu);
+    const size_t limit = opt.contexts > 0 ? (size_t)opt.contexts : 2;
+    for (;;) {
+        if (!free_ctx.empty()) {
+            ScoreContext* c = free_ctx.back();
+            free_ctx.pop_back();
+            return c;
+        }
+        if (all_ctx.size() < limit) {
+            ScoreContext* c = new ScoreContext(this);
+            all_ctx.push_back(c);
+            return c;
+        }
+        cv.wait(lk);
+    }
+}
+
+void Index::release(ScoreContext* c) {
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        free_ctx.push_back(c);
+    }
+    cv.notify_one();
+}
+
+// ------------------------------------------------------------------------------------------------ build
+
+void Index::build(const uint8_t* residues, bool residues_on_device, const uint64_t* offsets, const uint32_t* genome_ids,
+                  uint32_t S, int32_t k, const pd_options* o) {
+    memset(&info, 0, sizeof(info));
+    memset(&opt, 0, sizeof(opt));
+    opt.device = -1;
+    if (o) opt = *o;
+    if (k <= 0) throw Error(PD_ERR_INVALID, "K value must be greater than 0.");  // library.cpp:90-93
+    if (!offsets || (!genome_ids && S) || (!residues && S && offsets[S] != offsets[0]))
+        throw Error(PD_ERR_INVALID, "null input pointer");
+    if (rt::device_count() <= 0) throw Error(PD_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU path");
+    if (opt.device >= 0) rt::set_device(opt.device);
+    device = rt::current_device();
+    sms = rt::sm_count();
+    smem_optin = rt::max_optin_smem();
+
+    if (offsets[0] != 0) throw Error(PD_ERR_INVALID, "offsets[0] must be 0");
+    const uint64_t total = offsets[S];
+    kseq.assign(S, 0);
+    genome_of.assign(genome_ids, genome_ids + S);
+    std::vector<uint64_t> key_off((size_t)S + 1, 0);
+    uint64_t N = 0;
+    uint32_t G = 0, max_kseq = 0;
+    for (uint32_t s = 0; s < S; s++) {
+        if (offsets[s + 1] < offsets[s]) throw Error(PD_ERR_INVALID, "offsets must be ascending");
+        const uint64_t len = offsets[s + 1] - offsets[s];
+        if (len >= (1ull << 20)) throw Error(PD_ERR_UNSUPPORTED, "a gene of 2^20 or more residues");
+        const int64_t kl = (int64_t)len - k + 1;  // library.cpp:250
+        kseq[s] = kl > 0 ? (uint32_t)kl : 0;
+        max_kseq = std::max(max_kseq, kseq[s]);
+        key_off[s] = N;
+        N += kseq[s];
+        G = std::max(G, genome_ids[s] + 1);  // library.cpp:242
+    }
+    key_off[S] = N;
+    if (N >= (1ull << 31)) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more k-mers (the reference's own int index limit)");
+    info.S = S;
+    info.G = G;
+    info.k = k;
+    info.N = N;
+    info.max_kseq = max_kseq;
+    thr = 1.0f / (2.0f * (float)k);
+
+    // genes of each genome in input order (genome_sequences, library.cpp:245)
+    genome_ptr.assign((size_t)G + 1, 0);
+    for (uint32_t s = 0; s < S; s++) genome_ptr[genome_ids[s] + 1]++;
+    for (uint32_t g = 0; g < G; g++) genome_ptr[g + 1] += genome_ptr[g];
+    genome_rows.assign(S, 0);
+    {
+        std::vector<uint32_t> cur(genome_ptr.begin(), genome_ptr.end() - (G ? 1 : 0));
+        for (uint32_t s = 0; s < S; s++) genome_rows[cur[genome_ids[s]]++] = s;
+    }
+    visited.assign(S, 0);
+    row_multi.assign(S, 0);
+
+    rt::stream_t st = rt::stream_create();
+    uint64_t launches = 0;
+    Timer t_all(st), t_h2d(st), t_hist(st), t_enc(st), t_sort(st), t_grp(st), t_fwd(st);
+    t_all.start();
+
+    // ---- residues to HBM
+    rt::DevBuf<uint8_t> d_res_own;
+    const uint8_t* d_res = residues;
+    t_h2d.start();
+    if (!residues_on_device) {
+        d_res_own.alloc(total + 16);
+        rt::h2d(d_res_own.p, residues, total, st);
+        d_res = d_res_own.p;
+    }
+    rt::DevBuf<uint64_t> d_gene_off((size_t)S + 1), d_key_off((size_t)S + 1);
+    rt::h2d(d_gene_off.p, offsets, sizeof(uint64_t) * ((size_t)S + 1), st);
+    rt::h2d(d_key_off.p, key_off.data(), sizeof(uint64_t) * ((size_t)S + 1), st);
+    {
+        std::vector<uint2> m(S);
+        for (uint32_t s = 0; s < S; s++) m[s] = make_uint2(kseq[s], genome_ids[s]);
+        meta.alloc(std::max<size_t>(S, 1));
+        rt::h2d(meta.p, m.data(), sizeof(uint2) * S, st);
+        rt::sync(st);  // m goes out of scope
+    }
+    t_h2d.stop();
+
+    // ---- alphabet (library.cpp:216-230, 96-100)
+    t_hist.start();
+    rt::DevBuf<unsigned long long> d_hist(256);
+    rt::zero(d_hist.p, 256 * sizeof(unsigned long long), st);
+    if (total) {
+        unsigned grid = std::min<uint64_t>((uint64_t)sms * 8, (total + 4095) / 4096);
+        PD_LAUNCH(ik::byte_hist_kernel, std::max(1u, grid), 256, 0, st, d_res, total, d_hist.p);
+        launches++;
+    }
+    unsigned long long h_hist[256];
+    rt::d2h(h_hist, d_hist.p, sizeof(h_hist), st);
+    rt::sync(st);
+    t_hist.stop();
+    ik::ValTable vt;
+    memset(&vt, 0, sizeof(vt));
+    uint32_t base = 0;
+    for (int b = 0; b < 256; b++)
+        if (h_hist[b]) vt.v[b] = (uint8_t)base++;
+    info.base = base;
+
+    // base^k must be exactly representable; the reference would switch to its Rabin hash (library.cpp:103-119)
+    unsigned __int128 pw = 1;
+    for (int i = 0; i < k; i++) {
+        pw *= (base ? base : 1);
+        if (pw >> 63) throw Error(PD_ERR_UNSUPPORTED, "base^k >= 2^63: the reference's hash fallback is out of scope");
+    }
+    const int rank_bits = std::max(1, bits_for((uint64_t)pw - 1));
+    const int seq_bits = std::max(1, bits_for(S ? (uint64_t)S - 1 : 0));
+    if (rank_bits + seq_bits > 64) throw Error(PD_ERR_UNSUPPORTED, "k-mer rank and gene id do not fit one 64-bit sort key");
+    info.rank_bits = rank_bits;
+    info.seq_bits = seq_bits;
+
+    fwd_ptr.alloc((size_t)S + 1);
+    rt::zero(fwd_ptr.p, sizeof(uint32_t) * ((size_t)S + 1), st);
+
+    if (N > 0) {
+        // ---- encode (library.cpp:234-265)
+        t_enc.start();
+        rt::DevBuf<uint64_t> keys_a(N), keys_b(N);
+        {
+            unsigned grid = std::min<uint64_t>((uint64_t)sms * 16, ((uint64_t)S + 7) / 8);
+            PD_LAUNCH(ik::encode_kernel, std::max(1u, grid), 256, 0, st, d_res, (const uint64_t*)d_gene_off.p,
+                      (const uint64_t*)d_key_off.p, S, (int)k, base, seq_bits, vt, keys_a.p);
+            launches++;
+        }
+        t_enc.stop();
+        d_res_own.release();  // stream-ordered free happens after the kernel (cudaFree synchronises)
+
+        // ---- sort by rank; stability keeps genes ascending inside a rank (library.cpp:270-278)
+        t_sort.start();
+        rt::DevBuf<uint32_t> sort_tmp(prims::radix_tmp_words(N) + 16);
+        uint64_t* sorted = prims::radix_sort_u64(keys_a.p, keys_b.p, N, seq_bits, seq_bits + rank_bits, sort_tmp.p, st, &launches);
+        t_sort.stop();
+
+        // ---- count dedup (library.cpp:280-287) and rank groups incl. the tail merge (library.cpp:297-306)
+        t_grp.start();
+        rt::DevBuf<uint32_t>& scratch = sort_tmp;
+        rt::DevBuf<uint32_t> d_total(4);
+        uint32_t U = 0, n_groups = 0;
+        rt::DevBuf<uint32_t> ent_pos;
+        {
+            rt::DevBuf<uint32_t> flags(N);
+            scratch.ensure(prims::scan_tmp_words(N) + 16);
+            PD_LAUNCH(ik::head_flag_kernel, blocks_for(N), 256, 0, st, (const uint64_t*)sorted, N, flags.p);
+            prims::exclusive_scan_u32(flags.p, flags.p, N, scratch.p, d_total.p, st, &launches);
+            rt::d2h(&U, d_total.p, sizeof(uint32_t), st);
+            rt::sync(st);
+            ent_pos.alloc(U);
+            PD_LAUNCH(ik::head_scatter_kernel, blocks_for(N), 256, 0, st, (const uint64_t*)sorted, N, (const uint32_t*)flags.p, ent_pos.p);
+            launches += 2;
+            rt::sync(st);
+        }
+        info.U = U;
+        post.alloc(U);
+        rt::DevBuf<uint32_t> rflag(U);
+        if (opt.keep_sorted) ent_rank.alloc(U);
+        PD_LAUNCH(ik::entries_kernel, blocks_for(U), 256, 0, st, (const uint64_t*)sorted, (const uint32_t*)ent_pos.p, U, N, seq_bits,
+                  post.p, rflag.p, opt.keep_sorted ? ent_rank.p : (uint64_t*)nullptr);
+        launches++;
+        rt::DevBuf<uint32_t> gexcl(U);
+        prims::exclusive_scan_u32(rflag.p, gexcl.p, U, scratch.p, d_total.p, st, &launches);
+        rt::d2h(&n_groups, d_total.p, sizeof(uint32_t), st);
+        rt::sync(st);
+        keys_a.release();
+        keys_b.release();
+        ent_pos.release();
+        info.groups = n_groups;
+        grp_head.alloc((size_t)n_groups + 1);
+        ent_gid.alloc(U);
+        PD_LAUNCH(ik::group_heads_kernel, blocks_for(U), 256, 0, st, (const uint32_t*)rflag.p, (const uint32_t*)gexcl.p, U, grp_head.p,
+                  ent_gid.p);
+        launches++;
+        rt::h2d(grp_head.p + n_groups, &U, sizeof(uint32_t), st);
+        t_grp.stop();
+
+        // ---- forward lists and the cost model (library.cpp:308-330)
+        t_fwd.start();
+        rt::DevBuf<uint32_t>& sflag = rflag;   // reuse
+        rt::DevBuf<uint32_t>& sexcl = gexcl;   // reuse
+        rt::DevBuf<uint32_t> gene_cnt((size_t)S + 1);
+        rt::DevBuf<unsigned long long> d_visited(S);
+        rt::DevBuf<uint8_t> grp_multi((size_t)n_groups + 1), d_row_multi(S);
+        rt::zero(gene_cnt.p, sizeof(uint32_t) * ((size_t)S + 1), st);
+        rt::zero(d_visited.p, sizeof(unsigned long long) * S, st);
+        rt::zero(grp_multi.p, (size_t)n_groups + 1, st);
+        rt::zero(d_row_multi.p, S, st);
+        PD_LAUNCH(ik::shared_mark_kernel, blocks_for(U), 256, 0, st, (const uint2*)post.p, (const uint32_t*)ent_gid.p,
+                  (const uint32_t*)grp_head.p, U, sflag.p, gene_cnt.p, d_visited.p, grp_multi.p);
+        launches++;
+        prims::exclusive_scan_u32(sflag.p, sexcl.p, U, scratch.p, d_total.p, st, &launches);
+        uint32_t R = 0;
+        rt::d2h(&R, d_total.p, sizeof(uint32_t), st);
+        rt::sync(st);
+        info.R = R;
+        scratch.ensure(prims::scan_tmp_words((uint64_t)S + 1) + 16);
+        prims::exclusive_scan_u32(gene_cnt.p, fwd_ptr.p, (uint64_t)S + 1, scratch.p, nullptr, st, &launches);
+        fwd.alloc(std::max<size_t>(R, 1));
+        fwd_cnt.alloc(std::max<size_t>(R, 1));
+        if (R) {
+            rt::DevBuf<uint64_t> fk_a(R), fk_b(R);
+            PD_LAUNCH(ik::fwd_keys_kernel, blocks_for(U), 256, 0, st, (const uint2*)post.p, (const uint32_t*)sflag.p,
+                      (const uint32_t*)sexcl.p, U, fk_a.p);
+            launches++;
+            scratch.ensure(prims::radix_tmp_words(R) + 16);
+            uint64_t* fsorted = prims::radix_sort_u64(fk_a.p, fk_b.p, R, 32, 32 + seq_bits, scratch.p, st, &launches);
+            PD_LAUNCH(ik::fwd_fill_kernel, blocks_for(R), 256, 0, st, (const uint64_t*)fsorted, R, (const uint2*)post.p,
+                      (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, (const uint8_t*)grp_multi.p, fwd.p, fwd_cnt.p,
+                      d_row_multi.p);
+            launches++;
+            rt::sync(st);
+        }
+        static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
+        rt::d2h(visited.data(), d_visited.p, sizeof(uint64_t) * S, st);
+        rt::d2h(row_multi.data(), d_row_multi.p, S, st);
+        rt::sync(st);
+        t_fwd.stop();
+        if (!opt.keep_sorted) {
+            ent_gid.release();
+            grp_head.release();
+        }
+    } else {
+        post.alloc(1);
+        fwd.alloc(1);
+        fwd_cnt.alloc(1);
+    }
+    t_all.stop();
+    rt::sync(st);
+
+    uint64_t lookups = 0;
+    for (uint32_t s = 0; s < S; s++) lookups += visited[s];
+    info.lookups = lookups;
+    // lanes per posting list: largest power of two <= mean list length seen per forward entry, in [4, 32]
+    {
+        double mean = info.R ? (double)lookups / (double)info.R : 1.0;
+        uint32_t gs = 2;
+        while (gs < 5 && (double)(2u << gs) <= mean) gs++;
+        gshift = gs;
+        const char* e = getenv("PD_GSHIFT");
+        if (e && *e) gshift = (uint32_t)std::min(5, std::max(0, atoi(e)));
+    }
+    info.build_ms[0] = total ? t_hist.ms() : 0;
+    if (N) {
+        info.build_ms[1] = t_enc.ms();
+        info.build_ms[2] = t_sort.ms();
+        info.build_ms[3] = t_grp.ms();
+        info.build_ms[4] = t_fwd.ms();
+    }
+    info.build_ms[5] = t_all.ms();
+    info.build_ms[6] = t_h2d.ms();
+    info.build_ms[7] = (double)launches;
+    rt::stream_destroy(st);
+
+    if (opt.verbose) {
+        // the reference's cost report (library.cpp:347-370); "Total cost" is the work-unit ground truth
+        printf("------------\nCOMPUTATIONAL COSTS: \nTotal cost: %llu lookups\nLinear ratio: %g\n", (unsigned long long)lookups,
+               N ? (double)((float)lookups / (float)N) : 0.0);
+        printf("Index: %u genes, %u genomes, k=%d, base=%u, %llu k-mers, %llu postings, %llu shared (gene,k-mer) pairs\n", S, G, k, base,
+               (unsigned long long)N, (unsigned long long)info.U, (unsigned long long)info.R);
+        printf("------------\n\n");
+        fflush(stdout);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ scoring
+
+namespace {
+
+struct Level {
+    size_t smem;
+};
+
+// shared-memory budget of the three table levels
+inline void level_smem(const Index& ix, size_t out[3]) {
+    size_t l1 = 64 * 1024;
+    if (ix.opt.hash_log2 > 0) l1 = (size_t)8 << ix.opt.hash_log2;
+    size_t top = ix.smem_optin > 4096 ? ix.smem_optin - 2048 : 46 * 1024;
+    if (const char* e = getenv("PD_SMEM_TOP")) {  // tests: shrink the largest table to force the dense path
+        size_t v = (size_t)atoll(e);
+        if (v >= 64) top = std::min(top, v);
+    }
+    l1 = std::min(l1, top);
+    out[0] = std::min<size_t>(16 * 1024, l1);
+    out[1] = l1;
+    out[2] = std::max(l1, std::min<size_t>(192 * 1024, top));
+}
+
+struct RowLists {
+    // 0: unit L0, 1: multi L0, 2: unit L1, 3: multi L1
+    uint32_t begin[5];
+};
+
+template <bool MULTI>
+void launch_rows(ScoreContext& c, sk::ScoreArgs a, size_t smem, int cursor_id) {
+    Index& ix = *c.ix;
+    if (a.n_rows == 0) return;
+    a.slots = (uint32_t)(smem / (MULTI ? 16 : 8));
+    a.cursor = c.d_cursors.p + cursor_id;
+    rt::allow_smem(sk::score_rows_kernel<MULTI>, smem);
+    int occ = rt::occupancy(sk::score_rows_kernel<MULTI>, sk::kScoreThreads, smem);
+    unsigned grid = (unsigned)std::min<uint64_t>(a.n_rows, (uint64_t)ix.sms * std::max(1, occ));
+    PD_LAUNCH(sk::score_rows_kernel<MULTI>, grid, sk::kScoreThreads, smem, c.st, a);
+    c.stats.launches++;
+}
+
+}  // namespace
+
+// Scores the `n` (gene, bh_row) pairs of h_rows (already classified into the four lists of `rl`).  Returns the number
+// of non-zero cells; cells beyond c.cap are counted but not stored (caller grows and re-runs).
+static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32_t* d_bh, uint32_t* d_colmax, uint64_t* pairs) {
+    Index& ix = *c.ix;
+    size_t lv[3];
+    level_smem(ix, lv);
+    rt::zero(c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
+    rt::zero(c.d_cursors.p, 16 * sizeof(uint32_t), c.st);
+    c.d_rows.ensure(n);
+    c.d_ovf.ensure((size_t)4 * n);
+    rt::h2d(c.d_rows.p, c.h_rows.p, sizeof(uint2) * n, c.st);
+
+    sk::ScoreArgs a;
+    memset(&a, 0, sizeof(a));
+    a.post = ix.post.p; a.fwd = ix.fwd.p; a.fwd_cnt = ix.fwd_cnt.p; a.fwd_ptr = ix.fwd_ptr.p; a.meta = ix.meta.p;
+    a.G = ix.info.G; a.thr = ix.thr; a.gshift = ix.gshift;
+    a.o_score = c.d_score.p; a.o_perc = c.d_perc.p; a.o_trperc = c.d_trperc.p;
+    a.o_row = c.d_row.p; a.o_col = c.d_col.p; a.o_g1 = c.d_g1.p; a.o_g2 = c.d_g2.p;
+    a.cell_cap = c.cap;
+    a.n_cells = c.d_counters.p + 0;
+    a.n_pairs = c.d_counters.p + 1;
+    a.bh = d_bh;
+    a.colmax = d_colmax;
+
+    rt::event_record(c.ev_k0, c.st);
+    for (int list = 0; list < 4; list++) {
+        sk::ScoreArgs b = a;
+        b.rows = c.d_rows.p + rl.begin[list];
+        b.n_rows = rl.begin[list + 1] - rl.begin[list];
+        const bool multi = list & 1;
+        const int level = list >> 1;
+        b.overflow_rows = c.d_ovf.p + (size_t)(multi ? 1 : 0) * n;
+        b.n_overflow = c.d_counters.p + 2 + (multi ? 1 : 0);
+        if (multi) launch_rows<true>(c, b, lv[level], list);
+        else launch_rows<false>(c, b, lv[level], list);
+    }
+    rt::d2h(c.h_counters.p, c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
+    rt::sync(c.st);
+    // level 2: rows that overflowed the level-1 table
+    if (c.h_counters.p[2] || c.h_counters.p[3]) {
+        for (int multi = 0; multi < 2; multi++) {
+            sk::ScoreArgs b = a;
+            b.rows = c.d_ovf.p + (size_t)multi * n;
+            b.n_rows = (uint32_t)c.h_counters.p[2 + multi];
+            b.overflow_rows = c.d_ovf.p + (size_t)(2 + multi) * n;
+            b.n_overflow = c.d_counters.p + 4 + multi;
+            if (multi) launch_rows<true>(c, b, lv[2], 4 + multi);
+            else launch_rows<false>(c, b, lv[2], 4 + multi);
+        }
+        rt::d2h(c.h_counters.p, c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
+        rt::sync(c.st);
+        // last resort: dense global accumulators
+        for (int multi = 0; multi < 2; multi++) {
+            const uint32_t nr = (uint32_t)c.h_counters.p[4 + multi];
+            if (!nr) continue;
+            const unsigned grid = std::min<unsigned>(nr, 8);
+            const size_t words = (size_t)grid * 4 * ix.info.S;
+            if (c.d_dense.n < words) {
+                c.d_dense.alloc(words);
+                rt::zero(c.d_dense.p, words * sizeof(uint32_t), c.st);
+            }
+            sk::ScoreArgs b = a;
+            b.rows = c.d_ovf.p + (size_t)(2 + multi) * n;
+            b.n_rows = nr;
+            b.cursor = c.d_cursors.p + 8 + multi;
+            sk::DenseArgs d;
+            d.S = ix.info.S;
+            d.acc = c.d_dense.p;
+            PD_LAUNCH(sk::score_rows_dense_kernel, grid, sk::kScoreThreads, 0, c.st, b, d);
+            c.stats.launches++;
+            c.stats.fallback_rows += nr;
+        }
+        rt::d2h(c.h_counters.p, c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
+    }
+    rt::event_record(c.ev_k1, c.st);
+    rt::sync(c.st);
+    c.stats.kernel_ms += rt::event_ms(c.ev_k0, c.ev_k1);
+    *pairs = c.h_counters.p[1];
+    return c.h_counters.p[0];
+}
+
+// Classifies rows into (unit/multi) x (level 0/1) lists inside c.h_rows; `gene_at(i)` and bh row i.
+template <class F>
+static RowLists classify_rows(ScoreContext& c, uint32_t n, F gene_at, uint64_t* lookups) {
+    Index& ix = *c.ix;
+    size_t lv[3];
+    level_smem(ix, lv);
+    c.h_rows.ensure(std::max<uint32_t>(n, 1));
+    uint32_t cnt[4] = {0, 0, 0, 0};
+    const uint64_t cap0_unit = (uint64_t)(lv[0] / 8) * 3 / 4, cap0_multi = (uint64_t)(lv[0] / 16) * 3 / 4;
+    auto cls = [&](uint32_t g) {
+        const int multi = ix.row_multi[g] ? 1 : 0;
+        const uint64_t bound = std::min<uint64_t>(ix.visited[g], ix.info.S);
+        const int level = bound <= (multi ? cap0_multi : cap0_unit) ? 0 : 1;
+        return level * 2 + multi;
+    };
+    uint64_t lk = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t g = gene_at(i);
+        cnt[cls(g)]++;
+        lk += ix.visited[g];
+    }
+    RowLists rl;
+    rl.begin[0] = 0;
+    for (int l = 0; l < 4; l++) rl.begin[l + 1] = rl.begin[l] + cnt[l];
+    uint32_t cur[4] = {rl.begin[0], rl.begin[1], rl.begin[2], rl.begin[3]};
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t g = gene_at(i);
+        c.h_rows.p[cur[cls(g)]++] = make_uint2(g, i);
+    }
+    *lookups = lk;
+    return rl;
+}
+
+void Index::compute_scores(uint32_t genome, pd_scores* out) {
+    if (genome >= info.G) throw Error(PD_ERR_INVALID, "unknown genome");
+    rt::set_device(device);
+    ScoreContext* cp = acquire();
+    ScoreContext& c = *cp;
+    try {
+        memset(&c.stats, 0, sizeof(c.stats));
+        const uint32_t S = info.S, G = info.G;
+        const uint32_t r0 = genome_ptr[genome], rows = genome_ptr[genome + 1] - r0;
+        rt::event_record(c.ev_call0, c.st);
+        uint64_t lookups = 0;
+        RowLists rl = classify_rows(c, rows, [&](uint32_t i) { return genome_rows[r0 + i]; }, &lookups);
+        c.d_bh.ensure(std::max<size_t>((size_t)rows * G, 1));
+        c.d_colmax.ensure(std::max<size_t>(S, 1));
+        if (c.cap == 0) c.ensure_cells(opt.cell_capacity ? opt.cell_capacity : std::max<uint64_t>(1u << 16, (uint64_t)rows * 256));
+        uint64_t cells = 0, pairs = 0;
+        for (int attempt = 0; attempt < 3; attempt++) {
+            rt::zero(c.d_bh.p, sizeof(uint32_t) * (size_t)rows * G, c.st);
+            rt::zero(c.d_colmax.p, sizeof(uint32_t) * S, c.st);
+            cells = rows ? run_rows(c, rl, rows, c.d_bh.p, c.d_colmax.p, &pairs) : 0;
+            if (cells <= c.cap) break;
+            c.ensure_cells(cells + cells / 8);
+        }
+        if (cells > c.cap) throw Error(PD_ERR_CUDA, "cell count unstable between passes");
+        if (cells > 0x7fffffffull) throw Error(PD_ERR_UNSUPPORTED, "more than 2^31 cells in one computeScores call");
+
+        const size_t nc = std::max<uint64_t>(cells, 1);
+        c.h_score.ensure(nc); c.h_perc.ensure(nc); c.h_trperc.ensure(nc);
+        c.h_row.ensure(nc); c.h_col.ensure(nc); c.h_g1.ensure(nc); c.h_g2.ensure(nc);
+        c.h_bh.ensure(std::max<size_t>((size_t)rows * G, 1));
+        c.h_colmax.ensure(std::max<size_t>(S, 1));
+        c.h_map.ensure(std::max<size_t>(S, 1));
+        rt::d2h(c.h_score.p, c.d_score.p, sizeof(float) * cells, c.st);
+        rt::d2h(c.h_perc.p, c.d_perc.p, sizeof(float) * cells, c.st);
+        rt::d2h(c.h_trperc.p, c.d_trperc.p, sizeof(float) * cells, c.st);
+        rt::d2h(c.h_row.p, c.d_row.p, sizeof(int32_t) * cells, c.st);
+        rt::d2h(c.h_col.p, c.d_col.p, sizeof(int32_t) * cells, c.st);
+        rt::d2h(c.h_g1.p, c.d_g1.p, sizeof(int32_t) * cells, c.st);
+        rt::d2h(c.h_g2.p, c.d_g2.p, sizeof(int32_t) * cells, c.st);
+        rt::d2h(c.h_bh.p, c.d_bh.p, sizeof(float) * (size_t)rows * G, c.st);
+        rt::d2h(c.h_colmax.p, c.d_colmax.p, sizeof(float) * S, c.st);
+        rt::event_record(c.ev_call1, c.st);
+        // flat_map (library.cpp:428-432) while the copies run
+        for (uint32_t s = 0; s < S; s++) c.h_map.p[s] = INT32_MAX;
+        for (uint32_t i = 0; i < rows; i++) c.h_map.p[genome_rows[r0 + i]] = (int32_t)i;
+        rt::sync(c.st);
+        c.stats.total_ms = rt::event_ms(c.ev_call0, c.ev_call1);
+        c.stats.rows = rows;
+        c.stats.lookups = lookups;
+        c.stats.pairs = pairs;
+        c.stats.cells = cells;
+
+        out->scoresCount = (int32_t)cells;
+        out->S = (int32_t)S;
+        out->rows = (int32_t)rows;
+        out->G = (int32_t)G;
+        out->scores = c.h_score.p; out->percs = c.h_perc.p; out->tr_percs = c.h_trperc.p;
+        out->row = c.h_row.p; out->column = c.h_col.p;
+        out->first_seq_genome = c.h_g1.p; out->second_seq_genome = c.h_g2.p;
+        out->max_genome_score = c.h_bh.p;
+        out->max_genome_score_col = c.h_colmax.p;
+        out->scoresMaxMappings = c.h_map.p;
+        out->owner = cp;
+    } catch (...) {
+        release(cp);
+        throw;
+    }
+}
+
+void Index::score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_per_launch, float* d_best_hit, pd_score_stats* st_out) {
+    if (row_begin > row_end || row_end > info.S) throw Error(PD_ERR_INVALID, "bad row range");
+    rt::set_device(device);
+    ScoreContext* cp = acquire();
+    ScoreContext& c = *cp;
+    try {
+        memset(&c.stats, 0, sizeof(c.stats));
+        const uint32_t G = info.G;
+        const uint32_t total_rows = row_end - row_begin;
+        if (rows_per_launch == 0) rows_per_launch = 16384;
+        uint32_t* bh = reinterpret_cast<uint32_t*>(d_best_hit);
+        if (!bh) {
+            c.d_bh.ensure(std::max<size_t>((size_t)total_rows * G, 1));
+            bh = c.d_bh.p;
+        }
+        if (c.cap == 0) c.ensure_cells(opt.cell_capacity ? opt.cell_capacity : std::max<uint64_t>(1u << 20, (uint64_t)rows_per_launch * 256));
+        rt::event_record(c.ev_call0, c.st);
+        rt::zero(bh, sizeof(uint32_t) * (size_t)total_rows * G, c.st);
+        for (uint32_t b0 = row_begin; b0 < row_end; b0 += rows_per_launch) {
+            const uint32_t n = std::min(rows_per_launch, row_end - b0);
+            uint64_t lookups = 0, pairs = 0, cells = 0;
+            RowLists rl = classify_rows(c, n, [&](uint32_t i) { return b0 + i; }, &lookups);
+            uint32_t* bh_blk = bh + (size_t)(b0 - row_begin) * G;
+            for (int attempt = 0; attempt < 3; attempt++) {
+                cells = run_rows(c, rl, n, bh_blk, nullptr, &pairs);
+                if (cells <= c.cap) break;
+                c.ensure_cells(cells + cells / 8);
+            }
+            if (cells > c.cap) throw Error(PD_ERR_CUDA, "cell count unstable between passes");
+            c.stats.rows += n;
+            c.stats.lookups += lookups;
+            c.stats.pairs += pairs;
+            c.stats.cells += cells;
+        }
+        rt::event_record(c.ev_call1, c.st);
+        rt::sync(c.st);
+        c.stats.total_ms = rt::event_ms(c.ev_call0, c.ev_call1);
+        if (st_out) *st_out = c.stats;
+    } catch (...) {
+        release(cp);
+        throw;
+    }
+    release(cp);
+}
+
+void Index::partition_rows(uint32_t parts, bool snap, uint32_t* bounds) const {
+    if (parts == 0) throw Error(PD_ERR_INVALID, "parts must be > 0");
+    const uint32_t S = info.S;
+    // cost of a row = postings it visits, +1 so that empty rows still spread
+    std::vector<uint64_t> pre((size_t)S + 1, 0);
+    for (uint32_t s = 0; s < S; s++) pre[s + 1] = pre[s] + visited[s] + 1;
+    bool contiguous = true;  // genomes occupy contiguous gene ranges?
+    for (uint32_t s = 1; s < S && contiguous; s++)
+        if (genome_of[s] < genome_of[s - 1]) contiguous = false;
+    bounds[0] = 0;
+    for (uint32_t p = 1; p < parts; p++) {
+        const uint64_t target = pre[S] / parts * p + (pre[S] % parts) * p / parts;
+        uint32_t b = (uint32_t)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
+        b = std::min(b, S);
+        if (snap && contiguous && b > 0 && b < S) {
+            // move to the nearest genome boundary
+            uint32_t lo = b, hi = b;
+            while (lo > 0 && genome_of[lo - 1] == genome_of[lo]) lo--;
+            while (hi < S && genome_of[hi - 1] == genome_of[hi]) hi++;
+            b = (pre[b] - pre[lo] <= pre[hi] - pre[b]) ? lo : hi;
+        }
+        bounds[p] = std::max(b, bounds[p - 1]);
+    }
+    bounds[parts] = S;
+}
+
+void Index::context_stats(ScoreContext* c, pd_score_stats* out) { *out = c->stats; }
+
+void Index::entries(uint64_t* rank, uint32_t* seq, uint32_t* count, uint32_t* gs, uint32_t* gl) {
+    rt::set_device(device);
+    const uint32_t U = (uint32_t)info.U;
+    if (!U) return;
+    if ((rank || gs || gl) && !opt.keep_sorted) throw Error(PD_ERR_INVALID, "pd_entries: ranks and groups need pd_options.keep_sorted");
+    rt::stream_t st = rt::stream_create();
+    if (seq || count) {
+        std::vector<uint2> h(U);
+        rt::d2h(h.data(), post.p, sizeof(uint2) * U, st);
+        rt::sync(st);
+        for (uint32_t e = 0; e < U; e++) {
+            if (seq) seq[e] = h[e].x;
+            if (count) count[e] = h[e].y;
+        }
+    }
+    if (rank) {
+        rt::d2h(rank, ent_rank.p, sizeof(uint64_t) * U, st);
+        rt::sync(st);
+    }
+    if (gs || gl) {
+        rt::DevBuf<uint32_t> a(U), b(U);
+        PD_LAUNCH(ik::entry_groups_kernel, blocks_for(U), 256, 0, st, (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, U, a.p, b.p);
+        if (gs) rt::d2h(gs, a.p, sizeof(uint32_t) * U, st);
+        if (gl) rt::d2h(gl, b.p, sizeof(uint32_t) * U, st);
+        rt::sync(st);
+    }
+    rt::stream_destroy(st);
+}
+
+}  // namespace pd

@@ -1,0 +1,63 @@
+// Engine: owns the device-resident index (replaces `pair_info global_info`, reference ig/native/library.cpp:56-73)
+// and the per-call scoring contexts.  Everything here throws pd::Error; c_api.cu maps that to status codes.
+#pragma once
+
+#include <condition_variable>
+#include <mutex>
+#include <vector>
+
+#include "pandelos_b200.h"
+#include "pd_rt.h"
+
+namespace pd {
+
+struct ScoreContext;
+
+struct Index {
+    int device = 0;
+    pd_options opt;
+    pd_index_info info;
+    float thr = 0.f;            // 1/(2k) in float32 (library.cpp:499)
+    uint32_t gshift = 5;        // lanes per posting list = 1 << gshift, from the mean list length
+    int sms = 1;
+    size_t smem_optin = 0;
+
+    // device index
+    rt::DevBuf<uint2> post;
+    rt::DevBuf<uint2> fwd;
+    rt::DevBuf<uint32_t> fwd_cnt;
+    rt::DevBuf<uint32_t> fwd_ptr;
+    rt::DevBuf<uint2> meta;
+    rt::DevBuf<uint32_t> ent_gid;    // kept only with opt.keep_sorted
+    rt::DevBuf<uint32_t> grp_head;   // kept only with opt.keep_sorted
+    rt::DevBuf<uint64_t> ent_rank;   // kept only with opt.keep_sorted
+
+    // host mirrors (O(S))
+    std::vector<uint32_t> kseq;
+    std::vector<uint32_t> genome_of;
+    std::vector<uint64_t> visited;
+    std::vector<uint8_t> row_multi;
+    std::vector<uint32_t> genome_ptr;   // G+1
+    std::vector<uint32_t> genome_rows;  // genes grouped by genome, input order inside (genome_sequences, library.cpp:245)
+
+    // contexts
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<ScoreContext*> free_ctx;
+    std::vector<ScoreContext*> all_ctx;
+
+    ~Index();
+    void build(const uint8_t* residues, bool residues_on_device, const uint64_t* offsets, const uint32_t* genome_ids, uint32_t S,
+               int32_t k, const pd_options* o);
+    ScoreContext* acquire();
+    void release(ScoreContext* c);
+    void compute_scores(uint32_t genome, pd_scores* out);
+    void score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_per_launch, float* d_best_hit, pd_score_stats* st);
+    void partition_rows(uint32_t parts, bool snap, uint32_t* bounds) const;
+    static void context_stats(ScoreContext* c, pd_score_stats* out);
+    void entries(uint64_t* rank, uint32_t* seq, uint32_t* count, uint32_t* gs, uint32_t* gl);
+};
+
+void set_last_error(const std::string& s);
+
+}  // namespace pd

@@ -1,0 +1,188 @@
+// Index-construction kernels: the device counterpart of preprocessSequences (reference ig/native/library.cpp:189-335).
+//
+//   byte_hist_kernel      alphabet histogram                      library.cpp:216-228
+//   encode_kernel         positional k-mer rank -> 64-bit key     library.cpp:75-79,134-150,234-265
+//   (prims.cuh)           stable LSD radix sort on the rank bits   library.cpp:270-278
+//   head_scatter_kernel   run heads of equal (rank, seq)          library.cpp:280-287   (count dedup, part 1)
+//   entries_kernel        count per entry + rank-run heads         library.cpp:280-287, 297-306 (incl. the tail merge)
+//   group_*_kernel        rank groups -> inverted index CSR        library.cpp:297-335
+//   fwd_*_kernel          per-gene forward lists + cost model      library.cpp:314-328
+//
+// HBM layout produced (all SoA, 32-bit indices; the reference's 16-B kmer_rank / 24-B kmers_range records are gone):
+//   post[U]     uint2 (seq, count)     entries sorted by (rank, seq): the posting lists, group after group
+//   fwd[R]      uint2 (group start, group length) one per (gene, shared k-mer), genes ascending, ranks ascending
+//   fwd_cnt[R]  uint32 the gene's own multiplicity of that k-mer
+//   fwd_ptr[S+1], meta[S] = (kseq_len, genome), visited[S] (uint64), row_multi[S]
+#pragma once
+
+#include "pd_rt.h"
+#include "prims.cuh"
+
+namespace pd {
+namespace ik {
+
+struct ValTable {
+    uint8_t v[256];
+};
+
+// ---- alphabet histogram: 16-B loads, per-warp privatised shared histograms
+__global__ void __launch_bounds__(256) byte_hist_kernel(const uint8_t* __restrict__ res, uint64_t n,
+                                                         unsigned long long* __restrict__ hist) {
+    __shared__ uint32_t h[8][256];
+    const unsigned tid = threadIdx.x;
+    for (unsigned i = tid; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
+    __syncthreads();
+    uint32_t* mine = h[tid >> 5];
+    // head up to 16-B alignment, vector body, scalar tail
+    uint64_t head = (16 - (reinterpret_cast<uintptr_t>(res) & 15)) & 15;
+    if (head > n) head = n;
+    const uint64_t nvec = (n - head) / 16;
+    const uint4* vp = reinterpret_cast<const uint4*>(res + head);
+    const uint64_t gtid = (uint64_t)blockIdx.x * 256 + tid, gsz = (uint64_t)gridDim.x * 256;
+    for (uint64_t i = gtid; i < nvec; i += gsz) {
+        uint4 q = vp[i];
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            atomicAdd(&mine[w[j] & 0xFF], 1u);
+            atomicAdd(&mine[(w[j] >> 8) & 0xFF], 1u);
+            atomicAdd(&mine[(w[j] >> 16) & 0xFF], 1u);
+            atomicAdd(&mine[w[j] >> 24], 1u);
+        }
+    }
+    const uint64_t tail0 = head + nvec * 16;
+    for (uint64_t i = gtid; i < head; i += gsz) atomicAdd(&mine[res[i]], 1u);
+    for (uint64_t i = tail0 + gtid; i < n; i += gsz) atomicAdd(&mine[res[i]], 1u);
+    __syncthreads();
+    uint32_t s = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) s += h[w][tid];
+    if (s) atomicAdd(&hist[tid], (unsigned long long)s);
+}
+
+// ---- k-mer encode: one warp per gene, lanes stride over positions; key = rank << seq_bits | gene
+__global__ void __launch_bounds__(256) encode_kernel(const uint8_t* __restrict__ res, const uint64_t* __restrict__ gene_off,
+                                                      const uint64_t* __restrict__ key_off, uint32_t S, int k, uint32_t base,
+                                                      int seq_bits, ValTable vt, uint64_t* __restrict__ keys) {
+    __shared__ uint8_t val[256];
+    val[threadIdx.x] = vt.v[threadIdx.x];
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * 256u) >> 5;
+    for (uint32_t g = (blockIdx.x * 256u + threadIdx.x) >> 5; g < S; g += warps) {
+        const uint64_t ko = key_off[g];
+        const uint32_t nk = (uint32_t)(key_off[g + 1] - ko);
+        const uint8_t* p = res + gene_off[g];
+        for (uint32_t i = lane; i < nk; i += 32) {
+            uint64_t r = 0;
+            for (int j = 0; j < k; j++) r = r * base + val[p[i + j]];
+            keys[ko + i] = (r << seq_bits) | g;
+        }
+    }
+}
+
+// ---- dedup part 1: flags[i] = 1 iff key i starts a run of equal keys
+__global__ void __launch_bounds__(256) head_flag_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ flags) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+// ent_pos[e] = position in the sorted key list of the e-th distinct key
+__global__ void __launch_bounds__(256) head_scatter_kernel(const uint64_t* __restrict__ keys, uint64_t n,
+                                                            const uint32_t* __restrict__ excl, uint32_t* __restrict__ ent_pos) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n && (i == 0 || keys[i] != keys[i - 1])) ent_pos[excl[i]] = (uint32_t)i;
+}
+
+// per entry: posting (seq, count); rflag = 1 iff the entry opens a rank group.  The tail merge of the reference
+// (library.cpp:300-306: at the last entry the open run [start, i+1) is closed whatever its rank) means the last
+// entry never opens a group of its own unless it is the only entry.
+__global__ void __launch_bounds__(256) entries_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ent_pos,
+                                                       uint32_t U, uint64_t N, int seq_bits, uint2* __restrict__ post,
+                                                       uint32_t* __restrict__ rflag, uint64_t* __restrict__ ent_rank) {
+    const uint32_t e = blockIdx.x * 256u + threadIdx.x;
+    if (e >= U) return;
+    const uint32_t p = ent_pos[e];
+    const uint32_t pn = (e + 1 < U) ? ent_pos[e + 1] : (uint32_t)N;
+    const uint64_t key = keys[p];
+    const uint64_t rank = key >> seq_bits;
+    post[e] = make_uint2((uint32_t)(key & ((1ull << seq_bits) - 1ull)), pn - p);
+    uint32_t f;
+    if (e == 0)
+        f = 1;
+    else if (e == U - 1)
+        f = 0;
+    else
+        f = ((keys[ent_pos[e - 1]] >> seq_bits) != rank) ? 1u : 0u;
+    rflag[e] = f;
+    if (ent_rank) ent_rank[e] = rank;
+}
+
+// grp_head[g] = first entry of group g; ent_gid[e] = group of entry e
+__global__ void __launch_bounds__(256) group_heads_kernel(const uint32_t* __restrict__ rflag, const uint32_t* __restrict__ excl,
+                                                           uint32_t U, uint32_t* __restrict__ grp_head, uint32_t* __restrict__ ent_gid) {
+    const uint32_t e = blockIdx.x * 256u + threadIdx.x;
+    if (e >= U) return;
+    const uint32_t f = rflag[e];
+    const uint32_t g = excl[e] + f - 1u;
+    ent_gid[e] = g;
+    if (f) grp_head[g] = e;
+}
+
+// per entry in a shared group (length >= 2): mark it, count it for its gene, add the group length to the gene's
+// cost (computation_costs[].total_visited, library.cpp:327), and mark groups that hold any count > 1.
+__global__ void __launch_bounds__(256) shared_mark_kernel(const uint2* __restrict__ post, const uint32_t* __restrict__ ent_gid,
+                                                           const uint32_t* __restrict__ grp_head, uint32_t U,
+                                                           uint32_t* __restrict__ sflag, uint32_t* __restrict__ gene_cnt,
+                                                           unsigned long long* __restrict__ visited, uint8_t* __restrict__ grp_multi) {
+    const uint32_t e = blockIdx.x * 256u + threadIdx.x;
+    if (e >= U) return;
+    const uint32_t g = ent_gid[e];
+    const uint32_t gl = grp_head[g + 1] - grp_head[g];
+    const uint2 p = post[e];
+    const uint32_t s = gl >= 2 ? 1u : 0u;
+    sflag[e] = s;
+    if (s) {
+        atomicAdd(&gene_cnt[p.x], 1u);
+        atomicAdd(&visited[p.x], (unsigned long long)gl);
+        if (p.y > 1) grp_multi[g] = 1;
+    }
+}
+
+// compact the shared entries into sort keys (gene << 32 | entry)
+__global__ void __launch_bounds__(256) fwd_keys_kernel(const uint2* __restrict__ post, const uint32_t* __restrict__ sflag,
+                                                        const uint32_t* __restrict__ excl, uint32_t U, uint64_t* __restrict__ fkeys) {
+    const uint32_t e = blockIdx.x * 256u + threadIdx.x;
+    if (e >= U) return;
+    if (sflag[e]) fkeys[excl[e]] = ((uint64_t)post[e].x << 32) | e;
+}
+
+// forward lists from the gene-sorted keys
+__global__ void __launch_bounds__(256) fwd_fill_kernel(const uint64_t* __restrict__ fkeys, uint32_t R, const uint2* __restrict__ post,
+                                                        const uint32_t* __restrict__ ent_gid, const uint32_t* __restrict__ grp_head,
+                                                        const uint8_t* __restrict__ grp_multi, uint2* __restrict__ fwd,
+                                                        uint32_t* __restrict__ fwd_cnt, uint8_t* __restrict__ row_multi) {
+    const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+    if (j >= R) return;
+    const uint64_t fk = fkeys[j];
+    const uint32_t e = (uint32_t)fk, gene = (uint32_t)(fk >> 32);
+    const uint32_t g = ent_gid[e];
+    const uint32_t gs = grp_head[g];
+    fwd[j] = make_uint2(gs, grp_head[g + 1] - gs);
+    fwd_cnt[j] = post[e].y;
+    if (grp_multi[g]) row_multi[gene] = 1;
+}
+
+// per-entry group (start, length) for pd_entries (tests / diagnostics)
+__global__ void __launch_bounds__(256) entry_groups_kernel(const uint32_t* __restrict__ ent_gid, const uint32_t* __restrict__ grp_head,
+                                                            uint32_t U, uint32_t* __restrict__ gs_out, uint32_t* __restrict__ gl_out) {
+    const uint32_t e = blockIdx.x * 256u + threadIdx.x;
+    if (e >= U) return;
+    const uint32_t g = ent_gid[e];
+    const uint32_t gs = grp_head[g];
+    gs_out[e] = gs;
+    gl_out[e] = grp_head[g + 1] - gs;
+}
+
+}  // namespace ik
+}  // namespace pd

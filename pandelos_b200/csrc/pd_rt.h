@@ -1,0 +1,190 @@
+// Thin device-runtime vocabulary used by the engine: memory, copies, streams, events, launches.
+//
+// Product build (nvcc, sm_100a): plain CUDA runtime calls, every status checked; any failure throws pd::Error,
+// which the C ABI turns into an error code + message (there is no CPU path to fall back to).
+// PD_EMU build (g++, tests/emu only): the same vocabulary mapped onto host memory and the fiber-based SIMT logic
+// emulator in tests/emu/cuemu.h — test infrastructure for a GPU-less container, never shipped.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#ifdef PD_EMU
+#include "cuemu.h"
+#include <chrono>
+#else
+#include <cuda_runtime.h>
+#endif
+
+namespace pd {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+namespace rt {
+
+#ifndef PD_EMU
+
+#define PD_CUDA(call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            throw pd::Error(-3, std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" +  \
+                                    std::to_string(__LINE__) + ")");                                       \
+    } while (0)
+
+typedef cudaStream_t stream_t;
+typedef cudaEvent_t event_t;
+
+inline int device_count() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+inline void set_device(int d) { PD_CUDA(cudaSetDevice(d)); }
+inline int current_device() { int d = 0; PD_CUDA(cudaGetDevice(&d)); return d; }
+inline int sm_count() {
+    int d = current_device(), n = 0;
+    PD_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d));
+    return n;
+}
+inline size_t max_optin_smem() {
+    int d = current_device(), n = 0;
+    PD_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, d));
+    return static_cast<size_t>(n);
+}
+inline void* dmalloc(size_t n) { void* p = nullptr; PD_CUDA(cudaMalloc(&p, n ? n : 1)); return p; }
+inline void dfree(void* p) { if (p) cudaFree(p); }
+inline void* hmalloc(size_t n) { void* p = nullptr; PD_CUDA(cudaMallocHost(&p, n ? n : 1)); return p; }
+inline void hfree(void* p) { if (p) cudaFreeHost(p); }
+inline stream_t stream_create() { stream_t s; PD_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return s; }
+inline void stream_destroy(stream_t s) { cudaStreamDestroy(s); }
+inline void sync(stream_t s) { PD_CUDA(cudaStreamSynchronize(s)); }
+inline void h2d(void* d, const void* h, size_t n, stream_t s) { if (n) PD_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
+inline void d2h(void* h, const void* d, size_t n, stream_t s) { if (n) PD_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
+inline void d2d(void* dst, const void* src, size_t n, stream_t s) { if (n) PD_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s)); }
+inline void zero(void* d, size_t n, stream_t s) { if (n) PD_CUDA(cudaMemsetAsync(d, 0, n, s)); }
+inline void fill_byte(void* d, int v, size_t n, stream_t s) { if (n) PD_CUDA(cudaMemsetAsync(d, v, n, s)); }
+inline event_t event_create() { event_t e; PD_CUDA(cudaEventCreate(&e)); return e; }
+inline void event_destroy(event_t e) { cudaEventDestroy(e); }
+inline void event_record(event_t e, stream_t s) { PD_CUDA(cudaEventRecord(e, s)); }
+inline float event_ms(event_t a, event_t b) { float ms = 0; PD_CUDA(cudaEventSynchronize(b)); PD_CUDA(cudaEventElapsedTime(&ms, a, b)); return ms; }
+inline void check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw pd::Error(-3, std::string("launch ") + what + ": " + cudaGetErrorString(e));
+}
+template <class K>
+inline void allow_smem(K kern, size_t bytes) {
+    if (bytes > 48 * 1024) PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+}
+template <class K>
+inline int occupancy(K kern, int threads, size_t smem) {
+    int n = 0;
+    PD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem));
+    return n;
+}
+
+#define PD_LAUNCH(kern, grid, block, smem, stream, ...)              \
+    do {                                                             \
+        kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
+        pd::rt::check_launch(#kern);                                 \
+    } while (0)
+
+#define PD_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+
+#else  // ---------------------------------------------------------------- PD_EMU (tests only)
+
+typedef int stream_t;
+struct event_rec { std::chrono::steady_clock::time_point t; };
+typedef event_rec* event_t;
+
+inline int device_count() { return 1; }
+inline void set_device(int) {}
+inline int current_device() { return 0; }
+inline int sm_count() { return 2; }  // tiny grid: the emulator runs blocks one after another
+inline size_t max_optin_smem() { return 227 * 1024; }
+inline void* dmalloc(size_t n) {
+    void* p = malloc(n ? n : 1);
+    if (p) memset(p, 0xA5, n);  // device memory is not zero-initialised
+    return p;
+}
+inline void dfree(void* p) { free(p); }
+inline void* hmalloc(size_t n) { return malloc(n ? n : 1); }
+inline void hfree(void* p) { free(p); }
+inline stream_t stream_create() { return 0; }
+inline void stream_destroy(stream_t) {}
+inline void sync(stream_t) {}
+inline void h2d(void* d, const void* h, size_t n, stream_t) { if (n) memcpy(d, h, n); }
+inline void d2h(void* h, const void* d, size_t n, stream_t) { if (n) memcpy(h, d, n); }
+inline void d2d(void* dst, const void* src, size_t n, stream_t) { if (n) memmove(dst, src, n); }
+inline void zero(void* d, size_t n, stream_t) { if (n) memset(d, 0, n); }
+inline void fill_byte(void* d, int v, size_t n, stream_t) { if (n) memset(d, v, n); }
+inline event_t event_create() { return new event_rec; }
+inline void event_destroy(event_t e) { delete e; }
+inline void event_record(event_t e, stream_t) { e->t = std::chrono::steady_clock::now(); }
+inline float event_ms(event_t a, event_t b) { return std::chrono::duration<float, std::milli>(b->t - a->t).count(); }
+template <class K>
+inline void allow_smem(K, size_t) {}
+template <class K>
+inline int occupancy(K, int, size_t) { return 1; }
+
+template <class K, class... A>
+inline void emu_launch(K kern, dim3 grid, dim3 block, size_t smem, A... args) {
+    cuemu::launch(grid, block, smem, [=]() { kern(args...); });
+}
+
+#define PD_LAUNCH(kern, grid, block, smem, stream, ...)                              \
+    do {                                                                             \
+        (void)(stream);                                                              \
+        pd::rt::emu_launch(kern, dim3(grid), dim3(block), (smem), __VA_ARGS__);      \
+    } while (0)
+
+#define PD_DYNAMIC_SMEM(name) unsigned char* name = cuemu::dyn_smem()
+
+#endif
+
+// RAII device buffer
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) { release(); p = static_cast<T*>(dmalloc(count * sizeof(T))); n = count; }
+    void ensure(size_t count) { if (count > n) alloc(count); }
+    void release() { if (p) dfree(p); p = nullptr; n = 0; }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+template <class T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    PinBuf() {}
+    PinBuf(const PinBuf&) = delete;
+    PinBuf& operator=(const PinBuf&) = delete;
+    ~PinBuf() { release(); }
+    void ensure(size_t count) {
+        if (count > n) { release(); p = static_cast<T*>(hmalloc(count * sizeof(T))); n = count; }
+    }
+    void release() { if (p) hfree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace rt
+}  // namespace pd
