@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — the PanDelos Pangenes similarity hot path on B200, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
+
+A STEP is one pass of the hot path over the rank's share of one synthetic pan-genome (SURVEY.md §8d shapes):
+index build from residues already in HBM (k-mer encode, sort, dedup, groups, forward lists = preprocessSequences)
+followed by scoring of the rank's query genes against the whole index (computeScores: accumulate along posting
+lists, float32 Jaccard, best hits), cells left in HBM.  With N > 1 every rank holds the whole index (built
+redundantly, "built once and replicated") and scores its own block of query genomes; the best-hit slices are then
+all-gathered over NCCL.  Per-rank work is fixed as N grows (scaling "weak"): N = 8 covers the whole data set.
+
+metric  = candidate gene pairs scored per second (distinct (row, col != row) cells evaluated, library.cpp:493)
+e2e     = the same through the reference-facing C ABI with HOST buffers: pd_build from host residues, then one
+          pd_compute_scores per query genome with every Scores array copied back to pinned host memory.
+roofline= scoring kernels: algorithmic bytes / CUDA-event time of the kernels, vs measured HBM peak.
+cpu_baseline / --impl reference = the UNMODIFIED reference library (oracle/_ref, fake JNIEnv driver, thread pool
+          over genomes as Pangenes.java:54-66) on the box's host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_WORKLOAD = "scaleout1000"
+# genomes scored per rank (weak scaling); None = all genomes on every rank count once (N must be 1)
+QUERY_GENOMES = {"scaleout1000": 125}
+# genomes of the workload the CPU reference is timed on (bounded sample: ~10-30 s of host work)
+CPU_SAMPLE_GENOMES = {"scaleout1000": 12, "mycoplasma64": 64}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(name):
+    from pandelos_b200 import synth
+    t = time.time()
+    w = synth.shape(name)
+    k = synth.calculate_k(w)
+    log("[bench] workload %s: %d genes, %d genomes, %d residues, k=%d (%.1fs)" % (name, w.S, w.G, len(w.residues), k, time.time() - t))
+    return w, k
+
+
+def genome_bounds(w):
+    return np.searchsorted(w.genome_of, np.arange(w.G + 1), side="left").astype(np.int64)
+
+
+def cpu_reference_sample(w, k, name, threads):
+    """Times the unmodified reference on the first `n` genomes of the workload.  Returns dict or None."""
+    from oracle import refjni
+    if not refjni.available():
+        return None
+    n = min(CPU_SAMPLE_GENOMES.get(name, w.G), w.G)
+    sub = w.subset_genomes(n) if n < w.G else w
+    ref = refjni.RefJni()
+    t_pre = ref.preprocess(sub.residues, sub.offsets, sub.genome_of, k)
+    t_sc, cells = ref.compute_scores_pool(0, n, threads)
+    return {"sample": sub, "genomes": n, "preprocess_s": t_pre, "scores_s": t_sc, "cells": cells}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from pandelos_b200 import native
+    name = args.workload
+    w, k = make_workload(name)
+    threads = os.cpu_count() or 1
+    times = []
+    res = None
+    for i in range(args.warmup + args.steps):
+        res = cpu_reference_sample(w, k, name, threads)
+        if res is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this box"}))
+            return 0
+        if i >= args.warmup:
+            times.append(res["preprocess_s"] + res["scores_s"])
+    # pair count of the sample (denominator only) from the engine when a GPU is here, else from the C port
+    sub = res["sample"]
+    try:
+        pn = native.PangeneNative(k, native.PangeneIData(sub.residues, sub.offsets, sub.genome_of))
+        pairs = pn.score_partition_device(0, sub.S).pairs
+        lookups = pn.info.lookups
+        pn.close()
+    except Exception:
+        from oracle import cport
+        o = cport.OracleIndex(sub.residues, sub.offsets, sub.genome_of, k)
+        pairs = sum(o.candidate_pairs(g) for g in range(sub.G))
+        lookups = o.total_lookups
+    t = float(np.mean(times))
+    val = pairs / t
+    sample = "first %d of %d genomes of %s (%d genes, k=%d, %d lookups); preprocess 1 thread %.2fs + computeScores %d threads %.2fs" % (
+        res["genomes"], w.G, name, sub.S, k, lookups, res["preprocess_s"], threads, res["scores_s"])
+    out = {"impl": "reference", "metric": "gene-pair Jaccard scores/sec", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
+           "config": {"workload": name, "k": k, "genes": int(w.S), "genomes": int(w.G)},
+           "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "reference", "sample": sample},
+           "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--query-genomes", type=int, default=0, help="genomes scored per rank (0 = workload default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from pandelos_b200 import native
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    native.load()
+
+    name = args.workload
+    w, k = make_workload(name)
+    gb = genome_bounds(w)
+    q = args.query_genomes or QUERY_GENOMES.get(name) or w.G
+    q = min(q, w.G)
+    if world * q > w.G:
+        q = max(1, w.G // world)
+    g0, g1 = rank * q, (rank + 1) * q
+    row0, row1 = int(gb[g0]), int(gb[g1])
+    data = native.PangeneIData(w.residues, w.offsets, w.genome_of)
+
+    # residues resident in HBM before the timed region
+    res_host = torch.from_numpy(w.residues).pin_memory()
+    res_dev = res_host.to(dev, non_blocking=False)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    G = w.G
+    bh_local = torch.zeros((row1 - row0, G), dtype=torch.float32, device=dev)
+    bh_all = torch.zeros((world * (row1 - row0), G), dtype=torch.float32, device=dev) if world > 1 else None
+    if world > 1:
+        rows_all = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(rows_all, torch.tensor([row1 - row0], dtype=torch.int64, device=dev))
+        max_rows = int(max(int(x.item()) for x in rows_all))
+        bh_local = torch.zeros((max_rows, G), dtype=torch.float32, device=dev)   # padded to the largest slice
+        bh_all = torch.zeros((world * max_rows, G), dtype=torch.float32, device=dev)
+
+    def step():
+        pn = native.PangeneNative(k, data, device=local, residues_device_ptr=res_dev.data_ptr())
+        st = pn.score_partition_device(row0, row1, best_hit_ptr=bh_local.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(bh_all, bh_local)
+        return pn, st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        pn, st = step()
+        pn.close()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = build_ms = 0.0
+    launches = 0
+    ms_steps = []
+    info = None
+    for _ in range(args.steps):
+        flush.fill_(1)  # L2 flush between timed iterations
+        barrier()
+        ev0.record()
+        t0 = time.perf_counter()
+        pn, st = step()
+        ev1.record()
+        barrier()
+        ms_steps.append(max(ev0.elapsed_time(ev1), 0.0))
+        wall = (time.perf_counter() - t0) * 1e3
+        kernel_ms += st.kernel_ms
+        build_ms += pn.info.build_ms[5]
+        launches += int(st.launches + pn.info.build_ms[7])
+        info = pn.info
+        stats = st.as_dict()
+        pn.close()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = float(np.mean(ms_steps))
+    t = torch.tensor([ms, float(stats["pairs"]), float(stats["lookups"]), float(stats["cells"]), kernel_ms / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms = float(tmax[0].item())
+        pairs_all, lookups_all, cells_all = float(tsum[1].item()), float(tsum[2].item()), float(tsum[3].item())
+    else:
+        pairs_all, lookups_all, cells_all = float(stats["pairs"]), float(stats["lookups"]), float(stats["cells"])
+    value = pairs_all / (ms * 1e-3)
+
+    # ---- roofline of the scoring kernels on this rank (algorithmic bytes)
+    rows_n = row1 - row0
+    kms = kernel_ms / args.steps
+    # 8 B per posting visited + 8 B per forward entry + 28 B per emitted cell + best-hit table + gene metadata once
+    alg_bytes = 8.0 * stats["lookups"] + 8.0 * stats["fwd_entries"] + 28.0 * stats["cells"] + 4.0 * rows_n * G + 8.0 * info.S
+    peak, peak_kind = peaks()
+    achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "score_rows_kernel", "kernel_ms_per_step": kms, "peak_kind": peak_kind,
+                "lookups_per_s": stats["lookups"] / (kms * 1e-3) if kms > 0 else 0.0}
+
+    # ---- e2e through the C ABI with host buffers (this rank's query genomes), max over ranks
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, 2))
+        e2e_ms = []
+        d2h = h2d = 0
+        pairs_e = 0
+        for i in range(1 + e2e_steps):
+            barrier()
+            t0 = time.perf_counter()
+            pn = native.PangeneNative(k, data, device=local)
+            h2d = len(w.residues) + 8 * (w.S + 1) + 4 * w.S
+            d2h = 0
+            pairs_e = 0
+            for g in range(g0, g1):
+                stt, rel = pn.compute_scores_raw(g)
+                d2h += 28 * stt.scoresCount + 4 * stt.rows * stt.G + 8 * stt.S
+                ss = native.ScoreStats()
+                pn._L.pd_last_score_stats(stt, ss)
+                pairs_e += ss.pairs
+                rel()
+            barrier()
+            if i > 0:
+                e2e_ms.append((time.perf_counter() - t0) * 1e3)
+            pn.close()
+        te = torch.tensor([float(np.mean(e2e_ms)), float(pairs_e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tm = te.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ts = te.clone()
+            dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            e_ms, e_pairs = float(tm[0].item()), float(ts[1].item())
+        else:
+            e_ms, e_pairs = float(te[0].item()), float(te[1].item())
+        e2e = {"value": e_pairs / (e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e_ms}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        res = cpu_reference_sample(w, k, name, threads)
+        if res is not None:
+            sub = res["sample"]
+            pn = native.PangeneNative(k, native.PangeneIData(sub.residues, sub.offsets, sub.genome_of), device=local)
+            sp = pn.score_partition_device(0, sub.S)
+            tt = res["preprocess_s"] + res["scores_s"]
+            cpu = {"value": sp.pairs / tt, "unit": "pairs/s", "cores": threads, "kind": "reference",
+                   "sample": "first %d of %d genomes of %s (%d genes, k=%d, %d lookups): preprocess (1 thread) %.2fs + computeScores (%d threads) %.2fs; "
+                             "scoring only %.3g lookups/s" % (res["genomes"], w.G, name, sub.S, k, pn.info.lookups, res["preprocess_s"], threads,
+                                                               res["scores_s"], pn.info.lookups / max(res["scores_s"], 1e-9))}
+            pn.close()
+
+    if rank == 0:
+        out = {"metric": "gene-pair Jaccard scores/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "int32+f32", "data": "synthetic",
+               "config": {"workload": name, "k": int(k), "genes": int(w.S), "genomes": int(G), "kmers": int(info.N),
+                          "query_genomes_per_rank": int(q), "query_rows_per_rank": int(rows_n), "l2": "flushed between timed steps (256 MiB fill)",
+                          "step": "index build from HBM-resident residues + scoring of the rank's query rows" + (" + NCCL allgather of best-hit slices" if world > 1 else "")},
+               "lookups_per_s": lookups_all / (ms * 1e-3), "cells_per_step": cells_all, "pairs_per_step": pairs_all,
+               "build_ms_per_step": build_ms / args.steps, "score_kernel_ms_per_step": kms,
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

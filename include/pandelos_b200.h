@@ -91,6 +91,7 @@ typedef struct pd_score_stats {
     uint64_t cells;          /* non-zero cells emitted */
     uint64_t fallback_rows;  /* rows that overflowed the shared-memory accumulator and took the dense global path */
     uint64_t launches;       /* kernels launched */
+    uint64_t fwd_entries;    /* (row, shared k-mer) forward entries read */
     double kernel_ms;        /* CUDA-event time of the scoring kernels */
     double total_ms;         /* CUDA-event time of the whole call on its stream (memsets, kernels, copies) */
 } pd_score_stats;

@@ -86,7 +86,7 @@ def build_jni(force=False):
     """libnative.so = JNI shim linked against libpandelos_b200.so ($ORIGIN rpath). Skipped (prebuilt kept) without jni.h."""
     inc = jni_include_dirs()
     src = os.path.join(CSRC, "jni_shim.cpp")
-    if inc is None:
+    if inc is None or not os.path.exists(src):
         if not os.path.exists(JNI_LIB):
             sys.stderr.write("pandelos_b200.build: no jni.h (JAVA_HOME unset, reference absent); libnative.so not built\n")
         return JNI_LIB if os.path.exists(JNI_LIB) else None
@@ -101,6 +101,8 @@ def build_jni(force=False):
 def build_host(force=False):
     build_engine(force=False)
     hdir = os.path.join(CSRC, "host")
+    if not os.path.isdir(hdir):
+        return None
     srcs = [os.path.join(hdir, f) for f in sorted(os.listdir(hdir)) if f.endswith(".cpp")]
     if force or _stale(CLI_BIN, srcs + _sources(hdir, INCLUDE) + [ENGINE_LIB]):
         cmd = [CXX, "-std=c++17", "-O2", "-Wall", "-I", INCLUDE, "-I", hdir, "-o", CLI_BIN] + srcs + \

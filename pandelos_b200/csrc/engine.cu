@@ -180,6 +180,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     }
     visited.assign(S, 0);
     row_multi.assign(S, 0);
+    fwd_ptr_h.assign((size_t)S + 1, 0);
 
     rt::stream_t st = rt::stream_create();
     uint64_t launches = 0;
@@ -341,6 +342,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
         rt::d2h(visited.data(), d_visited.p, sizeof(uint64_t) * S, st);
         rt::d2h(row_multi.data(), d_row_multi.p, S, st);
+        rt::d2h(fwd_ptr_h.data(), fwd_ptr.p, sizeof(uint32_t) * ((size_t)S + 1), st);
         rt::sync(st);
         t_fwd.stop();
         if (!opt.keep_sorted) {
@@ -516,7 +518,7 @@ static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32
 
 // Classifies rows into (unit/multi) x (level 0/1) lists inside c.h_rows; `gene_at(i)` and bh row i.
 template <class F>
-static RowLists classify_rows(ScoreContext& c, uint32_t n, F gene_at, uint64_t* lookups) {
+static RowLists classify_rows(ScoreContext& c, uint32_t n, F gene_at, uint64_t* lookups, uint64_t* fwd_entries) {
     Index& ix = *c.ix;
     size_t lv[3];
     level_smem(ix, lv);
@@ -529,12 +531,14 @@ static RowLists classify_rows(ScoreContext& c, uint32_t n, F gene_at, uint64_t* 
         const int level = bound <= (multi ? cap0_multi : cap0_unit) ? 0 : 1;
         return level * 2 + multi;
     };
-    uint64_t lk = 0;
+    uint64_t lk = 0, fe = 0;
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t g = gene_at(i);
         cnt[cls(g)]++;
         lk += ix.visited[g];
+        fe += ix.fwd_ptr_h[g + 1] - ix.fwd_ptr_h[g];
     }
+    *fwd_entries = fe;
     RowLists rl;
     rl.begin[0] = 0;
     for (int l = 0; l < 4; l++) rl.begin[l + 1] = rl.begin[l] + cnt[l];
@@ -557,8 +561,8 @@ void Index::compute_scores(uint32_t genome, pd_scores* out) {
         const uint32_t S = info.S, G = info.G;
         const uint32_t r0 = genome_ptr[genome], rows = genome_ptr[genome + 1] - r0;
         rt::event_record(c.ev_call0, c.st);
-        uint64_t lookups = 0;
-        RowLists rl = classify_rows(c, rows, [&](uint32_t i) { return genome_rows[r0 + i]; }, &lookups);
+        uint64_t lookups = 0, fwd_entries = 0;
+        RowLists rl = classify_rows(c, rows, [&](uint32_t i) { return genome_rows[r0 + i]; }, &lookups, &fwd_entries);
         c.d_bh.ensure(std::max<size_t>((size_t)rows * G, 1));
         c.d_colmax.ensure(std::max<size_t>(S, 1));
         if (c.cap == 0) c.ensure_cells(opt.cell_capacity ? opt.cell_capacity : std::max<uint64_t>(1u << 16, (uint64_t)rows * 256));
@@ -596,6 +600,7 @@ void Index::compute_scores(uint32_t genome, pd_scores* out) {
         c.stats.total_ms = rt::event_ms(c.ev_call0, c.ev_call1);
         c.stats.rows = rows;
         c.stats.lookups = lookups;
+        c.stats.fwd_entries = fwd_entries;
         c.stats.pairs = pairs;
         c.stats.cells = cells;
 
@@ -636,8 +641,8 @@ void Index::score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_
         rt::zero(bh, sizeof(uint32_t) * (size_t)total_rows * G, c.st);
         for (uint32_t b0 = row_begin; b0 < row_end; b0 += rows_per_launch) {
             const uint32_t n = std::min(rows_per_launch, row_end - b0);
-            uint64_t lookups = 0, pairs = 0, cells = 0;
-            RowLists rl = classify_rows(c, n, [&](uint32_t i) { return b0 + i; }, &lookups);
+            uint64_t lookups = 0, pairs = 0, cells = 0, fwd_entries = 0;
+            RowLists rl = classify_rows(c, n, [&](uint32_t i) { return b0 + i; }, &lookups, &fwd_entries);
             uint32_t* bh_blk = bh + (size_t)(b0 - row_begin) * G;
             for (int attempt = 0; attempt < 3; attempt++) {
                 cells = run_rows(c, rl, n, bh_blk, nullptr, &pairs);
@@ -647,6 +652,7 @@ void Index::score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_
             if (cells > c.cap) throw Error(PD_ERR_CUDA, "cell count unstable between passes");
             c.stats.rows += n;
             c.stats.lookups += lookups;
+            c.stats.fwd_entries += fwd_entries;
             c.stats.pairs += pairs;
             c.stats.cells += cells;
         }

@@ -47,7 +47,7 @@ class ScoresStruct(C.Structure):
 
 class ScoreStats(C.Structure):
     _fields_ = [("rows", C.c_uint64), ("lookups", C.c_uint64), ("pairs", C.c_uint64), ("cells", C.c_uint64),
-                ("fallback_rows", C.c_uint64), ("launches", C.c_uint64), ("kernel_ms", C.c_double), ("total_ms", C.c_double)]
+                ("fallback_rows", C.c_uint64), ("launches", C.c_uint64), ("fwd_entries", C.c_uint64), ("kernel_ms", C.c_double), ("total_ms", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -60,6 +60,8 @@ _lib_path = None
 def load(path=None):
     """Loads the engine library.  There is no fallback: a missing library is an error."""
     global _lib, _lib_path
+    if path is None and _lib is not None:
+        return _lib
     path = path or os.environ.get("PANDELOS_B200_LIB") or ENGINE_LIB
     if _lib is not None and _lib_path == path:
         return _lib

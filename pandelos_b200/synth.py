@@ -129,8 +129,19 @@ def calculate_k(w):
     if total == 0:
         raise ValueError("empty input")
     counts = np.bincount(res, minlength=256)
-    _, first = np.unique(res, return_index=True)
-    order = res[np.sort(first)]
+    # alphabet in first-appearance order (the reference's dict insertion order); found from growing prefixes
+    present = set(np.flatnonzero(counts).tolist())
+    order, seen, pos, chunk = [], set(), 0, 1 << 16
+    while len(seen) < len(present):
+        part = res[pos:pos + chunk]
+        vals, first = np.unique(part, return_index=True)
+        for i in np.argsort(first):
+            b = int(vals[i])
+            if b not in seen:
+                seen.add(b)
+                order.append(b)
+        pos += chunk
+        chunk *= 4
     a = len(order)
     if a < 2:
         raise ValueError("alphabet of one letter: entropy is zero")

@@ -1,0 +1,146 @@
+"""GPU (-m gpu): the sm_100a engine against the oracle through the C ABI — bit-exact k-mer entries, groups, cost
+model, cells (float32 bit patterns), best-hit tables — on fixtures, the reference's golden vectors, seeded
+workloads at sizes the oracle finishes in seconds, and size-independent properties on a config-sized input."""
+import numpy as np
+import pytest
+
+import fixtures
+import golden_util
+from parity import check_scores, check_workload
+from pandelos_b200 import native, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def product_lib(engine_lib):
+    native._lib = None
+    native.load(native.ENGINE_LIB)
+    yield
+
+
+@pytest.mark.parametrize("name", sorted(fixtures.LITERAL))
+def test_literal_fixtures(name):
+    w, k = fixtures.literal(name)
+    check_workload(w, k)
+
+
+@pytest.mark.parametrize("name", golden_util.names())
+def test_reference_golden_vectors(name):
+    w, k, gold = golden_util.load(name)
+    pn = native.PangeneNative(k, native.PangeneIData(w.residues, w.offsets, w.genome_of))
+    try:
+        assert pn.info.G == len(gold)
+        for g, ref in enumerate(gold):
+            check_scores(pn.generateScoresPart(g), ref, "%s genome %d" % (name, g))
+    finally:
+        pn.close()
+
+
+@pytest.mark.parametrize("seed,k", [(201, 2), (202, 3), (203, 4), (204, 5)])
+def test_random_dense_sharing(seed, k):
+    w, _ = fixtures.random_workload(seed, genes=400, genomes=6, max_len=120, alphabet="ACDEFG", k=k)
+    check_workload(w, k)
+
+
+@pytest.mark.parametrize("shape,scale,k", [("salmonella7", 0.12, 4), ("mycoplasma64", 0.1, 4), ("ecoli10", 0.08, 5)])
+def test_config_shapes_scaled(shape, scale, k):
+    """The BASELINE.json shapes with fewer genes per genome: full index + every genome's cells vs the oracle."""
+    w = synth.shape(shape, scale=scale)
+    st = check_workload(w, k)
+    assert st["cells"] > 0 and st["fallback_rows"] == 0
+
+
+def test_low_complexity_multiplicities():
+    """poly-A / poly-Q runs: counts > 1 everywhere, long posting lists, MULTI rows."""
+    w = synth.generate(8, 300, 200.0, 0.1, 61, low_complexity=0.5)
+    st = check_workload(w, 4)
+    assert st["cells"] > 0
+
+
+def test_overflow_levels_and_dense_path(monkeypatch):
+    monkeypatch.setenv("PD_SMEM_TOP", "2048")
+    w = synth.generate(6, 200, 150.0, 0.1, 62, low_complexity=0.3)
+    st = check_workload(w, 4, hash_log2=6, index=False)
+    assert st["fallback_rows"] > 0
+
+
+@pytest.mark.parametrize("gshift", ["0", "3", "5"])
+def test_lanes_per_list(monkeypatch, gshift):
+    monkeypatch.setenv("PD_GSHIFT", gshift)
+    w = synth.generate(5, 150, 150.0, 0.1, 63)
+    check_workload(w, 4, index=False)
+
+
+def test_cell_buffer_regrow_and_concurrent_calls():
+    import threading
+    w = synth.generate(6, 200, 150.0, 0.1, 64)
+    data = native.PangeneIData(w.residues, w.offsets, w.genome_of)
+    pn = native.PangeneNative(4, data, cell_capacity=100, contexts=3)
+    from oracle import cport
+    o = cport.OracleIndex(w.residues, w.offsets, w.genome_of, 4)
+    want = [o.compute_scores(g) for g in range(pn.info.G)]
+    got = [None] * pn.info.G
+    errs = []
+
+    def work(g):
+        try:
+            got[g] = pn.generateScoresPart(g)   # Pangenes.java:60-66: one pool task per genome, concurrent
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(g,)) for g in range(pn.info.G)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+    for g in range(pn.info.G):
+        check_scores(got[g], want[g], "genome %d" % g)
+    pn.close()
+
+
+def test_full_size_properties():
+    """E. coli-shaped config at full size (10 x ~5,000 proteins, k from calculate_k): properties that need no oracle —
+    every cell has its mirror with identical score bits and swapped percs; best-hit tables equal the maxima of the
+    cells; colmax_g[c] == BH[c][g]; the device partition path reproduces pairs/cells; one sampled genome vs the oracle."""
+    w = synth.shape("ecoli10")
+    k = synth.calculate_k(w)
+    data = native.PangeneIData(w.residues, w.offsets, w.genome_of)
+    pn = native.PangeneNative(k, data)
+    S, G = pn.info.S, pn.info.G
+    BH = np.zeros((S, G), np.float32)
+    keys, vals = [], []
+    pairs = cells = 0
+    colmax = []
+    for g in range(G):
+        s = pn.generateScoresPart(g)
+        pairs += pn.last_stats.pairs
+        cells += s.scoresCount
+        rows = np.nonzero(w.genome_of == g)[0]
+        BH[rows] = s.max_genome_score
+        colmax.append(s.max_genome_score_col)
+        assert (s.first_seq_genome == g).all() and (s.second_seq_genome == w.genome_of[s.column].astype(np.int32)).all()
+        assert (s.row != s.column).all() and (s.scores > 0).all() and (s.scores <= 1).all()
+        # best hits are the maxima of the emitted cells
+        m = np.zeros((S, G), np.float32)
+        np.maximum.at(m, (s.row, s.second_seq_genome), s.scores)
+        assert (m[rows] == s.max_genome_score).all()
+        keys.append(s.row.astype(np.int64) * S + s.column)
+        vals.append(np.stack([s.scores.view(np.uint32), s.percs.view(np.uint32), s.tr_percs.view(np.uint32)], 1))
+    keys = np.concatenate(keys)
+    vals = np.concatenate(vals)
+    order = np.argsort(keys)
+    keys, vals = keys[order], vals[order]
+    assert len(np.unique(keys)) == len(keys)
+    mirror = (keys % S) * S + keys // S
+    pos = np.searchsorted(keys, mirror)
+    assert (keys[pos] == mirror).all()
+    assert (vals[pos][:, 0] == vals[:, 0]).all() and (vals[pos][:, 1] == vals[:, 2]).all() and (vals[pos][:, 2] == vals[:, 1]).all()
+    for g in range(G):
+        assert (colmax[g] == BH[:, g]).all()
+    st = pn.score_partition_device(0, S)
+    assert st.pairs == pairs and st.cells == cells and st.lookups == pn.info.lookups
+    from oracle import cport
+    o = cport.OracleIndex(w.residues, w.offsets, w.genome_of, k)
+    assert o.total_lookups == pn.info.lookups and o.num_entries == pn.info.U
+    check_scores(pn.generateScoresPart(3), o.compute_scores(3), "ecoli10 genome 3")
+    pn.close()
