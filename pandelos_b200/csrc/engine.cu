@@ -61,10 +61,11 @@ struct ScoreContext {
     rt::DevBuf<uint32_t> d_bh, d_colmax;
     rt::DevBuf<unsigned long long> d_counters;  // 8
     rt::DevBuf<uint32_t> d_cursors;             // 16
-    rt::DevBuf<uint2> d_rows, d_ovf;
-    rt::DevBuf<uint32_t> d_dense;
+    rt::DevBuf<sk::RowDesc> d_rows, d_ovf;
+    rt::DevBuf<uint32_t> d_dense, d_xtab;
+    uint32_t xtab_ctas = 0;
     rt::PinBuf<unsigned long long> h_counters;
-    rt::PinBuf<uint2> h_rows;
+    rt::PinBuf<sk::RowDesc> h_rows;
     rt::PinBuf<float> h_score, h_perc, h_trperc, h_bh, h_colmax;
     rt::PinBuf<int32_t> h_row, h_col, h_g1, h_g2, h_map;
     pd_score_stats stats;
@@ -179,7 +180,6 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         for (uint32_t s = 0; s < S; s++) genome_rows[cur[genome_ids[s]]++] = s;
     }
     visited.assign(S, 0);
-    row_multi.assign(S, 0);
     fwd_ptr_h.assign((size_t)S + 1, 0);
 
     rt::stream_t st = rt::stream_create();
@@ -309,13 +309,10 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         rt::DevBuf<uint32_t>& sexcl = gexcl;   // reuse
         rt::DevBuf<uint32_t> gene_cnt((size_t)S + 1);
         rt::DevBuf<unsigned long long> d_visited(S);
-        rt::DevBuf<uint8_t> grp_multi((size_t)n_groups + 1), d_row_multi(S);
         rt::zero(gene_cnt.p, sizeof(uint32_t) * ((size_t)S + 1), st);
         rt::zero(d_visited.p, sizeof(unsigned long long) * S, st);
-        rt::zero(grp_multi.p, (size_t)n_groups + 1, st);
-        rt::zero(d_row_multi.p, S, st);
         PD_LAUNCH(ik::shared_mark_kernel, blocks_for(U), 256, 0, st, (const uint2*)post.p, (const uint32_t*)ent_gid.p,
-                  (const uint32_t*)grp_head.p, U, sflag.p, gene_cnt.p, d_visited.p, grp_multi.p);
+                  (const uint32_t*)grp_head.p, U, sflag.p, gene_cnt.p, d_visited.p);
         launches++;
         prims::exclusive_scan_u32(sflag.p, sexcl.p, U, scratch.p, d_total.p, st, &launches);
         uint32_t R = 0;
@@ -334,14 +331,12 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
             scratch.ensure(prims::radix_tmp_words(R) + 16);
             uint64_t* fsorted = prims::radix_sort_u64(fk_a.p, fk_b.p, R, 32, 32 + seq_bits, scratch.p, st, &launches);
             PD_LAUNCH(ik::fwd_fill_kernel, blocks_for(R), 256, 0, st, (const uint64_t*)fsorted, R, (const uint2*)post.p,
-                      (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, (const uint8_t*)grp_multi.p, fwd.p, fwd_cnt.p,
-                      d_row_multi.p);
+                      (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, fwd.p, fwd_cnt.p);
             launches++;
             rt::sync(st);
         }
         static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
         rt::d2h(visited.data(), d_visited.p, sizeof(uint64_t) * S, st);
-        rt::d2h(row_multi.data(), d_row_multi.p, S, st);
         rt::d2h(fwd_ptr_h.data(), fwd_ptr.p, sizeof(uint32_t) * ((size_t)S + 1), st);
         rt::sync(st);
         t_fwd.stop();
@@ -360,15 +355,6 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     uint64_t lookups = 0;
     for (uint32_t s = 0; s < S; s++) lookups += visited[s];
     info.lookups = lookups;
-    // lanes per posting list: largest power of two <= mean list length seen per forward entry, in [4, 32]
-    {
-        double mean = info.R ? (double)lookups / (double)info.R : 1.0;
-        uint32_t gs = 2;
-        while (gs < 5 && (double)(2u << gs) <= mean) gs++;
-        gshift = gs;
-        const char* e = getenv("PD_GSHIFT");
-        if (e && *e) gshift = (uint32_t)std::min(5, std::max(0, atoi(e)));
-    }
     info.build_ms[0] = total ? t_hist.ms() : 0;
     if (N) {
         info.build_ms[1] = t_enc.ms();
@@ -396,15 +382,21 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
 
 namespace {
 
-struct Level {
-    size_t smem;
-};
+static const int kMaxCtasPerSm = 16;
 
-// shared-memory budget of the three table levels
+// side tables (score_kernels.cuh): keys empty, sums zero
+__global__ void __launch_bounds__(256) xtab_init_kernel(uint32_t* xtab, uint32_t ctas) {
+    const uint64_t n = (uint64_t)ctas * 5 * sk::kXSlots;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256)
+        xtab[i] = (i % (5 * sk::kXSlots)) < sk::kXSlots ? sk::kEmpty : 0u;
+}
+
+// shared-memory budget of the three table levels; a table of H slots costs 8 H (keys, counters) + 2 * (3H/4) bytes
+// (touched list), so H = bytes / 9.5
 inline void level_smem(const Index& ix, size_t out[3]) {
     size_t l1 = 64 * 1024;
-    if (ix.opt.hash_log2 > 0) l1 = (size_t)8 << ix.opt.hash_log2;
-    size_t top = ix.smem_optin > 4096 ? ix.smem_optin - 2048 : 46 * 1024;
+    if (ix.opt.hash_log2 > 0) l1 = (size_t)10 << ix.opt.hash_log2;
+    size_t top = ix.smem_optin > 8192 ? ix.smem_optin - 6144 : 40 * 1024;  // static scratch of the kernel is ~5.4 KB
     if (const char* e = getenv("PD_SMEM_TOP")) {  // tests: shrink the largest table to force the dense path
         size_t v = (size_t)atoll(e);
         if (v >= 64) top = std::min(top, v);
@@ -414,43 +406,54 @@ inline void level_smem(const Index& ix, size_t out[3]) {
     out[1] = l1;
     out[2] = std::max(l1, std::min<size_t>(192 * 1024, top));
 }
+inline uint32_t slots_for(size_t bytes) {
+    uint32_t h = (uint32_t)(bytes * 2 / 19) & ~3u;
+    return std::min<uint32_t>(std::max<uint32_t>(h, 8), 65532);
+}
+inline size_t smem_for(uint32_t slots) { return (size_t)slots * 8 + (size_t)(slots * 3 / 4) * 2 + 16; }
 
 struct RowLists {
-    // 0: unit L0, 1: multi L0, 2: unit L1, 3: multi L1
-    uint32_t begin[5];
+    uint32_t begin[3];  // level-0 rows, level-1 rows
 };
 
-template <bool MULTI>
-void launch_rows(ScoreContext& c, sk::ScoreArgs a, size_t smem, int cursor_id) {
+void launch_rows(ScoreContext& c, sk::ScoreArgs a, size_t level_bytes, int cursor_id) {
     Index& ix = *c.ix;
     if (a.n_rows == 0) return;
-    a.slots = (uint32_t)(smem / (MULTI ? 16 : 8));
+    a.slots = slots_for(level_bytes);
+    a.cap = a.slots * 3 / 4;
+    const size_t smem = smem_for(a.slots);
     a.cursor = c.d_cursors.p + cursor_id;
-    rt::allow_smem(sk::score_rows_kernel<MULTI>, smem);
-    int occ = rt::occupancy(sk::score_rows_kernel<MULTI>, sk::kScoreThreads, smem);
-    unsigned grid = (unsigned)std::min<uint64_t>(a.n_rows, (uint64_t)ix.sms * std::max(1, occ));
-    PD_LAUNCH(sk::score_rows_kernel<MULTI>, grid, sk::kScoreThreads, smem, c.st, a);
+    rt::allow_smem(sk::score_rows_kernel, smem);
+    int occ = std::min(kMaxCtasPerSm, std::max(1, rt::occupancy(sk::score_rows_kernel, sk::kScoreThreads, smem)));
+    unsigned grid = (unsigned)std::min<uint64_t>(a.n_rows, (uint64_t)ix.sms * occ);
+    PD_LAUNCH(sk::score_rows_kernel, grid, sk::kScoreThreads, smem, c.st, a);
     c.stats.launches++;
 }
 
 }  // namespace
 
-// Scores the `n` (gene, bh_row) pairs of h_rows (already classified into the four lists of `rl`).  Returns the number
-// of non-zero cells; cells beyond c.cap are counted but not stored (caller grows and re-runs).
+// Scores the `n` rows of c.h_rows (already ordered into the two lists of `rl`).  Returns the number of non-zero
+// cells; cells beyond c.cap are counted but not stored (caller grows and re-runs).
 static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32_t* d_bh, uint32_t* d_colmax, uint64_t* pairs) {
     Index& ix = *c.ix;
     size_t lv[3];
     level_smem(ix, lv);
+    const uint32_t want_ctas = (uint32_t)ix.sms * kMaxCtasPerSm;
+    if (c.xtab_ctas < want_ctas) {
+        c.d_xtab.alloc((size_t)want_ctas * 5 * sk::kXSlots);
+        PD_LAUNCH(xtab_init_kernel, (unsigned)ix.sms * 4, 256, 0, c.st, c.d_xtab.p, want_ctas);
+        c.xtab_ctas = want_ctas;
+    }
     rt::zero(c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
     rt::zero(c.d_cursors.p, 16 * sizeof(uint32_t), c.st);
     c.d_rows.ensure(n);
-    c.d_ovf.ensure((size_t)4 * n);
-    rt::h2d(c.d_rows.p, c.h_rows.p, sizeof(uint2) * n, c.st);
+    c.d_ovf.ensure((size_t)2 * n);
+    rt::h2d(c.d_rows.p, c.h_rows.p, sizeof(sk::RowDesc) * n, c.st);
 
     sk::ScoreArgs a;
     memset(&a, 0, sizeof(a));
-    a.post = ix.post.p; a.fwd = ix.fwd.p; a.fwd_cnt = ix.fwd_cnt.p; a.fwd_ptr = ix.fwd_ptr.p; a.meta = ix.meta.p;
-    a.G = ix.info.G; a.thr = ix.thr; a.gshift = ix.gshift;
+    a.post = ix.post.p; a.fwd = ix.fwd.p; a.fwd_cnt = ix.fwd_cnt.p; a.meta = ix.meta.p;
+    a.G = ix.info.G; a.thr = ix.thr; a.k2 = 2u * (uint32_t)ix.info.k;
     a.o_score = c.d_score.p; a.o_perc = c.d_perc.p; a.o_trperc = c.d_trperc.p;
     a.o_row = c.d_row.p; a.o_col = c.d_col.p; a.o_g1 = c.d_g1.p; a.o_g2 = c.d_g2.p;
     a.cell_cap = c.cap;
@@ -458,56 +461,50 @@ static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32
     a.n_pairs = c.d_counters.p + 1;
     a.bh = d_bh;
     a.colmax = d_colmax;
+    a.xtab = c.d_xtab.p;
 
     rt::event_record(c.ev_k0, c.st);
-    for (int list = 0; list < 4; list++) {
+    for (int level = 0; level < 2; level++) {
         sk::ScoreArgs b = a;
-        b.rows = c.d_rows.p + rl.begin[list];
-        b.n_rows = rl.begin[list + 1] - rl.begin[list];
-        const bool multi = list & 1;
-        const int level = list >> 1;
-        b.overflow_rows = c.d_ovf.p + (size_t)(multi ? 1 : 0) * n;
-        b.n_overflow = c.d_counters.p + 2 + (multi ? 1 : 0);
-        if (multi) launch_rows<true>(c, b, lv[level], list);
-        else launch_rows<false>(c, b, lv[level], list);
+        b.rows = c.d_rows.p + rl.begin[level];
+        b.n_rows = rl.begin[level + 1] - rl.begin[level];
+        b.overflow_rows = c.d_ovf.p;
+        b.n_overflow = c.d_counters.p + 2;
+        launch_rows(c, b, lv[level], level);
     }
     rt::d2h(c.h_counters.p, c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
     rt::sync(c.st);
     // level 2: rows that overflowed the level-1 table
-    if (c.h_counters.p[2] || c.h_counters.p[3]) {
-        for (int multi = 0; multi < 2; multi++) {
-            sk::ScoreArgs b = a;
-            b.rows = c.d_ovf.p + (size_t)multi * n;
-            b.n_rows = (uint32_t)c.h_counters.p[2 + multi];
-            b.overflow_rows = c.d_ovf.p + (size_t)(2 + multi) * n;
-            b.n_overflow = c.d_counters.p + 4 + multi;
-            if (multi) launch_rows<true>(c, b, lv[2], 4 + multi);
-            else launch_rows<false>(c, b, lv[2], 4 + multi);
-        }
+    if (c.h_counters.p[2]) {
+        sk::ScoreArgs b = a;
+        b.rows = c.d_ovf.p;
+        b.n_rows = (uint32_t)c.h_counters.p[2];
+        b.overflow_rows = c.d_ovf.p + n;
+        b.n_overflow = c.d_counters.p + 3;
+        launch_rows(c, b, lv[2], 2);
         rt::d2h(c.h_counters.p, c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
         rt::sync(c.st);
         // last resort: dense global accumulators
-        for (int multi = 0; multi < 2; multi++) {
-            const uint32_t nr = (uint32_t)c.h_counters.p[4 + multi];
-            if (!nr) continue;
-            const unsigned grid = std::min<unsigned>(nr, 8);
+        const uint32_t nr = (uint32_t)c.h_counters.p[3];
+        if (nr) {
+            const unsigned grid = std::min<unsigned>(nr, 32);
             const size_t words = (size_t)grid * 4 * ix.info.S;
             if (c.d_dense.n < words) {
                 c.d_dense.alloc(words);
                 rt::zero(c.d_dense.p, words * sizeof(uint32_t), c.st);
             }
-            sk::ScoreArgs b = a;
-            b.rows = c.d_ovf.p + (size_t)(2 + multi) * n;
-            b.n_rows = nr;
-            b.cursor = c.d_cursors.p + 8 + multi;
+            sk::ScoreArgs b2 = a;
+            b2.rows = c.d_ovf.p + n;
+            b2.n_rows = nr;
+            b2.cursor = c.d_cursors.p + 3;
             sk::DenseArgs d;
             d.S = ix.info.S;
             d.acc = c.d_dense.p;
-            PD_LAUNCH(sk::score_rows_dense_kernel, grid, sk::kScoreThreads, 0, c.st, b, d);
+            PD_LAUNCH(sk::score_rows_dense_kernel, grid, sk::kScoreThreads, 0, c.st, b2, d);
             c.stats.launches++;
             c.stats.fallback_rows += nr;
+            rt::d2h(c.h_counters.p, c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
         }
-        rt::d2h(c.h_counters.p, c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
     }
     rt::event_record(c.ev_k1, c.st);
     rt::sync(c.st);
@@ -516,36 +513,40 @@ static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32
     return c.h_counters.p[0];
 }
 
-// Classifies rows into (unit/multi) x (level 0/1) lists inside c.h_rows; `gene_at(i)` and bh row i.
+// Builds the row descriptors of the `n` rows gene_at(i) (best-hit row i) in c.h_rows, level-0 rows first.
 template <class F>
 static RowLists classify_rows(ScoreContext& c, uint32_t n, F gene_at, uint64_t* lookups, uint64_t* fwd_entries) {
     Index& ix = *c.ix;
     size_t lv[3];
     level_smem(ix, lv);
     c.h_rows.ensure(std::max<uint32_t>(n, 1));
-    uint32_t cnt[4] = {0, 0, 0, 0};
-    const uint64_t cap0_unit = (uint64_t)(lv[0] / 8) * 3 / 4, cap0_multi = (uint64_t)(lv[0] / 16) * 3 / 4;
-    auto cls = [&](uint32_t g) {
-        const int multi = ix.row_multi[g] ? 1 : 0;
-        const uint64_t bound = std::min<uint64_t>(ix.visited[g], ix.info.S);
-        const int level = bound <= (multi ? cap0_multi : cap0_unit) ? 0 : 1;
-        return level * 2 + multi;
-    };
+    const uint64_t cap0 = slots_for(lv[0]) * 3 / 4;
+    auto level_of = [&](uint32_t g) { return std::min<uint64_t>(ix.visited[g], ix.info.S) <= cap0 ? 0 : 1; };
+    uint32_t cnt[2] = {0, 0};
     uint64_t lk = 0, fe = 0;
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t g = gene_at(i);
-        cnt[cls(g)]++;
+        cnt[level_of(g)]++;
         lk += ix.visited[g];
         fe += ix.fwd_ptr_h[g + 1] - ix.fwd_ptr_h[g];
     }
     *fwd_entries = fe;
     RowLists rl;
     rl.begin[0] = 0;
-    for (int l = 0; l < 4; l++) rl.begin[l + 1] = rl.begin[l] + cnt[l];
-    uint32_t cur[4] = {rl.begin[0], rl.begin[1], rl.begin[2], rl.begin[3]};
+    rl.begin[1] = cnt[0];
+    rl.begin[2] = cnt[0] + cnt[1];
+    uint32_t cur[2] = {rl.begin[0], rl.begin[1]};
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t g = gene_at(i);
-        c.h_rows.p[cur[cls(g)]++] = make_uint2(g, i);
+        sk::RowDesc d;
+        d.gene = g;
+        d.bh_row = i;
+        d.fb = ix.fwd_ptr_h[g];
+        d.fe = ix.fwd_ptr_h[g + 1];
+        d.kr = ix.kseq[g];
+        d.gr = ix.genome_of[g];
+        d.pad0 = d.pad1 = 0;
+        c.h_rows.p[cur[level_of(g)]++] = d;
     }
     *lookups = lk;
     return rl;

@@ -18,7 +18,6 @@ struct Index {
     pd_options opt;
     pd_index_info info;
     float thr = 0.f;            // 1/(2k) in float32 (library.cpp:499)
-    uint32_t gshift = 5;        // lanes per posting list = 1 << gshift, from the mean list length
     int sms = 1;
     size_t smem_optin = 0;
 
@@ -36,7 +35,6 @@ struct Index {
     std::vector<uint32_t> kseq;
     std::vector<uint32_t> genome_of;
     std::vector<uint64_t> visited;
-    std::vector<uint8_t> row_multi;
     std::vector<uint32_t> fwd_ptr_h;    // S+1
     std::vector<uint32_t> genome_ptr;   // G+1
     std::vector<uint32_t> genome_rows;  // genes grouped by genome, input order inside (genome_sequences, library.cpp:245)

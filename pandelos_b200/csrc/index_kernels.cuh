@@ -10,9 +10,9 @@
 //
 // HBM layout produced (all SoA, 32-bit indices; the reference's 16-B kmer_rank / 24-B kmers_range records are gone):
 //   post[U]     uint2 (seq, count)     entries sorted by (rank, seq): the posting lists, group after group
-//   fwd[R]      uint2 (group start, group length) one per (gene, shared k-mer), genes ascending, ranks ascending
+//   fwd[R]      uint2 (group start, group length | own-count>1 flag) one per (gene, shared k-mer), genes ascending, ranks ascending
 //   fwd_cnt[R]  uint32 the gene's own multiplicity of that k-mer
-//   fwd_ptr[S+1], meta[S] = (kseq_len, genome), visited[S] (uint64), row_multi[S]
+//   fwd_ptr[S+1], meta[S] = (kseq_len, genome), visited[S] (uint64)
 #pragma once
 
 #include "pd_rt.h"
@@ -130,11 +130,11 @@ __global__ void __launch_bounds__(256) group_heads_kernel(const uint32_t* __rest
 }
 
 // per entry in a shared group (length >= 2): mark it, count it for its gene, add the group length to the gene's
-// cost (computation_costs[].total_visited, library.cpp:327), and mark groups that hold any count > 1.
+// cost (computation_costs[].total_visited, library.cpp:327).
 __global__ void __launch_bounds__(256) shared_mark_kernel(const uint2* __restrict__ post, const uint32_t* __restrict__ ent_gid,
                                                            const uint32_t* __restrict__ grp_head, uint32_t U,
                                                            uint32_t* __restrict__ sflag, uint32_t* __restrict__ gene_cnt,
-                                                           unsigned long long* __restrict__ visited, uint8_t* __restrict__ grp_multi) {
+                                                           unsigned long long* __restrict__ visited) {
     const uint32_t e = blockIdx.x * 256u + threadIdx.x;
     if (e >= U) return;
     const uint32_t g = ent_gid[e];
@@ -145,7 +145,6 @@ __global__ void __launch_bounds__(256) shared_mark_kernel(const uint2* __restric
     if (s) {
         atomicAdd(&gene_cnt[p.x], 1u);
         atomicAdd(&visited[p.x], (unsigned long long)gl);
-        if (p.y > 1) grp_multi[g] = 1;
     }
 }
 
@@ -157,20 +156,18 @@ __global__ void __launch_bounds__(256) fwd_keys_kernel(const uint2* __restrict__
     if (sflag[e]) fkeys[excl[e]] = ((uint64_t)post[e].x << 32) | e;
 }
 
-// forward lists from the gene-sorted keys
+// forward lists from the gene-sorted keys; bit 31 of the length flags an own multiplicity > 1 (then fwd_cnt is read)
 __global__ void __launch_bounds__(256) fwd_fill_kernel(const uint64_t* __restrict__ fkeys, uint32_t R, const uint2* __restrict__ post,
                                                         const uint32_t* __restrict__ ent_gid, const uint32_t* __restrict__ grp_head,
-                                                        const uint8_t* __restrict__ grp_multi, uint2* __restrict__ fwd,
-                                                        uint32_t* __restrict__ fwd_cnt, uint8_t* __restrict__ row_multi) {
+                                                        uint2* __restrict__ fwd, uint32_t* __restrict__ fwd_cnt) {
     const uint32_t j = blockIdx.x * 256u + threadIdx.x;
     if (j >= R) return;
-    const uint64_t fk = fkeys[j];
-    const uint32_t e = (uint32_t)fk, gene = (uint32_t)(fk >> 32);
+    const uint32_t e = (uint32_t)fkeys[j];
     const uint32_t g = ent_gid[e];
     const uint32_t gs = grp_head[g];
-    fwd[j] = make_uint2(gs, grp_head[g + 1] - gs);
-    fwd_cnt[j] = post[e].y;
-    if (grp_multi[g]) row_multi[gene] = 1;
+    const uint32_t cnt = post[e].y;
+    fwd[j] = make_uint2(gs, (grp_head[g + 1] - gs) | (cnt > 1 ? 0x80000000u : 0u));
+    fwd_cnt[j] = cnt;
 }
 
 // per-entry group (start, length) for pd_entries (tests / diagnostics)

@@ -1,15 +1,20 @@
 // Scoring kernels: the device counterpart of computeScores (reference ig/native/library.cpp:409-527).
 //
-// One CTA per row gene (persistent CTAs, rows handed out through a global cursor).  The reference's S-sized dense
-// accumulators with colour stamps (library.cpp:417-428,467-473) become an open-addressing hash table in shared
-// memory keyed by column gene; every posting visited is one coalesced 8-B HBM read and shared-memory atomics only.
+// One CTA per row gene (persistent CTAs, rows handed out through a global cursor, next row's descriptor prefetched
+// behind the current row's work).  The reference's S-sized dense accumulators with colour stamps
+// (library.cpp:417-428,467-473) become an open-addressing hash table in shared memory keyed by column gene.
 //
-//   accumulate   inter[c] += min(n, m); pc[c] += m; tc[c] += n          library.cpp:461-479
-//                UNIT rows (no multiplicity > 1 anywhere in the row's lists, known from the index): all three sums
-//                equal the number of shared k-mers, so ONE counter and ONE atomic per posting.
-//   finalize     union, perc, tr_perc, validity, float32 Jaccard          library.cpp:493-505
-//   emit         cells with score > 0, SoA in the layout of Scores.java   library.cpp:506-512, 554-575
-//   best hits    BH[row][genome(col)] and colmax[col] by atomic max        library.cpp:513-515
+//   accumulate   inter[c] += min(n, m); pc[c] += m; tc[c] += n                          library.cpp:461-479
+//                Written as (1,1,1) + (min(n,m)-1, m-1, n-1): the first part is ONE shared-memory counter per
+//                column (one atomic per posting visited); the second part is non-zero only where a k-mer repeats
+//                inside a gene (U/N > 0.999: rare) and goes to a small per-CTA side table in global memory (L2).
+//   postings     read through a warp-level load-balanced walk: short posting lists of a batch of 32 forward
+//                entries are flattened so that every lane has one posting per step (coalesced inside each list);
+//                long lists are walked by the whole warp, 256 B per step.
+//   finalize     only the columns touched (a list of table slots), integer validity gate, float32 Jaccard for the
+//                cells that pass                                                          library.cpp:493-505
+//   emit         cells with score > 0, SoA in the layout of Scores.java                   library.cpp:506-512, 554-575
+//   best hits    BH[row][genome(col)] and colmax[col] by atomic max                        library.cpp:513-515
 //
 // Rows whose distinct-column count overflows the table are appended to an overflow list and re-run with a larger
 // table; the last resort is score_rows_dense_kernel (global S-sized accumulators, as the reference).
@@ -21,26 +26,34 @@ namespace pd {
 namespace sk {
 
 static const int kScoreThreads = 256;
+static const int kScoreWarps = kScoreThreads / 32;
 static const uint32_t kEmpty = 0xFFFFFFFFu;
-static const uint32_t kMaxProbe = 192;
+static const uint32_t kFlag = 0x80000000u;     // "this column has side-table corrections"
+static const uint32_t kShortList = 64;          // lists up to this length are flattened
+static const uint32_t kXSlots = 2048;           // side-table slots per CTA (global memory)
+static const uint32_t kXCap = kXSlots * 3 / 4;
+static const uint32_t kFwdMulti = 0x80000000u;  // bit 31 of a forward entry's length: own multiplicity > 1
+
+struct __align__(16) RowDesc {  // 32 B, built on the host per call
+    uint32_t gene, bh_row, fb, fe, kr, gr, pad0, pad1;
+};
 
 struct ScoreArgs {
     // index
     const uint2* post;
-    const uint2* fwd;
+    const uint2* fwd;          // (group start, group length | kFwdMulti)
     const uint32_t* fwd_cnt;
-    const uint32_t* fwd_ptr;
-    const uint2* meta;  // (kseq_len, genome)
-    // work: (gene, best-hit row) pairs handed out through *cursor; n_rows read from *n_rows_ptr when non-null
-    const uint2* rows;
+    const uint2* meta;         // (kseq_len, genome)
+    // work
+    const RowDesc* rows;
     uint32_t n_rows;
-    const unsigned long long* n_rows_ptr;
     uint32_t* cursor;
     // parameters
     uint32_t G;
-    float thr;       // 1.0f / (2.0f * (float)k), library.cpp:499
-    uint32_t slots;  // hash table slots
-    uint32_t gshift; // log2(lanes cooperating on one posting list)
+    float thr;        // 1.0f / (2.0f * (float)k), library.cpp:499
+    uint32_t k2;      // 2k: perc >= thr  <=>  2k * pc >= K  (exact for K < 2^20, see finalize_cell)
+    uint32_t slots;   // hash table slots
+    uint32_t cap;     // touched-list capacity = max distinct columns accepted (<= 3/4 slots)
     // outputs
     float* o_score;
     float* o_perc;
@@ -54,34 +67,38 @@ struct ScoreArgs {
     unsigned long long* n_pairs;     // candidate cells evaluated (col != row)
     uint32_t* bh;                    // float bits, [bh_row * G + genome]
     uint32_t* colmax;                // float bits, [S] (may be null)
-    uint2* overflow_rows;            // rows that did not fit `slots`
+    RowDesc* overflow_rows;          // rows that did not fit
     unsigned long long* n_overflow;
+    // side tables: per CTA kXSlots x (key, d_inter, d_pc, d_tc) + kXSlots touched indices, clean between rows
+    uint32_t* xtab;
 };
 
 struct DenseArgs {
     uint32_t S;
-    uint32_t* acc;      // per CTA: inter[S], pc[S], tc[S], touched[S]; inter/pc/tc all zero between rows
+    uint32_t* acc;  // per CTA: inter[S], pc[S], tc[S], touched[S]; inter/pc/tc all zero between rows
 };
 
-// shared finalize: one candidate cell (row r, column c) with its three integer sums
 struct RowCtx {
     uint32_t r, bh_row, kr, gr;
 };
 
+// One candidate cell.  Validity gate (library.cpp:497-500) in integers:
+//   (float)pc / (float)K >= 1.0f / (2.0f * (float)k)   <=>   2k * pc >= K        for K < 2^20
+// (=>) division and reciprocal are correctly rounded and rounding is monotonic; (<=) if 2k*pc <= K - 1 the two reals
+// differ by more than 2^-20 relative, far more than the two roundings (2^-24 each) can close.
+// Only cells that pass pay for the three float divisions.
 __device__ __forceinline__ bool finalize_cell(const ScoreArgs& a, const RowCtx& rc, uint32_t c, uint32_t inter, uint32_t pc,
                                               uint32_t tc, float* score, float* perc, float* tr_perc, uint32_t* gc) {
     const uint2 mc = a.meta[c];
-    const int uni = (int)rc.kr + (int)mc.x - (int)inter;                       // library.cpp:494-496
-    const float p = __fdiv_rn(__int2float_rn((int)pc), __int2float_rn((int)rc.kr));   // :497
-    const float t = __fdiv_rn(__int2float_rn((int)tc), __int2float_rn((int)mc.x));    // :498
-    const bool valid = (p >= a.thr) || (t >= a.thr);                           // :500
-    const float q = __fdiv_rn(__int2float_rn((int)inter), __int2float_rn(uni));
-    const float s = valid ? q : 0.0f;                                          // q * 1.0f == q, q * 0.0f == +0 (:501-502)
-    *score = s;
-    *perc = p;
-    *tr_perc = t;
     *gc = mc.y;
-    return s > 0.0f;                                                           // :505
+    const bool valid = (a.k2 * pc >= rc.kr) || (a.k2 * tc >= mc.x);
+    if (!valid || inter == 0) return false;
+    const int uni = (int)rc.kr + (int)mc.x - (int)inter;                              // library.cpp:494-496
+    *perc = __fdiv_rn(__int2float_rn((int)pc), __int2float_rn((int)rc.kr));            // :497
+    *tr_perc = __fdiv_rn(__int2float_rn((int)tc), __int2float_rn((int)mc.x));          // :498
+    const float s = __fdiv_rn(__int2float_rn((int)inter), __int2float_rn(uni));        // :501 (valid -> * 1.0f)
+    *score = s;
+    return s > 0.0f;                                                                   // :505
 }
 
 // warp-aggregated append of the cells wanted by the lanes of a fully converged warp
@@ -111,144 +128,299 @@ __device__ __forceinline__ void emit_cells(const ScoreArgs& a, const RowCtx& rc,
     }
 }
 
-__device__ __forceinline__ uint32_t find_slot(uint32_t* keys, uint32_t c, uint32_t slots, volatile int* s_over) {
-    uint32_t h = __umulhi(c * 0x9E3779B1u, slots);
-#pragma unroll 1
-    for (uint32_t probe = 0; probe < kMaxProbe; probe++) {
-        const uint32_t k = *(volatile uint32_t*)(keys + h);
+// Per-warp scratch of the load-balanced walk
+struct WarpScratch {
+    uint32_t bits[kShortList];  // 32 lists x kShortList postings = 2048 marks
+    uint32_t gs[32];
+    uint32_t pre[32];
+    uint32_t m[32];
+};
+
+// Calls body(column gene, its count n, the row's own count m, active) once per posting of the row's shared k-mers.
+// Every lane of every warp calls body the same number of times (inactive lanes with active == false), so body may
+// use full-mask warp votes.  `stop` is polled (warp-uniformly) between batches.
+template <class F>
+__device__ __forceinline__ void for_each_posting(const ScoreArgs& a, uint32_t fb, uint32_t fe, WarpScratch* ws_all,
+                                                 volatile int* stop, F body) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpScratch& ws = ws_all[warp];
+    const unsigned lt = (1u << lane) - 1u;
+    for (uint32_t b0 = fb + warp * 32; b0 < fe; b0 += kScoreWarps * 32) {
+        if (__any_sync(0xffffffffu, *stop != 0)) break;
+        const uint32_t f = b0 + lane;
+        const bool has = f < fe;
+        uint2 fw = has ? a.fwd[f] : make_uint2(0u, 0u);
+        uint32_t m = 1;
+        if (fw.y & kFwdMulti) {
+            fw.y &= ~kFwdMulti;
+            m = a.fwd_cnt[f];
+        }
+        const bool is_short = has && fw.y <= kShortList;
+        // ---- short lists: compact them to the front, mark each list's first posting, one posting per lane per step
+        const unsigned smask = __ballot_sync(0xffffffffu, is_short);
+        if (smask) {
+            const uint32_t len = is_short ? fw.y : 0u;
+            uint32_t incl = len;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (unsigned)d) incl += o;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t pre = incl - len;
+            ws.bits[lane] = 0;
+            ws.bits[lane + 32] = 0;
+            __syncwarp();
+            if (is_short) {
+                const unsigned rnk = __popc(smask & lt);
+                ws.gs[rnk] = fw.x;
+                ws.pre[rnk] = pre;
+                ws.m[rnk] = m;
+                atomicOr(&ws.bits[pre >> 5], 1u << (pre & 31));
+            }
+            __syncwarp();
+            uint32_t seen = 0;  // marks before this step
+            for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+                const uint32_t word = ws.bits[t0 >> 5];
+                const uint32_t t = t0 + lane;
+                const bool act = t < total;
+                const uint32_t owner = (seen + __popc(word & (lt | (1u << lane))) - 1u) & 31u;
+                seen += __popc(word);
+                uint2 e = make_uint2(kEmpty, 0u);
+                uint32_t om = 1;
+                if (act) {
+                    e = a.post[ws.gs[owner] + (t - ws.pre[owner])];
+                    om = ws.m[owner];
+                }
+                body(e.x, e.y, om, act);
+            }
+            __syncwarp();
+        }
+        // ---- long lists: the whole warp walks each one, 32 consecutive postings per step
+        unsigned lmask = __ballot_sync(0xffffffffu, has && !is_short);
+        while (lmask) {
+            const int j = __ffs(lmask) - 1;
+            lmask &= lmask - 1;
+            const uint32_t gs = __shfl_sync(0xffffffffu, fw.x, j);
+            const uint32_t gl = __shfl_sync(0xffffffffu, fw.y, j);
+            const uint32_t mj = __shfl_sync(0xffffffffu, m, j);
+            const uint2* pl = a.post + gs;
+            for (uint32_t p0 = 0; p0 < gl; p0 += 64) {
+                // two independent 8-B loads in flight per lane
+                const uint32_t pa = p0 + lane, pb = p0 + 32 + lane;
+                const bool aa = pa < gl, ab = pb < gl;
+                const uint2 ea = aa ? pl[pa] : make_uint2(kEmpty, 0u);
+                const uint2 eb = ab ? pl[pb] : make_uint2(kEmpty, 0u);
+                body(ea.x, ea.y, mj, aa);
+                if (p0 + 32 < gl) body(eb.x, eb.y, mj, ab);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t x_find_or_insert(uint32_t* xkeys, uint32_t* xtouched, uint32_t c, uint32_t* s_nx,
+                                                     volatile int* s_over) {
+    uint32_t h = __umulhi(c * 0x85EBCA6Bu, kXSlots);
+    for (uint32_t probe = 0; probe < kXSlots; probe++) {
+        const uint32_t k = *(volatile uint32_t*)(xkeys + h);
         if (k == c) return h;
         if (k == kEmpty) {
-            const uint32_t old = atomicCAS(keys + h, kEmpty, c);
-            if (old == kEmpty || old == c) return h;
+            const uint32_t old = atomicCAS(xkeys + h, kEmpty, c);
+            if (old == kEmpty) {
+                const uint32_t xi = atomicAdd(s_nx, 1u);
+                if (xi < kXCap) xtouched[xi] = h;
+                else *s_over = 1;
+                return h;
+            }
+            if (old == c) return h;
         }
-        h++;
-        if (h == slots) h = 0;
+        h = (h + 1 == kXSlots) ? 0 : h + 1;
     }
     *s_over = 1;
     return kEmpty;
 }
 
-// MULTI = false: UNIT rows, table = keys[slots] + cnt[slots]            ( 8 B per slot)
-// MULTI = true : general rows, table = keys + inter + pc + tc planes     (16 B per slot)
-template <bool MULTI>
 __global__ void __launch_bounds__(kScoreThreads) score_rows_kernel(ScoreArgs a) {
     PD_DYNAMIC_SMEM(smem_raw);
     uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);
-    uint32_t* v0 = keys + a.slots;   // UNIT: shared k-mer count; MULTI: inter
-    uint32_t* v1 = v0 + a.slots;     // MULTI: pc
-    uint32_t* v2 = v1 + a.slots;     // MULTI: tc
-    __shared__ uint32_t s_row;
-    __shared__ int s_over;
+    uint32_t* cnt = keys + a.slots;
+    uint16_t* touched = reinterpret_cast<uint16_t*>(cnt + a.slots);
+    __shared__ WarpScratch ws[kScoreWarps];
+    __shared__ uint4 s_desc[2][2];  // two RowDesc buffers
+    // per-row control words, double-buffered like s_desc: a row uses [buf]; thread 0 clears [buf ^ 1] at the end of
+    // the row, which nobody reads before the closing barrier
+    __shared__ uint32_t s_nt2[2], s_nx2[2];
+    __shared__ int s_over2[2];
 
     const unsigned tid = threadIdx.x;
-    const uint32_t slots = a.slots;
-    const uint32_t n_rows = a.n_rows_ptr ? (uint32_t)*a.n_rows_ptr : a.n_rows;
-    const unsigned gl_lanes = 1u << a.gshift;
-    const unsigned grp = tid >> a.gshift, lane_in_grp = tid & (gl_lanes - 1u), n_grp = kScoreThreads >> a.gshift;
+    const uint32_t slots = a.slots, cap = a.cap;
+    uint32_t* xkeys = a.xtab + (size_t)blockIdx.x * (5 * kXSlots);
+    uint32_t* xv0 = xkeys + kXSlots;
+    uint32_t* xv1 = xv0 + kXSlots;
+    uint32_t* xv2 = xv1 + kXSlots;
+    uint32_t* xtouched = xv2 + kXSlots;
 
     for (uint32_t i = tid; i < slots; i += kScoreThreads) {
         keys[i] = kEmpty;
-        v0[i] = 0;
-        if (MULTI) {
-            v1[i] = 0;
-            v2[i] = 0;
-        }
+        cnt[i] = 0;
     }
+    const uint4* rows4 = reinterpret_cast<const uint4*>(a.rows);
+    if (tid == 0) {
+        const uint32_t ri = atomicAdd(a.cursor, 1u);
+        uint4 d0 = make_uint4(kEmpty, 0u, 0u, 0u), d1 = make_uint4(0u, 0u, 0u, 0u);
+        if (ri < a.n_rows) {
+            d0 = rows4[2 * (size_t)ri];
+            d1 = rows4[2 * (size_t)ri + 1];
+        }
+        s_desc[0][0] = d0;
+        s_desc[0][1] = d1;
+        s_nt2[0] = s_nt2[1] = 0;
+        s_nx2[0] = s_nx2[1] = 0;
+        s_over2[0] = s_over2[1] = 0;
+    }
+    __syncthreads();
     unsigned long long pairs = 0;
+    int buf = 0;
 
     for (;;) {
-        if (tid == 0) {
-            s_row = atomicAdd(a.cursor, 1u);
-            s_over = 0;
-        }
-        __syncthreads();
-        const uint32_t ri = s_row;
-        if (ri >= n_rows) break;
-        const uint2 rw = a.rows[ri];
+        const uint4 rw0 = s_desc[buf][0], rw1 = s_desc[buf][1];  // (gene, bh_row, fb, fe), (kr, gr, -, -)
+        if (rw0.x == kEmpty) break;
+        uint32_t& s_nt = s_nt2[buf];
+        uint32_t& s_nx = s_nx2[buf];
+        int& s_over = s_over2[buf];
+        uint32_t next_ri = 0;
+        if (tid == 0) next_ri = atomicAdd(a.cursor, 1u);  // consumed after the accumulate phase
         RowCtx rc;
-        rc.r = rw.x;
-        rc.bh_row = rw.y;
-        const uint2 mr = a.meta[rc.r];
-        rc.kr = mr.x;
-        rc.gr = mr.y;
-        const uint32_t fb = a.fwd_ptr[rc.r], fe = a.fwd_ptr[rc.r + 1];
+        rc.r = rw0.x;
+        rc.bh_row = rw0.y;
+        rc.kr = rw1.x;
+        rc.gr = rw1.y;
 
-        // ---- accumulate along the posting lists of the row's shared k-mers
-        for (uint32_t f = fb + grp; f < fe; f += n_grp) {
-            if (*(volatile int*)&s_over) break;
-            const uint2 fw = a.fwd[f];
-            const uint32_t m = MULTI ? a.fwd_cnt[f] : 1u;
-            const uint2* pl = a.post + fw.x;
-            for (uint32_t p0 = lane_in_grp; p0 < fw.y; p0 += 4 * gl_lanes) {
-                // up to four independent 8-B loads in flight per lane
-                uint2 e[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t p = p0 + u * gl_lanes;
-                    e[u] = (p < fw.y) ? pl[p] : make_uint2(kEmpty, 0u);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (e[u].x == kEmpty) continue;
-                    const uint32_t h = find_slot(keys, e[u].x, slots, &s_over);
-                    if (h == kEmpty) continue;
-                    if (MULTI) {
-                        atomicAdd(&v0[h], e[u].y < m ? e[u].y : m);
-                        atomicAdd(&v1[h], m);
-                        atomicAdd(&v2[h], e[u].y);
+        // ---- accumulate
+        for_each_posting(a, rw0.z, rw0.w, ws, &s_over, [&](uint32_t c, uint32_t n, uint32_t m, bool act) {
+            uint32_t h = __umulhi(c * 0x9E3779B1u, slots);
+            bool pending = act;
+            uint32_t probes = 0;
+            while (__any_sync(0xffffffffu, pending)) {
+                if (pending) {
+                    const uint32_t k = *(volatile uint32_t*)(keys + h);
+                    bool hit = (k == c);
+                    if (!hit && k == kEmpty) {
+                        const uint32_t old = atomicCAS(keys + h, kEmpty, c);
+                        if (old == kEmpty) {
+                            hit = true;
+                            const uint32_t pos = atomicAdd(&s_nt, 1u);
+                            if (pos < cap) touched[pos] = (uint16_t)h;
+                            else s_over = 1;
+                        } else {
+                            hit = (old == c);
+                        }
+                    }
+                    if (hit) {
+                        atomicAdd(&cnt[h], 1u);
+                        if ((n | m) > 1u) {  // a repeated k-mer on either side: corrections go to the side table
+                            atomicOr(&cnt[h], kFlag);
+                            const uint32_t xs = x_find_or_insert(xkeys, xtouched, c, &s_nx, &s_over);
+                            if (xs != kEmpty) {
+                                const uint32_t mn = n < m ? n : m;
+                                if (mn > 1) atomicAdd(&xv0[xs], mn - 1);
+                                if (m > 1) atomicAdd(&xv1[xs], m - 1);
+                                if (n > 1) atomicAdd(&xv2[xs], n - 1);
+                            }
+                        }
+                        pending = false;
                     } else {
-                        atomicAdd(&v0[h], 1u);
+                        h = (h + 1 == slots) ? 0 : h + 1;
+                        if (++probes > slots) {
+                            s_over = 1;
+                            pending = false;
+                        }
                     }
                 }
             }
-        }
+        });
+        __threadfence_block();
         __syncthreads();
 
+        uint4 nd0 = make_uint4(kEmpty, 0u, 0u, 0u), nd1 = make_uint4(0u, 0u, 0u, 0u);
+        if (tid == 0 && next_ri < a.n_rows) {  // consumed at the end of the row
+            nd0 = rows4[2 * (size_t)next_ri];
+            nd1 = rows4[2 * (size_t)next_ri + 1];
+        }
+
+        const uint32_t nx = s_nx < kXCap ? s_nx : kXCap;
         if (s_over) {
-            // does not fit: hand the row to the next level, wipe the table
+            // does not fit: hand the row to the next level, wipe both tables
             if (tid == 0) {
                 const unsigned long long o = atomicAdd(a.n_overflow, 1ull);
-                a.overflow_rows[o] = rw;
+                uint4* dst = reinterpret_cast<uint4*>(a.overflow_rows + o);
+                dst[0] = rw0;
+                dst[1] = rw1;
             }
             for (uint32_t i = tid; i < slots; i += kScoreThreads) {
                 keys[i] = kEmpty;
-                v0[i] = 0;
-                if (MULTI) {
-                    v1[i] = 0;
-                    v2[i] = 0;
-                }
+                cnt[i] = 0;
             }
-            __syncthreads();
-            continue;
-        }
-
-        // ---- finalize + emit: every thread walks the same number of slots so warps stay converged
-        for (uint32_t b = 0; b < slots; b += kScoreThreads) {
-            const uint32_t h = b + tid;
-            bool want = false;
-            uint32_t c = kEmpty, gc = 0;
-            float score = 0.f, perc = 0.f, trp = 0.f;
-            if (h < slots) {
-                c = keys[h];
-                if (c != kEmpty) {
-                    const uint32_t inter = v0[h];
-                    const uint32_t pc = MULTI ? v1[h] : inter;
-                    const uint32_t tc = MULTI ? v2[h] : inter;
+            if (s_nx) {
+                for (uint32_t i = tid; i < kXSlots; i += kScoreThreads) {
+                    xkeys[i] = kEmpty;
+                    xv0[i] = 0;
+                    xv1[i] = 0;
+                    xv2[i] = 0;
+                }
+                __threadfence();
+            }
+        } else {
+            // ---- finalize + emit over the touched columns; all threads run the same number of steps
+            if (nx) __threadfence();
+            const uint32_t nt = s_nt;
+            for (uint32_t b = 0; b < nt; b += kScoreThreads) {
+                const uint32_t i = b + tid;
+                bool want = false;
+                uint32_t c = kEmpty, gc = 0;
+                float score = 0.f, perc = 0.f, trp = 0.f;
+                if (i < nt) {
+                    const uint32_t h = touched[i];
+                    c = keys[h];
+                    const uint32_t v = cnt[h];
                     keys[h] = kEmpty;
-                    v0[h] = 0;
-                    if (MULTI) {
-                        v1[h] = 0;
-                        v2[h] = 0;
+                    cnt[h] = 0;
+                    uint32_t inter = v & ~kFlag, pc = inter, tc = inter;
+                    if (v & kFlag) {
+                        uint32_t xs = __umulhi(c * 0x85EBCA6Bu, kXSlots);
+                        while (*(volatile uint32_t*)(xkeys + xs) != c) xs = (xs + 1 == kXSlots) ? 0 : xs + 1;
+                        inter += *(volatile uint32_t*)(xv0 + xs);
+                        pc += *(volatile uint32_t*)(xv1 + xs);
+                        tc += *(volatile uint32_t*)(xv2 + xs);
                     }
                     if (c != rc.r) {  // identity cell dropped (library.cpp:485-487)
                         pairs++;
                         want = finalize_cell(a, rc, c, inter, pc, tc, &score, &perc, &trp, &gc);
                     }
                 }
+                emit_cells(a, rc, want, c, score, perc, trp, gc);
             }
-            emit_cells(a, rc, want, c, score, perc, trp, gc);
+            if (nx) {  // side-table slots are released only after every reader is done (linear probing)
+                __syncthreads();
+                for (uint32_t i = tid; i < nx; i += kScoreThreads) {
+                    const uint32_t xs = xtouched[i];
+                    xkeys[xs] = kEmpty;
+                    xv0[xs] = 0;
+                    xv1[xs] = 0;
+                    xv2[xs] = 0;
+                }
+                __threadfence();
+            }
+        }
+        if (tid == 0) {
+            s_desc[buf ^ 1][0] = nd0;
+            s_desc[buf ^ 1][1] = nd1;
+            s_nt2[buf ^ 1] = 0;
+            s_nx2[buf ^ 1] = 0;
+            s_over2[buf ^ 1] = 0;
         }
         __syncthreads();
+        buf ^= 1;
     }
 
     // one atomic per warp for the pair statistic
@@ -260,17 +432,17 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_kernel(ScoreArgs a) 
 // Last resort for rows with more distinct columns than any shared-memory table holds: the reference's own scheme,
 // S-sized accumulators in global memory (zero between rows) plus a touched list.
 __global__ void __launch_bounds__(kScoreThreads) score_rows_dense_kernel(ScoreArgs a, DenseArgs d) {
+    __shared__ WarpScratch ws[kScoreWarps];
     __shared__ uint32_t s_row;
     __shared__ uint32_t s_touched;
+    __shared__ int s_stop;
     const unsigned tid = threadIdx.x;
-    const uint32_t n_rows = a.n_rows_ptr ? (uint32_t)*a.n_rows_ptr : a.n_rows;
     uint32_t* inter = d.acc + (size_t)blockIdx.x * 4 * d.S;
     uint32_t* pcv = inter + d.S;
     uint32_t* tcv = pcv + d.S;
     uint32_t* touched = tcv + d.S;
-    const unsigned gl_lanes = 1u << a.gshift;
-    const unsigned grp = tid >> a.gshift, lane_in_grp = tid & (gl_lanes - 1u), n_grp = kScoreThreads >> a.gshift;
     unsigned long long pairs = 0;
+    if (tid == 0) s_stop = 0;
 
     for (;;) {
         if (tid == 0) {
@@ -279,26 +451,21 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_dense_kernel(ScoreAr
         }
         __syncthreads();
         const uint32_t ri = s_row;
-        if (ri >= n_rows) break;
-        const uint2 rw = a.rows[ri];
+        if (ri >= a.n_rows) break;
+        const RowDesc rw = a.rows[ri];
         RowCtx rc;
-        rc.r = rw.x;
-        rc.bh_row = rw.y;
-        const uint2 mr = a.meta[rc.r];
-        rc.kr = mr.x;
-        rc.gr = mr.y;
-        const uint32_t fb = a.fwd_ptr[rc.r], fe = a.fwd_ptr[rc.r + 1];
-        for (uint32_t f = fb + grp; f < fe; f += n_grp) {
-            const uint2 fw = a.fwd[f];
-            const uint32_t m = a.fwd_cnt[f];
-            for (uint32_t p = lane_in_grp; p < fw.y; p += gl_lanes) {
-                const uint2 e = a.post[fw.x + p];
-                const uint32_t old = atomicAdd(&tcv[e.x], e.y);  // counts are >= 1: old == 0 <=> first touch
-                if (old == 0) touched[atomicAdd(&s_touched, 1u)] = e.x;
-                atomicAdd(&inter[e.x], e.y < m ? e.y : m);
-                atomicAdd(&pcv[e.x], m);
+        rc.r = rw.gene;
+        rc.bh_row = rw.bh_row;
+        rc.kr = rw.kr;
+        rc.gr = rw.gr;
+        for_each_posting(a, rw.fb, rw.fe, ws, &s_stop, [&](uint32_t c, uint32_t n, uint32_t m, bool act) {
+            if (act) {
+                const uint32_t old = atomicAdd(&tcv[c], n);  // counts are >= 1: old == 0 <=> first touch
+                if (old == 0) touched[atomicAdd(&s_touched, 1u)] = c;
+                atomicAdd(&inter[c], n < m ? n : m);
+                atomicAdd(&pcv[c], m);
             }
-        }
+        });
         __threadfence();
         __syncthreads();
         const uint32_t nt = s_touched;

@@ -62,13 +62,6 @@ def test_overflow_levels_and_dense_path(monkeypatch):
     assert st["fallback_rows"] > 0
 
 
-@pytest.mark.parametrize("gshift", ["0", "2", "5"])
-def test_lanes_per_list(monkeypatch, gshift):
-    monkeypatch.setenv("PD_GSHIFT", gshift)
-    w, k = fixtures.random_workload(53, genes=50, genomes=3, max_len=40)
-    check_workload(w, k)
-
-
 def test_cell_buffer_regrow():
     w, k = fixtures.random_workload(54, genes=60, genomes=3, max_len=40)
     st = check_workload(w, k, cell_capacity=7)

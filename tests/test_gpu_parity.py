@@ -65,13 +65,6 @@ def test_overflow_levels_and_dense_path(monkeypatch):
     assert st["fallback_rows"] > 0
 
 
-@pytest.mark.parametrize("gshift", ["0", "3", "5"])
-def test_lanes_per_list(monkeypatch, gshift):
-    monkeypatch.setenv("PD_GSHIFT", gshift)
-    w = synth.generate(5, 150, 150.0, 0.1, 63)
-    check_workload(w, 4, index=False)
-
-
 def test_cell_buffer_regrow_and_concurrent_calls():
     import threading
     w = synth.generate(6, 200, 150.0, 0.1, 64)
