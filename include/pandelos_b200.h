@@ -92,6 +92,7 @@ typedef struct pd_score_stats {
     uint64_t fallback_rows;  /* rows that overflowed the shared-memory accumulator and took the dense global path */
     uint64_t launches;       /* kernels launched */
     uint64_t fwd_entries;    /* (row, shared k-mer) forward entries read */
+    uint64_t retry_rows;     /* rows that overflowed their first table and were re-run with the largest one */
     double kernel_ms;        /* CUDA-event time of the scoring kernels */
     double total_ms;         /* CUDA-event time of the whole call on its stream (memsets, kernels, copies) */
 } pd_score_stats;

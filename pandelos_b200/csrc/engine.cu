@@ -476,6 +476,7 @@ static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32
     rt::sync(c.st);
     // level 2: rows that overflowed the level-1 table
     if (c.h_counters.p[2]) {
+        c.stats.retry_rows += c.h_counters.p[2];
         sk::ScoreArgs b = a;
         b.rows = c.d_ovf.p;
         b.n_rows = (uint32_t)c.h_counters.p[2];

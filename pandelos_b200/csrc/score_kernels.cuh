@@ -130,22 +130,27 @@ __device__ __forceinline__ void emit_cells(const ScoreArgs& a, const RowCtx& rc,
 
 // Per-warp scratch of the load-balanced walk
 struct WarpScratch {
-    uint32_t bits[kShortList];  // 32 lists x kShortList postings = 2048 marks
+    uint32_t bits[kShortList + 1];  // 32 lists x kShortList postings = 2048 marks (+1: the walk reads one word ahead)
     uint32_t gs[32];
     uint32_t pre[32];
     uint32_t m[32];
 };
 
-// Calls body(column gene, its count n, the row's own count m, active) once per posting of the row's shared k-mers.
-// Every lane of every warp calls body the same number of times (inactive lanes with active == false), so body may
-// use full-mask warp votes.  `stop` is polled (warp-uniformly) between batches.
+// Calls body(column gene, its count n, the row's own count m) once per posting of the row's shared k-mers, from the
+// lane that read the posting.  Batches of 32 forward entries are handed to the warps through *batch_ctr (shared,
+// zero at entry).  `stop` is polled warp-uniformly between batches and inside long walks.
 template <class F>
 __device__ __forceinline__ void for_each_posting(const ScoreArgs& a, uint32_t fb, uint32_t fe, WarpScratch* ws_all,
-                                                 volatile int* stop, F body) {
+                                                 uint32_t* batch_ctr, volatile int* stop, F body) {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& ws = ws_all[warp];
     const unsigned lt = (1u << lane) - 1u;
-    for (uint32_t b0 = fb + warp * 32; b0 < fe; b0 += kScoreWarps * 32) {
+    for (;;) {
+        uint32_t bi = 0;
+        if (lane == 0) bi = atomicAdd(batch_ctr, 1u);
+        bi = __shfl_sync(0xffffffffu, bi, 0);
+        const uint32_t b0 = fb + bi * 32;
+        if (b0 >= fe) break;
         if (__any_sync(0xffffffffu, *stop != 0)) break;
         const uint32_t f = b0 + lane;
         const bool has = f < fe;
@@ -180,23 +185,30 @@ __device__ __forceinline__ void for_each_posting(const ScoreArgs& a, uint32_t fb
             }
             __syncwarp();
             uint32_t seen = 0;  // marks before this step
-            for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-                const uint32_t word = ws.bits[t0 >> 5];
-                const uint32_t t = t0 + lane;
-                const bool act = t < total;
-                const uint32_t owner = (seen + __popc(word & (lt | (1u << lane))) - 1u) & 31u;
-                seen += __popc(word);
-                uint2 e = make_uint2(kEmpty, 0u);
-                uint32_t om = 1;
-                if (act) {
-                    e = a.post[ws.gs[owner] + (t - ws.pre[owner])];
-                    om = ws.m[owner];
+            for (uint32_t t0 = 0; t0 < total; t0 += 64) {
+                // two steps per round: both postings are in flight before either is consumed
+                const uint32_t w0 = ws.bits[t0 >> 5], w1 = ws.bits[(t0 >> 5) + 1];
+                const uint32_t ta = t0 + lane, tb = ta + 32;
+                const uint32_t oa = (seen + __popc(w0 & (lt | (1u << lane))) - 1u) & 31u;
+                seen += __popc(w0);
+                const uint32_t ob = (seen + __popc(w1 & (lt | (1u << lane))) - 1u) & 31u;
+                seen += __popc(w1);
+                uint2 ea = make_uint2(kEmpty, 0u), eb = make_uint2(kEmpty, 0u);
+                uint32_t ma = 1, mb = 1;
+                if (ta < total) {
+                    ea = a.post[ws.gs[oa] + (ta - ws.pre[oa])];
+                    ma = ws.m[oa];
                 }
-                body(e.x, e.y, om, act);
+                if (tb < total) {
+                    eb = a.post[ws.gs[ob] + (tb - ws.pre[ob])];
+                    mb = ws.m[ob];
+                }
+                if (ta < total) body(ea.x, ea.y, ma);
+                if (tb < total) body(eb.x, eb.y, mb);
             }
             __syncwarp();
         }
-        // ---- long lists: the whole warp walks each one, 32 consecutive postings per step
+        // ---- long lists: the whole warp walks each one, 4 x 32 consecutive postings per round
         unsigned lmask = __ballot_sync(0xffffffffu, has && !is_short);
         while (lmask) {
             const int j = __ffs(lmask) - 1;
@@ -205,15 +217,15 @@ __device__ __forceinline__ void for_each_posting(const ScoreArgs& a, uint32_t fb
             const uint32_t gl = __shfl_sync(0xffffffffu, fw.y, j);
             const uint32_t mj = __shfl_sync(0xffffffffu, m, j);
             const uint2* pl = a.post + gs;
-            for (uint32_t p0 = 0; p0 < gl; p0 += 64) {
-                // two independent 8-B loads in flight per lane
-                const uint32_t pa = p0 + lane, pb = p0 + 32 + lane;
-                const bool aa = pa < gl, ab = pb < gl;
-                const uint2 ea = aa ? pl[pa] : make_uint2(kEmpty, 0u);
-                const uint2 eb = ab ? pl[pb] : make_uint2(kEmpty, 0u);
-                body(ea.x, ea.y, mj, aa);
-                if (p0 + 32 < gl) body(eb.x, eb.y, mj, ab);
+            for (uint32_t p0 = lane; p0 < gl; p0 += 128) {
+                uint2 e[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) e[u] = (p0 + 32 * u < gl) ? pl[p0 + 32 * u] : make_uint2(kEmpty, 0u);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (e[u].x != kEmpty) body(e[u].x, e[u].y, mj);
             }
+            if (__any_sync(0xffffffffu, *stop != 0)) break;
         }
     }
 }
@@ -251,6 +263,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_kernel(ScoreArgs a) 
     // the row, which nobody reads before the closing barrier
     __shared__ uint32_t s_nt2[2], s_nx2[2];
     __shared__ int s_over2[2];
+    __shared__ uint32_t s_batch2[2];
 
     const unsigned tid = threadIdx.x;
     const uint32_t slots = a.slots, cap = a.cap;
@@ -277,6 +290,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_kernel(ScoreArgs a) 
         s_nt2[0] = s_nt2[1] = 0;
         s_nx2[0] = s_nx2[1] = 0;
         s_over2[0] = s_over2[1] = 0;
+        s_batch2[0] = s_batch2[1] = 0;
     }
     __syncthreads();
     unsigned long long pairs = 0;
@@ -288,6 +302,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_kernel(ScoreArgs a) 
         uint32_t& s_nt = s_nt2[buf];
         uint32_t& s_nx = s_nx2[buf];
         int& s_over = s_over2[buf];
+        uint32_t& s_batch = s_batch2[buf];
         uint32_t next_ri = 0;
         if (tid == 0) next_ri = atomicAdd(a.cursor, 1u);  // consumed after the accumulate phase
         RowCtx rc;
@@ -297,44 +312,44 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_kernel(ScoreArgs a) 
         rc.gr = rw1.y;
 
         // ---- accumulate
-        for_each_posting(a, rw0.z, rw0.w, ws, &s_over, [&](uint32_t c, uint32_t n, uint32_t m, bool act) {
+        for_each_posting(a, rw0.z, rw0.w, ws, &s_batch, &s_over, [&](uint32_t c, uint32_t n, uint32_t m) {
             uint32_t h = __umulhi(c * 0x9E3779B1u, slots);
-            bool pending = act;
-            uint32_t probes = 0;
-            while (__any_sync(0xffffffffu, pending)) {
-                if (pending) {
-                    const uint32_t k = *(volatile uint32_t*)(keys + h);
-                    bool hit = (k == c);
-                    if (!hit && k == kEmpty) {
+            uint32_t k = *(volatile uint32_t*)(keys + h);
+            if (k != c) {
+                // first visit of this column in the row, or a collision: probe / claim
+                uint32_t probes = 0;
+                for (;;) {
+                    if (k == kEmpty) {
                         const uint32_t old = atomicCAS(keys + h, kEmpty, c);
                         if (old == kEmpty) {
-                            hit = true;
                             const uint32_t pos = atomicAdd(&s_nt, 1u);
                             if (pos < cap) touched[pos] = (uint16_t)h;
                             else s_over = 1;
-                        } else {
-                            hit = (old == c);
+                            break;
                         }
+                        if (old == c) break;
                     }
-                    if (hit) {
-                        atomicAdd(&cnt[h], 1u);
-                        if ((n | m) > 1u) {  // a repeated k-mer on either side: corrections go to the side table
-                            atomicOr(&cnt[h], kFlag);
-                            const uint32_t xs = x_find_or_insert(xkeys, xtouched, c, &s_nx, &s_over);
-                            if (xs != kEmpty) {
-                                const uint32_t mn = n < m ? n : m;
-                                if (mn > 1) atomicAdd(&xv0[xs], mn - 1);
-                                if (m > 1) atomicAdd(&xv1[xs], m - 1);
-                                if (n > 1) atomicAdd(&xv2[xs], n - 1);
-                            }
-                        }
-                        pending = false;
-                    } else {
-                        h = (h + 1 == slots) ? 0 : h + 1;
-                        if (++probes > slots) {
-                            s_over = 1;
-                            pending = false;
-                        }
+                    h = (h + 1 == slots) ? 0 : h + 1;
+                    ++probes;
+                    if (probes > slots) s_over = 1;  // full table
+                    if ((probes & 15u) == 0 && *(volatile int*)&s_over) {  // row already lost
+                        h = kEmpty;
+                        break;
+                    }
+                    k = *(volatile uint32_t*)(keys + h);
+                    if (k == c) break;
+                }
+            }
+            if (h != kEmpty) {
+                atomicAdd(&cnt[h], 1u);
+                if ((n | m) > 1u) {  // a repeated k-mer on either side: corrections go to the side table
+                    atomicOr(&cnt[h], kFlag);
+                    const uint32_t xs = x_find_or_insert(xkeys, xtouched, c, &s_nx, &s_over);
+                    if (xs != kEmpty) {
+                        const uint32_t mn = n < m ? n : m;
+                        if (mn > 1) atomicAdd(&xv0[xs], mn - 1);
+                        if (m > 1) atomicAdd(&xv1[xs], m - 1);
+                        if (n > 1) atomicAdd(&xv2[xs], n - 1);
                     }
                 }
             }
@@ -418,6 +433,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_kernel(ScoreArgs a) 
             s_nt2[buf ^ 1] = 0;
             s_nx2[buf ^ 1] = 0;
             s_over2[buf ^ 1] = 0;
+            s_batch2[buf ^ 1] = 0;
         }
         __syncthreads();
         buf ^= 1;
@@ -436,6 +452,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_dense_kernel(ScoreAr
     __shared__ uint32_t s_row;
     __shared__ uint32_t s_touched;
     __shared__ int s_stop;
+    __shared__ uint32_t s_batch;
     const unsigned tid = threadIdx.x;
     uint32_t* inter = d.acc + (size_t)blockIdx.x * 4 * d.S;
     uint32_t* pcv = inter + d.S;
@@ -448,6 +465,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_dense_kernel(ScoreAr
         if (tid == 0) {
             s_row = atomicAdd(a.cursor, 1u);
             s_touched = 0;
+            s_batch = 0;
         }
         __syncthreads();
         const uint32_t ri = s_row;
@@ -458,13 +476,11 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_dense_kernel(ScoreAr
         rc.bh_row = rw.bh_row;
         rc.kr = rw.kr;
         rc.gr = rw.gr;
-        for_each_posting(a, rw.fb, rw.fe, ws, &s_stop, [&](uint32_t c, uint32_t n, uint32_t m, bool act) {
-            if (act) {
-                const uint32_t old = atomicAdd(&tcv[c], n);  // counts are >= 1: old == 0 <=> first touch
-                if (old == 0) touched[atomicAdd(&s_touched, 1u)] = c;
-                atomicAdd(&inter[c], n < m ? n : m);
-                atomicAdd(&pcv[c], m);
-            }
+        for_each_posting(a, rw.fb, rw.fe, ws, &s_batch, &s_stop, [&](uint32_t c, uint32_t n, uint32_t m) {
+            const uint32_t old = atomicAdd(&tcv[c], n);  // counts are >= 1: old == 0 <=> first touch
+            if (old == 0) touched[atomicAdd(&s_touched, 1u)] = c;
+            atomicAdd(&inter[c], n < m ? n : m);
+            atomicAdd(&pcv[c], m);
         });
         __threadfence();
         __syncthreads();

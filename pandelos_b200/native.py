@@ -47,7 +47,7 @@ class ScoresStruct(C.Structure):
 
 class ScoreStats(C.Structure):
     _fields_ = [("rows", C.c_uint64), ("lookups", C.c_uint64), ("pairs", C.c_uint64), ("cells", C.c_uint64),
-                ("fallback_rows", C.c_uint64), ("launches", C.c_uint64), ("fwd_entries", C.c_uint64), ("kernel_ms", C.c_double), ("total_ms", C.c_double)]
+                ("fallback_rows", C.c_uint64), ("launches", C.c_uint64), ("fwd_entries", C.c_uint64), ("retry_rows", C.c_uint64), ("kernel_ms", C.c_double), ("total_ms", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

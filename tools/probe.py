@@ -42,7 +42,7 @@ def main():
             wall = time.time() - t
             alg = 8.0 * st.lookups + 8.0 * st.fwd_entries + 28.0 * st.cells + 4.0 * st.rows * i.G + 8.0 * i.S
             print(json.dumps({"workload": spec, "rows": st.rows, "lookups": st.lookups, "pairs": st.pairs, "cells": st.cells,
-                              "fallback_rows": st.fallback_rows, "launches": st.launches, "kernel_ms": round(st.kernel_ms, 3),
+                              "fallback_rows": st.fallback_rows, "retry_rows": st.retry_rows, "launches": st.launches, "kernel_ms": round(st.kernel_ms, 3),
                               "total_ms": round(st.total_ms, 3), "wall_ms": round(wall * 1e3, 3),
                               "Glookups_per_s": round(st.lookups / st.kernel_ms / 1e6, 2), "Mpairs_per_s": round(st.pairs / st.kernel_ms / 1e3, 1),
                               "alg_GBps": round(alg / st.kernel_ms / 1e6, 1), "frac_of_6551": round(alg / st.kernel_ms / 1e6 / 6551, 4)}), flush=True)
