@@ -181,6 +181,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     }
     visited.assign(S, 0);
     fwd_ptr_h.assign((size_t)S + 1, 0);
+    fwd_short_h.assign((size_t)S + 1, 0);
 
     rt::stream_t st = rt::stream_create();
     uint64_t launches = 0;
@@ -307,12 +308,13 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         t_fwd.start();
         rt::DevBuf<uint32_t>& sflag = rflag;   // reuse
         rt::DevBuf<uint32_t>& sexcl = gexcl;   // reuse
-        rt::DevBuf<uint32_t> gene_cnt((size_t)S + 1);
+        rt::DevBuf<uint32_t> gene_cnt((size_t)S + 1), gene_short((size_t)S + 1);
         rt::DevBuf<unsigned long long> d_visited(S);
         rt::zero(gene_cnt.p, sizeof(uint32_t) * ((size_t)S + 1), st);
+        rt::zero(gene_short.p, sizeof(uint32_t) * ((size_t)S + 1), st);
         rt::zero(d_visited.p, sizeof(unsigned long long) * S, st);
         PD_LAUNCH(ik::shared_mark_kernel, blocks_for(U), 256, 0, st, (const uint2*)post.p, (const uint32_t*)ent_gid.p,
-                  (const uint32_t*)grp_head.p, U, sflag.p, gene_cnt.p, d_visited.p);
+                  (const uint32_t*)grp_head.p, U, sflag.p, gene_cnt.p, gene_short.p, sk::kShortList, d_visited.p);
         launches++;
         prims::exclusive_scan_u32(sflag.p, sexcl.p, U, scratch.p, d_total.p, st, &launches);
         uint32_t R = 0;
@@ -326,10 +328,10 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         if (R) {
             rt::DevBuf<uint64_t> fk_a(R), fk_b(R);
             PD_LAUNCH(ik::fwd_keys_kernel, blocks_for(U), 256, 0, st, (const uint2*)post.p, (const uint32_t*)sflag.p,
-                      (const uint32_t*)sexcl.p, U, fk_a.p);
+                      (const uint32_t*)sexcl.p, (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, sk::kShortList, U, fk_a.p);
             launches++;
             scratch.ensure(prims::radix_tmp_words(R) + 16);
-            uint64_t* fsorted = prims::radix_sort_u64(fk_a.p, fk_b.p, R, 32, 32 + seq_bits, scratch.p, st, &launches);
+            uint64_t* fsorted = prims::radix_sort_u64(fk_a.p, fk_b.p, R, 31, 32 + seq_bits, scratch.p, st, &launches);
             PD_LAUNCH(ik::fwd_fill_kernel, blocks_for(R), 256, 0, st, (const uint64_t*)fsorted, R, (const uint2*)post.p,
                       (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, fwd.p, fwd_cnt.p);
             launches++;
@@ -338,6 +340,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
         rt::d2h(visited.data(), d_visited.p, sizeof(uint64_t) * S, st);
         rt::d2h(fwd_ptr_h.data(), fwd_ptr.p, sizeof(uint32_t) * ((size_t)S + 1), st);
+        rt::d2h(fwd_short_h.data(), gene_short.p, sizeof(uint32_t) * S, st);
         rt::sync(st);
         t_fwd.stop();
         if (!opt.keep_sorted) {
@@ -544,9 +547,10 @@ static RowLists classify_rows(ScoreContext& c, uint32_t n, F gene_at, uint64_t* 
         d.bh_row = i;
         d.fb = ix.fwd_ptr_h[g];
         d.fe = ix.fwd_ptr_h[g + 1];
+        d.fm = d.fb + ix.fwd_short_h[g];
         d.kr = ix.kseq[g];
         d.gr = ix.genome_of[g];
-        d.pad0 = d.pad1 = 0;
+        d.pad1 = 0;
         c.h_rows.p[cur[level_of(g)]++] = d;
     }
     *lookups = lk;

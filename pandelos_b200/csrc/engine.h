@@ -36,6 +36,7 @@ struct Index {
     std::vector<uint32_t> genome_of;
     std::vector<uint64_t> visited;
     std::vector<uint32_t> fwd_ptr_h;    // S+1
+    std::vector<uint32_t> fwd_short_h;  // per gene: forward entries whose posting list is short (they come first)
     std::vector<uint32_t> genome_ptr;   // G+1
     std::vector<uint32_t> genome_rows;  // genes grouped by genome, input order inside (genome_sequences, library.cpp:245)
 

@@ -12,6 +12,7 @@
 //   post[U]     uint2 (seq, count)     entries sorted by (rank, seq): the posting lists, group after group
 //   fwd[R]      uint2 (group start, group length | own-count>1 flag) one per (gene, shared k-mer), genes ascending, ranks ascending
 //   fwd_cnt[R]  uint32 the gene's own multiplicity of that k-mer
+//               (a gene's short lists first, then its long ones: fwd_mid[S] is the split)
 //   fwd_ptr[S+1], meta[S] = (kseq_len, genome), visited[S] (uint64)
 #pragma once
 
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(256) group_heads_kernel(const uint32_t* __rest
 __global__ void __launch_bounds__(256) shared_mark_kernel(const uint2* __restrict__ post, const uint32_t* __restrict__ ent_gid,
                                                            const uint32_t* __restrict__ grp_head, uint32_t U,
                                                            uint32_t* __restrict__ sflag, uint32_t* __restrict__ gene_cnt,
+                                                           uint32_t* __restrict__ gene_short, uint32_t short_max,
                                                            unsigned long long* __restrict__ visited) {
     const uint32_t e = blockIdx.x * 256u + threadIdx.x;
     if (e >= U) return;
@@ -144,16 +146,24 @@ __global__ void __launch_bounds__(256) shared_mark_kernel(const uint2* __restric
     sflag[e] = s;
     if (s) {
         atomicAdd(&gene_cnt[p.x], 1u);
+        if (gl <= short_max) atomicAdd(&gene_short[p.x], 1u);
         atomicAdd(&visited[p.x], (unsigned long long)gl);
     }
 }
 
-// compact the shared entries into sort keys (gene << 32 | entry)
+// compact the shared entries into sort keys (gene << 32 | long-list flag << 31 | entry): sorted on the gene AND the
+// flag, a gene's forward list holds its short posting lists first, then the long ones, ranks ascending in each part
 __global__ void __launch_bounds__(256) fwd_keys_kernel(const uint2* __restrict__ post, const uint32_t* __restrict__ sflag,
-                                                        const uint32_t* __restrict__ excl, uint32_t U, uint64_t* __restrict__ fkeys) {
+                                                        const uint32_t* __restrict__ excl, const uint32_t* __restrict__ ent_gid,
+                                                        const uint32_t* __restrict__ grp_head, uint32_t short_max, uint32_t U,
+                                                        uint64_t* __restrict__ fkeys) {
     const uint32_t e = blockIdx.x * 256u + threadIdx.x;
     if (e >= U) return;
-    if (sflag[e]) fkeys[excl[e]] = ((uint64_t)post[e].x << 32) | e;
+    if (sflag[e]) {
+        const uint32_t g = ent_gid[e];
+        const uint32_t gl = grp_head[g + 1] - grp_head[g];
+        fkeys[excl[e]] = ((uint64_t)post[e].x << 32) | (gl > short_max ? 0x80000000ull : 0ull) | e;
+    }
 }
 
 // forward lists from the gene-sorted keys; bit 31 of the length flags an own multiplicity > 1 (then fwd_cnt is read)
@@ -162,7 +172,7 @@ __global__ void __launch_bounds__(256) fwd_fill_kernel(const uint64_t* __restric
                                                         uint2* __restrict__ fwd, uint32_t* __restrict__ fwd_cnt) {
     const uint32_t j = blockIdx.x * 256u + threadIdx.x;
     if (j >= R) return;
-    const uint32_t e = (uint32_t)fkeys[j];
+    const uint32_t e = (uint32_t)fkeys[j] & 0x7FFFFFFFu;
     const uint32_t g = ent_gid[e];
     const uint32_t gs = grp_head[g];
     const uint32_t cnt = post[e].y;

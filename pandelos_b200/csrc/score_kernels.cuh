@@ -35,7 +35,7 @@ static const uint32_t kXCap = kXSlots * 3 / 4;
 static const uint32_t kFwdMulti = 0x80000000u;  // bit 31 of a forward entry's length: own multiplicity > 1
 
 struct __align__(16) RowDesc {  // 32 B, built on the host per call
-    uint32_t gene, bh_row, fb, fe, kr, gr, pad0, pad1;
+    uint32_t gene, bh_row, fb, fe, kr, gr, fm, pad1;  // forward entries [fb, fm) short lists, [fm, fe) long lists
 };
 
 struct ScoreArgs {
@@ -136,96 +136,110 @@ struct WarpScratch {
     uint32_t m[32];
 };
 
-// Calls body(column gene, its count n, the row's own count m) once per posting of the row's shared k-mers, from the
-// lane that read the posting.  Batches of 32 forward entries are handed to the warps through *batch_ctr (shared,
-// zero at entry).  `stop` is polled warp-uniformly between batches and inside long walks.
-template <class F>
-__device__ __forceinline__ void for_each_posting(const ScoreArgs& a, uint32_t fb, uint32_t fe, WarpScratch* ws_all,
-                                                 uint32_t* batch_ctr, volatile int* stop, F body) {
+// Visits every posting (column gene c, its count n, the row's own count m) of the row's shared k-mers from the lane
+// that read it: fast(c, n, m) first — the common, branch-light case — and slow(c, n, m) for the postings fast()
+// declined, gathered per round so that the divergent code runs once per round instead of once per posting.
+//   phase A  forward entries [fb, fm): short posting lists, flattened in batches of 32 entries handed out through
+//            ctr[0]: every lane has one posting per step, coalesced inside each list
+//   phase B  forward entries [fm, fe): long posting lists, handed out one list at a time through ctr[1]; the warp
+//            walks the list 4 x 32 consecutive postings (1 KB) per round
+// ctr[0..1] are shared counters, zero at entry.  `stop` is polled warp-uniformly.
+template <class Fast, class Slow>
+__device__ __forceinline__ void for_each_posting(const ScoreArgs& a, uint32_t fb, uint32_t fm, uint32_t fe, WarpScratch* ws_all,
+                                                 uint32_t* ctr, volatile int* stop, Fast fast, Slow slow) {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& ws = ws_all[warp];
     const unsigned lt = (1u << lane) - 1u;
+    // ---- phase A
     for (;;) {
         uint32_t bi = 0;
-        if (lane == 0) bi = atomicAdd(batch_ctr, 1u);
+        if (lane == 0) bi = atomicAdd(ctr, 1u);
         bi = __shfl_sync(0xffffffffu, bi, 0);
         const uint32_t b0 = fb + bi * 32;
-        if (b0 >= fe) break;
+        if (b0 >= fm) break;
         if (__any_sync(0xffffffffu, *stop != 0)) break;
         const uint32_t f = b0 + lane;
-        const bool has = f < fe;
+        const bool has = f < fm;
         uint2 fw = has ? a.fwd[f] : make_uint2(0u, 0u);
         uint32_t m = 1;
         if (fw.y & kFwdMulti) {
             fw.y &= ~kFwdMulti;
             m = a.fwd_cnt[f];
         }
-        const bool is_short = has && fw.y <= kShortList;
-        // ---- short lists: compact them to the front, mark each list's first posting, one posting per lane per step
-        const unsigned smask = __ballot_sync(0xffffffffu, is_short);
-        if (smask) {
-            const uint32_t len = is_short ? fw.y : 0u;
-            uint32_t incl = len;
+        uint32_t incl = fw.y;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= (unsigned)d) incl += o;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            const uint32_t pre = incl - len;
-            ws.bits[lane] = 0;
-            ws.bits[lane + 32] = 0;
-            __syncwarp();
-            if (is_short) {
-                const unsigned rnk = __popc(smask & lt);
-                ws.gs[rnk] = fw.x;
-                ws.pre[rnk] = pre;
-                ws.m[rnk] = m;
-                atomicOr(&ws.bits[pre >> 5], 1u << (pre & 31));
-            }
-            __syncwarp();
-            uint32_t seen = 0;  // marks before this step
-            for (uint32_t t0 = 0; t0 < total; t0 += 64) {
-                // two steps per round: both postings are in flight before either is consumed
-                const uint32_t w0 = ws.bits[t0 >> 5], w1 = ws.bits[(t0 >> 5) + 1];
-                const uint32_t ta = t0 + lane, tb = ta + 32;
-                const uint32_t oa = (seen + __popc(w0 & (lt | (1u << lane))) - 1u) & 31u;
-                seen += __popc(w0);
-                const uint32_t ob = (seen + __popc(w1 & (lt | (1u << lane))) - 1u) & 31u;
-                seen += __popc(w1);
-                uint2 ea = make_uint2(kEmpty, 0u), eb = make_uint2(kEmpty, 0u);
-                uint32_t ma = 1, mb = 1;
-                if (ta < total) {
-                    ea = a.post[ws.gs[oa] + (ta - ws.pre[oa])];
-                    ma = ws.m[oa];
-                }
-                if (tb < total) {
-                    eb = a.post[ws.gs[ob] + (tb - ws.pre[ob])];
-                    mb = ws.m[ob];
-                }
-                if (ta < total) body(ea.x, ea.y, ma);
-                if (tb < total) body(eb.x, eb.y, mb);
-            }
-            __syncwarp();
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (unsigned)d) incl += o;
         }
-        // ---- long lists: the whole warp walks each one, 4 x 32 consecutive postings per round
-        unsigned lmask = __ballot_sync(0xffffffffu, has && !is_short);
-        while (lmask) {
-            const int j = __ffs(lmask) - 1;
-            lmask &= lmask - 1;
-            const uint32_t gs = __shfl_sync(0xffffffffu, fw.x, j);
-            const uint32_t gl = __shfl_sync(0xffffffffu, fw.y, j);
-            const uint32_t mj = __shfl_sync(0xffffffffu, m, j);
-            const uint2* pl = a.post + gs;
-            for (uint32_t p0 = lane; p0 < gl; p0 += 128) {
-                uint2 e[4];
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t pre = incl - fw.y;
+        ws.bits[lane] = 0;
+        ws.bits[lane + 32] = 0;
+        ws.gs[lane] = fw.x;
+        ws.pre[lane] = pre;
+        ws.m[lane] = m;
+        __syncwarp();
+        if (has) atomicOr(&ws.bits[pre >> 5], 1u << (pre & 31));  // lists are >= 2 long: one mark per list
+        __syncwarp();
+        uint32_t seen = 0;  // marks before this round
+        for (uint32_t t0 = 0; t0 < total; t0 += 64) {
+            // two steps per round: both postings are in flight before either is consumed
+            const uint32_t w0 = ws.bits[t0 >> 5], w1 = ws.bits[(t0 >> 5) + 1];
+            const uint32_t ta = t0 + lane, tb = ta + 32;
+            const uint32_t oa = (seen + __popc(w0 & (lt | (1u << lane))) - 1u) & 31u;
+            seen += __popc(w0);
+            const uint32_t ob = (seen + __popc(w1 & (lt | (1u << lane))) - 1u) & 31u;
+            seen += __popc(w1);
+            uint2 ea = make_uint2(kEmpty, 0u), eb = make_uint2(kEmpty, 0u);
+            uint32_t ma = 1, mb = 1;
+            if (ta < total) {
+                ea = a.post[ws.gs[oa] + (ta - ws.pre[oa])];
+                ma = ws.m[oa];
+            }
+            if (tb < total) {
+                eb = a.post[ws.gs[ob] + (tb - ws.pre[ob])];
+                mb = ws.m[ob];
+            }
+            const bool sa = ea.x != kEmpty && !fast(ea.x, ea.y, ma);
+            const bool sb = eb.x != kEmpty && !fast(eb.x, eb.y, mb);
+            if (sa | sb) {
+                if (sa) slow(ea.x, ea.y, ma);
+                if (sb) slow(eb.x, eb.y, mb);
+            }
+        }
+        __syncwarp();
+    }
+    // ---- phase B
+    for (;;) {
+        uint32_t li = 0;
+        if (lane == 0) li = atomicAdd(ctr + 1, 1u);
+        li = __shfl_sync(0xffffffffu, li, 0);
+        const uint32_t f = fm + li;
+        if (f >= fe) break;
+        if (__any_sync(0xffffffffu, *stop != 0)) break;
+        uint2 fw = a.fwd[f];
+        uint32_t mj = 1;
+        if (fw.y & kFwdMulti) {
+            fw.y &= ~kFwdMulti;
+            mj = a.fwd_cnt[f];
+        }
+        const uint2* pl = a.post + fw.x;
+        const uint32_t gl = fw.y;
+        for (uint32_t p0 = lane; p0 < gl; p0 += 128) {
+            uint2 e[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) e[u] = (p0 + 32 * u < gl) ? pl[p0 + 32 * u] : make_uint2(kEmpty, 0u);
+            for (int u = 0; u < 4; u++) e[u] = (p0 + 32 * u < gl) ? pl[p0 + 32 * u] : make_uint2(kEmpty, 0u);
+            unsigned miss = 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (e[u].x != kEmpty && !fast(e[u].x, e[u].y, mj)) miss |= 1u << u;
+            if (miss) {
 #pragma unroll
                 for (int u = 0; u < 4; u++)
-                    if (e[u].x != kEmpty) body(e[u].x, e[u].y, mj);
+                    if (miss & (1u << u)) slow(e[u].x, e[u].y, mj);
             }
-            if (__any_sync(0xffffffffu, *stop != 0)) break;
+            if ((p0 & 0xF80u) == 0xF80u && __any_sync(0xffffffffu, *stop != 0)) break;  // every 32 rounds
         }
     }
 }
@@ -263,7 +277,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_kernel(ScoreArgs a) 
     // the row, which nobody reads before the closing barrier
     __shared__ uint32_t s_nt2[2], s_nx2[2];
     __shared__ int s_over2[2];
-    __shared__ uint32_t s_batch2[2];
+    __shared__ uint32_t s_batch2[2][2];
 
     const unsigned tid = threadIdx.x;
     const uint32_t slots = a.slots, cap = a.cap;
@@ -290,7 +304,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_kernel(ScoreArgs a) 
         s_nt2[0] = s_nt2[1] = 0;
         s_nx2[0] = s_nx2[1] = 0;
         s_over2[0] = s_over2[1] = 0;
-        s_batch2[0] = s_batch2[1] = 0;
+        s_batch2[0][0] = s_batch2[0][1] = s_batch2[1][0] = s_batch2[1][1] = 0;
     }
     __syncthreads();
     unsigned long long pairs = 0;
@@ -302,7 +316,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_kernel(ScoreArgs a) 
         uint32_t& s_nt = s_nt2[buf];
         uint32_t& s_nx = s_nx2[buf];
         int& s_over = s_over2[buf];
-        uint32_t& s_batch = s_batch2[buf];
+        uint32_t* s_batch = s_batch2[buf];
         uint32_t next_ri = 0;
         if (tid == 0) next_ri = atomicAdd(a.cursor, 1u);  // consumed after the accumulate phase
         RowCtx rc;
@@ -312,13 +326,21 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_kernel(ScoreArgs a) 
         rc.gr = rw1.y;
 
         // ---- accumulate
-        for_each_posting(a, rw0.z, rw0.w, ws, &s_batch, &s_over, [&](uint32_t c, uint32_t n, uint32_t m) {
-            uint32_t h = __umulhi(c * 0x9E3779B1u, slots);
-            uint32_t k = *(volatile uint32_t*)(keys + h);
-            if (k != c) {
-                // first visit of this column in the row, or a collision: probe / claim
+        for_each_posting(
+            a, rw0.z, rw1.z, rw0.w, ws, s_batch, &s_over,
+            // fast: the column is already in its home slot and no k-mer repeats: one load, one atomic
+            [&](uint32_t c, uint32_t n, uint32_t m) -> bool {
+                const uint32_t h = __umulhi(c * 0x9E3779B1u, slots);
+                if ((n | m) > 1u || *(volatile uint32_t*)(keys + h) != c) return false;
+                atomicAdd(&cnt[h], 1u);
+                return true;
+            },
+            // slow: first visit of the column in this row, a displaced key, or a repeated k-mer
+            [&](uint32_t c, uint32_t n, uint32_t m) {
+                uint32_t h = __umulhi(c * 0x9E3779B1u, slots);
+                uint32_t k = *(volatile uint32_t*)(keys + h);
                 uint32_t probes = 0;
-                for (;;) {
+                while (k != c) {
                     if (k == kEmpty) {
                         const uint32_t old = atomicCAS(keys + h, kEmpty, c);
                         if (old == kEmpty) {
@@ -337,23 +359,21 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_kernel(ScoreArgs a) 
                         break;
                     }
                     k = *(volatile uint32_t*)(keys + h);
-                    if (k == c) break;
                 }
-            }
-            if (h != kEmpty) {
-                atomicAdd(&cnt[h], 1u);
-                if ((n | m) > 1u) {  // a repeated k-mer on either side: corrections go to the side table
-                    atomicOr(&cnt[h], kFlag);
-                    const uint32_t xs = x_find_or_insert(xkeys, xtouched, c, &s_nx, &s_over);
-                    if (xs != kEmpty) {
-                        const uint32_t mn = n < m ? n : m;
-                        if (mn > 1) atomicAdd(&xv0[xs], mn - 1);
-                        if (m > 1) atomicAdd(&xv1[xs], m - 1);
-                        if (n > 1) atomicAdd(&xv2[xs], n - 1);
+                if (h != kEmpty) {
+                    atomicAdd(&cnt[h], 1u);
+                    if ((n | m) > 1u) {  // corrections for the repeated k-mer go to the side table
+                        atomicOr(&cnt[h], kFlag);
+                        const uint32_t xs = x_find_or_insert(xkeys, xtouched, c, &s_nx, &s_over);
+                        if (xs != kEmpty) {
+                            const uint32_t mn = n < m ? n : m;
+                            if (mn > 1) atomicAdd(&xv0[xs], mn - 1);
+                            if (m > 1) atomicAdd(&xv1[xs], m - 1);
+                            if (n > 1) atomicAdd(&xv2[xs], n - 1);
+                        }
                     }
                 }
-            }
-        });
+            });
         __threadfence_block();
         __syncthreads();
 
@@ -433,7 +453,8 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_kernel(ScoreArgs a) 
             s_nt2[buf ^ 1] = 0;
             s_nx2[buf ^ 1] = 0;
             s_over2[buf ^ 1] = 0;
-            s_batch2[buf ^ 1] = 0;
+            s_batch2[buf ^ 1][0] = 0;
+            s_batch2[buf ^ 1][1] = 0;
         }
         __syncthreads();
         buf ^= 1;
@@ -452,7 +473,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_dense_kernel(ScoreAr
     __shared__ uint32_t s_row;
     __shared__ uint32_t s_touched;
     __shared__ int s_stop;
-    __shared__ uint32_t s_batch;
+    __shared__ uint32_t s_batch[2];
     const unsigned tid = threadIdx.x;
     uint32_t* inter = d.acc + (size_t)blockIdx.x * 4 * d.S;
     uint32_t* pcv = inter + d.S;
@@ -465,7 +486,8 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_dense_kernel(ScoreAr
         if (tid == 0) {
             s_row = atomicAdd(a.cursor, 1u);
             s_touched = 0;
-            s_batch = 0;
+            s_batch[0] = 0;
+            s_batch[1] = 0;
         }
         __syncthreads();
         const uint32_t ri = s_row;
@@ -476,12 +498,14 @@ __global__ void __launch_bounds__(kScoreThreads) score_rows_dense_kernel(ScoreAr
         rc.bh_row = rw.bh_row;
         rc.kr = rw.kr;
         rc.gr = rw.gr;
-        for_each_posting(a, rw.fb, rw.fe, ws, &s_batch, &s_stop, [&](uint32_t c, uint32_t n, uint32_t m) {
-            const uint32_t old = atomicAdd(&tcv[c], n);  // counts are >= 1: old == 0 <=> first touch
-            if (old == 0) touched[atomicAdd(&s_touched, 1u)] = c;
-            atomicAdd(&inter[c], n < m ? n : m);
-            atomicAdd(&pcv[c], m);
-        });
+        for_each_posting(
+            a, rw.fb, rw.fm, rw.fe, ws, s_batch, &s_stop, [](uint32_t, uint32_t, uint32_t) -> bool { return false; },
+            [&](uint32_t c, uint32_t n, uint32_t m) {
+                const uint32_t old = atomicAdd(&tcv[c], n);  // counts are >= 1: old == 0 <=> first touch
+                if (old == 0) touched[atomicAdd(&s_touched, 1u)] = c;
+                atomicAdd(&inter[c], n < m ? n : m);
+                atomicAdd(&pcv[c], m);
+            });
         __threadfence();
         __syncthreads();
         const uint32_t nt = s_touched;
