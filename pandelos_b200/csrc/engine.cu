@@ -163,6 +163,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     }
     key_off[S] = N;
     if (N >= (1ull << 31)) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more k-mers (the reference's own int index limit)");
+    if (S >= (1u << 31)) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more genes");
     info.S = S;
     info.G = G;
     info.k = k;
@@ -182,6 +183,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     visited.assign(S, 0);
     fwd_ptr_h.assign((size_t)S + 1, 0);
     fwd_short_h.assign((size_t)S + 1, 0);
+    fwd_huge_h.assign((size_t)S + 1, 0);
 
     rt::stream_t st = rt::stream_create();
     uint64_t launches = 0;
@@ -283,10 +285,11 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         }
         info.U = U;
         post.alloc(U);
+        post_cnt.alloc(U);
         rt::DevBuf<uint32_t> rflag(U);
         if (opt.keep_sorted) ent_rank.alloc(U);
         PD_LAUNCH(ik::entries_kernel, blocks_for(U), 256, 0, st, (const uint64_t*)sorted, (const uint32_t*)ent_pos.p, U, N, seq_bits,
-                  post.p, rflag.p, opt.keep_sorted ? ent_rank.p : (uint64_t*)nullptr);
+                  post.p, post_cnt.p, rflag.p, opt.keep_sorted ? ent_rank.p : (uint64_t*)nullptr);
         launches++;
         rt::DevBuf<uint32_t> gexcl(U);
         prims::exclusive_scan_u32(rflag.p, gexcl.p, U, scratch.p, d_total.p, st, &launches);
@@ -308,13 +311,15 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         t_fwd.start();
         rt::DevBuf<uint32_t>& sflag = rflag;   // reuse
         rt::DevBuf<uint32_t>& sexcl = gexcl;   // reuse
-        rt::DevBuf<uint32_t> gene_cnt((size_t)S + 1), gene_short((size_t)S + 1);
+        rt::DevBuf<uint32_t> gene_cnt((size_t)S + 1), gene_short((size_t)S + 1), gene_huge((size_t)S + 1);
         rt::DevBuf<unsigned long long> d_visited(S);
         rt::zero(gene_cnt.p, sizeof(uint32_t) * ((size_t)S + 1), st);
         rt::zero(gene_short.p, sizeof(uint32_t) * ((size_t)S + 1), st);
+        rt::zero(gene_huge.p, sizeof(uint32_t) * ((size_t)S + 1), st);
         rt::zero(d_visited.p, sizeof(unsigned long long) * S, st);
-        PD_LAUNCH(ik::shared_mark_kernel, blocks_for(U), 256, 0, st, (const uint2*)post.p, (const uint32_t*)ent_gid.p,
-                  (const uint32_t*)grp_head.p, U, sflag.p, gene_cnt.p, gene_short.p, sk::kShortList, d_visited.p);
+        PD_LAUNCH(ik::shared_mark_kernel, blocks_for(U), 256, 0, st, (const uint32_t*)post.p, (const uint32_t*)ent_gid.p,
+                  (const uint32_t*)grp_head.p, U, sflag.p, gene_cnt.p, gene_short.p, sk::kShortList, gene_huge.p, sk::kHugeList,
+                  d_visited.p);
         launches++;
         prims::exclusive_scan_u32(sflag.p, sexcl.p, U, scratch.p, d_total.p, st, &launches);
         uint32_t R = 0;
@@ -327,12 +332,13 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         fwd_cnt.alloc(std::max<size_t>(R, 1));
         if (R) {
             rt::DevBuf<uint64_t> fk_a(R), fk_b(R);
-            PD_LAUNCH(ik::fwd_keys_kernel, blocks_for(U), 256, 0, st, (const uint2*)post.p, (const uint32_t*)sflag.p,
-                      (const uint32_t*)sexcl.p, (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, sk::kShortList, U, fk_a.p);
+            PD_LAUNCH(ik::fwd_keys_kernel, blocks_for(U), 256, 0, st, (const uint32_t*)post.p, (const uint32_t*)sflag.p,
+                      (const uint32_t*)sexcl.p, (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, sk::kShortList, sk::kHugeList,
+                      U, fk_a.p);
             launches++;
             scratch.ensure(prims::radix_tmp_words(R) + 16);
-            uint64_t* fsorted = prims::radix_sort_u64(fk_a.p, fk_b.p, R, 31, 32 + seq_bits, scratch.p, st, &launches);
-            PD_LAUNCH(ik::fwd_fill_kernel, blocks_for(R), 256, 0, st, (const uint64_t*)fsorted, R, (const uint2*)post.p,
+            uint64_t* fsorted = prims::radix_sort_u64(fk_a.p, fk_b.p, R, 31, 33 + seq_bits, scratch.p, st, &launches);
+            PD_LAUNCH(ik::fwd_fill_kernel, blocks_for(R), 256, 0, st, (const uint64_t*)fsorted, R, (const uint32_t*)post_cnt.p,
                       (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, fwd.p, fwd_cnt.p);
             launches++;
             rt::sync(st);
@@ -341,6 +347,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         rt::d2h(visited.data(), d_visited.p, sizeof(uint64_t) * S, st);
         rt::d2h(fwd_ptr_h.data(), fwd_ptr.p, sizeof(uint32_t) * ((size_t)S + 1), st);
         rt::d2h(fwd_short_h.data(), gene_short.p, sizeof(uint32_t) * S, st);
+        rt::d2h(fwd_huge_h.data(), gene_huge.p, sizeof(uint32_t) * S, st);
         rt::sync(st);
         t_fwd.stop();
         if (!opt.keep_sorted) {
@@ -349,6 +356,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         }
     } else {
         post.alloc(1);
+        post_cnt.alloc(1);
         fwd.alloc(1);
         fwd_cnt.alloc(1);
     }
@@ -386,6 +394,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
 namespace {
 
 static const int kMaxCtasPerSm = 16;
+static const int kLevels = 4;  // three first-try levels by row size + the retry level
 
 // side tables (score_kernels.cuh): keys empty, sums zero
 __global__ void __launch_bounds__(256) xtab_init_kernel(uint32_t* xtab, uint32_t ctas) {
@@ -394,53 +403,100 @@ __global__ void __launch_bounds__(256) xtab_init_kernel(uint32_t* xtab, uint32_t
         xtab[i] = (i % (5 * sk::kXSlots)) < sk::kXSlots ? sk::kEmpty : 0u;
 }
 
-// shared-memory budget of the three table levels; a table of H slots costs 8 H (keys, counters) + 2 * (3H/4) bytes
-// (touched list), so H = bytes / 9.5
-inline void level_smem(const Index& ix, size_t out[3]) {
-    size_t l1 = 64 * 1024;
-    if (ix.opt.hash_log2 > 0) l1 = (size_t)10 << ix.opt.hash_log2;
-    size_t top = ix.smem_optin > 8192 ? ix.smem_optin - 6144 : 40 * 1024;  // static scratch of the kernel is ~5.4 KB
-    if (const char* e = getenv("PD_SMEM_TOP")) {  // tests: shrink the largest table to force the dense path
-        size_t v = (size_t)atoll(e);
-        if (v >= 64) top = std::min(top, v);
-    }
-    l1 = std::min(l1, top);
-    out[0] = std::min<size_t>(16 * 1024, l1);
-    out[1] = l1;
-    out[2] = std::max(l1, std::min<size_t>(192 * 1024, top));
-}
-inline uint32_t slots_for(size_t bytes) {
-    uint32_t h = (uint32_t)(bytes * 2 / 19) & ~3u;
-    return std::min<uint32_t>(std::max<uint32_t>(h, 8), 65532);
-}
-inline size_t smem_for(uint32_t slots) { return (size_t)slots * 8 + (size_t)(slots * 3 / 4) * 2 + 16; }
-
-struct RowLists {
-    uint32_t begin[3];  // level-0 rows, level-1 rows
+// One table configuration of score_rows_kernel.  A row goes to the first level whose `max_cols` covers the row's
+// bound on distinct columns, min(total_visited, S); rows that overflow their table are re-run on the last level and
+// then, if need be, on the dense global path.
+struct Level {
+    uint32_t hbits;     // log2 hash slots
+    int threads;        // CTA size: 128, 256 or 512
+    uint32_t fcap;      // forward entries staged per segment
+    uint64_t max_cols;  // first-try rows: bound on distinct columns
 };
 
-void launch_rows(ScoreContext& c, sk::ScoreArgs a, size_t level_bytes, int cursor_id) {
+inline uint32_t log2_floor(uint64_t v) {
+    uint32_t b = 0;
+    while (v > 1) {
+        v >>= 1;
+        b++;
+    }
+    return b;
+}
+
+// Defaults: tables of 1 Ki / 4 Ki / 8 Ki slots tried by row size, 16 Ki slots for the retry.  pd_options.hash_log2
+// replaces the first-try ladder by one table of that size; PD_SMEM_TOP (tests) caps the bytes of the retry table.
+inline void levels_of(const Index& ix, Level lv[kLevels]) {
+    lv[0] = {10, 128, 256, 256};
+    lv[1] = {12, 256, 512, 1536};
+    lv[2] = {13, 512, 1024, ~0ull};
+    lv[3] = {14, 512, 1024, 0};
+    if (const char* e = getenv("PD_LEVELS")) {  // tuning: "hbits:threads:fcap:maxcols,..." for the four levels
+        unsigned h, t, f;
+        unsigned long long m;
+        int i = 0;
+        while (i < kLevels && sscanf(e, "%u:%u:%u:%llu", &h, &t, &f, &m) == 4) {
+            lv[i++] = {h, (int)t, f, m};
+            e = strchr(e, ',');
+            if (!e) break;
+            e++;
+        }
+        lv[2].max_cols = ~0ull;
+    }
+    if (ix.opt.hash_log2 > 0) {
+        const uint32_t hb = std::min<uint32_t>(std::max<uint32_t>((uint32_t)ix.opt.hash_log2, 5), 14);
+        lv[0] = {hb, 128, 256, 0};   // unused
+        lv[1] = {hb, 128, 256, 0};   // unused
+        lv[2] = {hb, hb >= 12 ? 256 : 128, 256, ~0ull};
+        lv[3] = {std::max<uint32_t>(hb, 14), 512, 1024, 0};
+    }
+    if (const char* e = getenv("PD_SMEM_TOP")) {  // tests: shrink the retry table to force the dense path
+        const size_t v = (size_t)atoll(e);
+        if (v >= 64) {
+            const uint32_t hb = std::max<uint32_t>(5, log2_floor(v / 8));
+            lv[3].hbits = std::min(lv[3].hbits, hb);
+            lv[3].threads = 128;
+            lv[3].fcap = 256;
+        }
+    }
+    for (int i = 0; i < kLevels; i++) {
+        // the finalize pass gives every warp a 32-aligned slice of the table
+        while (lv[i].threads > 128 && (1u << lv[i].hbits) < 32u * (lv[i].threads / 32)) lv[i].threads /= 2;
+        while (sk::score_smem_bytes(lv[i].hbits, lv[i].fcap, lv[i].threads) > ix.smem_optin && lv[i].hbits > 5) lv[i].hbits--;
+    }
+}
+
+template <int THREADS>
+void launch_rows_t(ScoreContext& c, sk::ScoreArgs& a, size_t smem) {
     Index& ix = *c.ix;
-    if (a.n_rows == 0) return;
-    a.slots = slots_for(level_bytes);
-    a.cap = a.slots * 3 / 4;
-    const size_t smem = smem_for(a.slots);
-    a.cursor = c.d_cursors.p + cursor_id;
-    rt::allow_smem(sk::score_rows_kernel, smem);
-    int occ = std::min(kMaxCtasPerSm, std::max(1, rt::occupancy(sk::score_rows_kernel, sk::kScoreThreads, smem)));
+    rt::allow_smem(sk::score_rows_kernel<THREADS>, smem);
+    int occ = std::min(kMaxCtasPerSm, std::max(1, rt::occupancy(sk::score_rows_kernel<THREADS>, THREADS, smem)));
     unsigned grid = (unsigned)std::min<uint64_t>(a.n_rows, (uint64_t)ix.sms * occ);
-    PD_LAUNCH(sk::score_rows_kernel, grid, sk::kScoreThreads, smem, c.st, a);
+    PD_LAUNCH(sk::score_rows_kernel<THREADS>, grid, THREADS, smem, c.st, a);
+}
+
+void launch_rows(ScoreContext& c, sk::ScoreArgs a, const Level& lv, int cursor_id) {
+    if (a.n_rows == 0) return;
+    a.hbits = lv.hbits;
+    a.fcap = lv.fcap;
+    a.cursor = c.d_cursors.p + cursor_id;
+    const size_t smem = sk::score_smem_bytes(lv.hbits, lv.fcap, lv.threads);
+    if (lv.threads >= 512) launch_rows_t<512>(c, a, smem);
+    else if (lv.threads >= 256) launch_rows_t<256>(c, a, smem);
+    else launch_rows_t<128>(c, a, smem);
     c.stats.launches++;
 }
 
+struct RowLists {
+    uint32_t begin[kLevels];  // rows of first-try level i: [begin[i], begin[i+1])
+};
+
 }  // namespace
 
-// Scores the `n` rows of c.h_rows (already ordered into the two lists of `rl`).  Returns the number of non-zero
+// Scores the `n` rows of c.h_rows (already ordered into the lists of `rl`).  Returns the number of non-zero
 // cells; cells beyond c.cap are counted but not stored (caller grows and re-runs).
 static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32_t* d_bh, uint32_t* d_colmax, uint64_t* pairs) {
     Index& ix = *c.ix;
-    size_t lv[3];
-    level_smem(ix, lv);
+    Level lv[kLevels];
+    levels_of(ix, lv);
     const uint32_t want_ctas = (uint32_t)ix.sms * kMaxCtasPerSm;
     if (c.xtab_ctas < want_ctas) {
         c.d_xtab.alloc((size_t)want_ctas * 5 * sk::kXSlots);
@@ -455,8 +511,8 @@ static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32
 
     sk::ScoreArgs a;
     memset(&a, 0, sizeof(a));
-    a.post = ix.post.p; a.fwd = ix.fwd.p; a.fwd_cnt = ix.fwd_cnt.p; a.meta = ix.meta.p;
-    a.G = ix.info.G; a.thr = ix.thr; a.k2 = 2u * (uint32_t)ix.info.k;
+    a.post = ix.post.p; a.post_cnt = ix.post_cnt.p; a.fwd = ix.fwd.p; a.fwd_cnt = ix.fwd_cnt.p; a.meta = ix.meta.p;
+    a.G = ix.info.G; a.k2 = 2u * (uint32_t)ix.info.k;
     a.o_score = c.d_score.p; a.o_perc = c.d_perc.p; a.o_trperc = c.d_trperc.p;
     a.o_row = c.d_row.p; a.o_col = c.d_col.p; a.o_g1 = c.d_g1.p; a.o_g2 = c.d_g2.p;
     a.cell_cap = c.cap;
@@ -467,7 +523,7 @@ static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32
     a.xtab = c.d_xtab.p;
 
     rt::event_record(c.ev_k0, c.st);
-    for (int level = 0; level < 2; level++) {
+    for (int level = 0; level < kLevels - 1; level++) {
         sk::ScoreArgs b = a;
         b.rows = c.d_rows.p + rl.begin[level];
         b.n_rows = rl.begin[level + 1] - rl.begin[level];
@@ -477,7 +533,7 @@ static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32
     }
     rt::d2h(c.h_counters.p, c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
     rt::sync(c.st);
-    // level 2: rows that overflowed the level-1 table
+    // retry level: rows that overflowed their first table
     if (c.h_counters.p[2]) {
         c.stats.retry_rows += c.h_counters.p[2];
         sk::ScoreArgs b = a;
@@ -485,7 +541,7 @@ static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32
         b.n_rows = (uint32_t)c.h_counters.p[2];
         b.overflow_rows = c.d_ovf.p + n;
         b.n_overflow = c.d_counters.p + 3;
-        launch_rows(c, b, lv[2], 2);
+        launch_rows(c, b, lv[kLevels - 1], kLevels - 1);
         rt::d2h(c.h_counters.p, c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
         rt::sync(c.st);
         // last resort: dense global accumulators
@@ -500,11 +556,11 @@ static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32
             sk::ScoreArgs b2 = a;
             b2.rows = c.d_ovf.p + n;
             b2.n_rows = nr;
-            b2.cursor = c.d_cursors.p + 3;
+            b2.cursor = c.d_cursors.p + kLevels;
             sk::DenseArgs d;
             d.S = ix.info.S;
             d.acc = c.d_dense.p;
-            PD_LAUNCH(sk::score_rows_dense_kernel, grid, sk::kScoreThreads, 0, c.st, b2, d);
+            PD_LAUNCH(sk::score_rows_dense_kernel, grid, sk::kDenseThreads, 0, c.st, b2, d);
             c.stats.launches++;
             c.stats.fallback_rows += nr;
             rt::d2h(c.h_counters.p, c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
@@ -517,16 +573,20 @@ static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32
     return c.h_counters.p[0];
 }
 
-// Builds the row descriptors of the `n` rows gene_at(i) (best-hit row i) in c.h_rows, level-0 rows first.
+// Builds the row descriptors of the `n` rows gene_at(i) (best-hit row i) in c.h_rows, grouped by first-try level.
 template <class F>
 static RowLists classify_rows(ScoreContext& c, uint32_t n, F gene_at, uint64_t* lookups, uint64_t* fwd_entries) {
     Index& ix = *c.ix;
-    size_t lv[3];
-    level_smem(ix, lv);
+    Level lv[kLevels];
+    levels_of(ix, lv);
     c.h_rows.ensure(std::max<uint32_t>(n, 1));
-    const uint64_t cap0 = slots_for(lv[0]) * 3 / 4;
-    auto level_of = [&](uint32_t g) { return std::min<uint64_t>(ix.visited[g], ix.info.S) <= cap0 ? 0 : 1; };
-    uint32_t cnt[2] = {0, 0};
+    auto level_of = [&](uint32_t g) {
+        const uint64_t cols = std::min<uint64_t>(ix.visited[g], ix.info.S);
+        for (int l = 0; l < kLevels - 2; l++)
+            if (cols <= lv[l].max_cols) return l;
+        return kLevels - 2;
+    };
+    uint32_t cnt[kLevels] = {0, 0, 0, 0};
     uint64_t lk = 0, fe = 0;
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t g = gene_at(i);
@@ -536,10 +596,12 @@ static RowLists classify_rows(ScoreContext& c, uint32_t n, F gene_at, uint64_t* 
     }
     *fwd_entries = fe;
     RowLists rl;
+    uint32_t cur[kLevels];
     rl.begin[0] = 0;
-    rl.begin[1] = cnt[0];
-    rl.begin[2] = cnt[0] + cnt[1];
-    uint32_t cur[2] = {rl.begin[0], rl.begin[1]};
+    for (int l = 0; l < kLevels - 1; l++) {
+        cur[l] = rl.begin[l];
+        rl.begin[l + 1] = rl.begin[l] + cnt[l];
+    }
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t g = gene_at(i);
         sk::RowDesc d;
@@ -548,9 +610,9 @@ static RowLists classify_rows(ScoreContext& c, uint32_t n, F gene_at, uint64_t* 
         d.fb = ix.fwd_ptr_h[g];
         d.fe = ix.fwd_ptr_h[g + 1];
         d.fm = d.fb + ix.fwd_short_h[g];
+        d.fh = d.fe - ix.fwd_huge_h[g];
         d.kr = ix.kseq[g];
         d.gr = ix.genome_of[g];
-        d.pad1 = 0;
         c.h_rows.p[cur[level_of(g)]++] = d;
     }
     *lookups = lk;
@@ -707,14 +769,14 @@ void Index::entries(uint64_t* rank, uint32_t* seq, uint32_t* count, uint32_t* gs
     if (!U) return;
     if ((rank || gs || gl) && !opt.keep_sorted) throw Error(PD_ERR_INVALID, "pd_entries: ranks and groups need pd_options.keep_sorted");
     rt::stream_t st = rt::stream_create();
-    if (seq || count) {
-        std::vector<uint2> h(U);
-        rt::d2h(h.data(), post.p, sizeof(uint2) * U, st);
+    if (seq) {
+        rt::d2h(seq, post.p, sizeof(uint32_t) * U, st);
         rt::sync(st);
-        for (uint32_t e = 0; e < U; e++) {
-            if (seq) seq[e] = h[e].x;
-            if (count) count[e] = h[e].y;
-        }
+        for (uint32_t e = 0; e < U; e++) seq[e] &= 0x7FFFFFFFu;
+    }
+    if (count) {
+        rt::d2h(count, post_cnt.p, sizeof(uint32_t) * U, st);
+        rt::sync(st);
     }
     if (rank) {
         rt::d2h(rank, ent_rank.p, sizeof(uint64_t) * U, st);

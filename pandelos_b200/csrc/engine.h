@@ -22,7 +22,8 @@ struct Index {
     size_t smem_optin = 0;
 
     // device index
-    rt::DevBuf<uint2> post;
+    rt::DevBuf<uint32_t> post;       // column gene | bit 31 (count > 1)
+    rt::DevBuf<uint32_t> post_cnt;
     rt::DevBuf<uint2> fwd;
     rt::DevBuf<uint32_t> fwd_cnt;
     rt::DevBuf<uint32_t> fwd_ptr;
@@ -37,6 +38,7 @@ struct Index {
     std::vector<uint64_t> visited;
     std::vector<uint32_t> fwd_ptr_h;    // S+1
     std::vector<uint32_t> fwd_short_h;  // per gene: forward entries whose posting list is short (they come first)
+    std::vector<uint32_t> fwd_huge_h;   // per gene: forward entries whose posting list is huge (they come last)
     std::vector<uint32_t> genome_ptr;   // G+1
     std::vector<uint32_t> genome_rows;  // genes grouped by genome, input order inside (genome_sequences, library.cpp:245)
 

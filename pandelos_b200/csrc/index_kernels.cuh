@@ -9,11 +9,12 @@
 //   fwd_*_kernel          per-gene forward lists + cost model      library.cpp:314-328
 //
 // HBM layout produced (all SoA, 32-bit indices; the reference's 16-B kmer_rank / 24-B kmers_range records are gone):
-//   post[U]     uint2 (seq, count)     entries sorted by (rank, seq): the posting lists, group after group
-//   fwd[R]      uint2 (group start, group length | own-count>1 flag) one per (gene, shared k-mer), genes ascending, ranks ascending
+//   post[U]     uint32 seq | bit 31 (count > 1)   entries sorted by (rank, seq): the posting lists, group after group
+//   post_cnt[U] uint32 count                      read by the scoring kernels only where bit 31 is set (U/N > 0.999: rare)
+//   fwd[R]      uint2 (group start, group length | own-count>1 flag) one per (gene, shared k-mer), genes ascending;
+//               inside a gene: short posting lists first, then long, then huge ones, ranks ascending in each class
 //   fwd_cnt[R]  uint32 the gene's own multiplicity of that k-mer
-//               (a gene's short lists first, then its long ones: fwd_mid[S] is the split)
-//   fwd_ptr[S+1], meta[S] = (kseq_len, genome), visited[S] (uint64)
+//   fwd_ptr[S+1], gene_short[S], gene_huge[S], meta[S] = (kseq_len, genome), visited[S] (uint64)
 #pragma once
 
 #include "pd_rt.h"
@@ -99,15 +100,18 @@ __global__ void __launch_bounds__(256) head_scatter_kernel(const uint64_t* __res
 // (library.cpp:300-306: at the last entry the open run [start, i+1) is closed whatever its rank) means the last
 // entry never opens a group of its own unless it is the only entry.
 __global__ void __launch_bounds__(256) entries_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ent_pos,
-                                                       uint32_t U, uint64_t N, int seq_bits, uint2* __restrict__ post,
-                                                       uint32_t* __restrict__ rflag, uint64_t* __restrict__ ent_rank) {
+                                                       uint32_t U, uint64_t N, int seq_bits, uint32_t* __restrict__ post,
+                                                       uint32_t* __restrict__ post_cnt, uint32_t* __restrict__ rflag,
+                                                       uint64_t* __restrict__ ent_rank) {
     const uint32_t e = blockIdx.x * 256u + threadIdx.x;
     if (e >= U) return;
     const uint32_t p = ent_pos[e];
     const uint32_t pn = (e + 1 < U) ? ent_pos[e + 1] : (uint32_t)N;
     const uint64_t key = keys[p];
     const uint64_t rank = key >> seq_bits;
-    post[e] = make_uint2((uint32_t)(key & ((1ull << seq_bits) - 1ull)), pn - p);
+    const uint32_t cnt = pn - p;
+    post[e] = (uint32_t)(key & ((1ull << seq_bits) - 1ull)) | (cnt > 1 ? 0x80000000u : 0u);
+    post_cnt[e] = cnt;
     uint32_t f;
     if (e == 0)
         f = 1;
@@ -132,50 +136,55 @@ __global__ void __launch_bounds__(256) group_heads_kernel(const uint32_t* __rest
 
 // per entry in a shared group (length >= 2): mark it, count it for its gene, add the group length to the gene's
 // cost (computation_costs[].total_visited, library.cpp:327).
-__global__ void __launch_bounds__(256) shared_mark_kernel(const uint2* __restrict__ post, const uint32_t* __restrict__ ent_gid,
+__global__ void __launch_bounds__(256) shared_mark_kernel(const uint32_t* __restrict__ post, const uint32_t* __restrict__ ent_gid,
                                                            const uint32_t* __restrict__ grp_head, uint32_t U,
                                                            uint32_t* __restrict__ sflag, uint32_t* __restrict__ gene_cnt,
                                                            uint32_t* __restrict__ gene_short, uint32_t short_max,
+                                                           uint32_t* __restrict__ gene_huge, uint32_t huge_min,
                                                            unsigned long long* __restrict__ visited) {
     const uint32_t e = blockIdx.x * 256u + threadIdx.x;
     if (e >= U) return;
     const uint32_t g = ent_gid[e];
     const uint32_t gl = grp_head[g + 1] - grp_head[g];
-    const uint2 p = post[e];
+    const uint32_t gene = post[e] & 0x7FFFFFFFu;
     const uint32_t s = gl >= 2 ? 1u : 0u;
     sflag[e] = s;
     if (s) {
-        atomicAdd(&gene_cnt[p.x], 1u);
-        if (gl <= short_max) atomicAdd(&gene_short[p.x], 1u);
-        atomicAdd(&visited[p.x], (unsigned long long)gl);
+        atomicAdd(&gene_cnt[gene], 1u);
+        if (gl <= short_max) atomicAdd(&gene_short[gene], 1u);
+        if (gl > huge_min) atomicAdd(&gene_huge[gene], 1u);
+        atomicAdd(&visited[gene], (unsigned long long)gl);
     }
 }
 
-// compact the shared entries into sort keys (gene << 32 | long-list flag << 31 | entry): sorted on the gene AND the
-// flag, a gene's forward list holds its short posting lists first, then the long ones, ranks ascending in each part
-__global__ void __launch_bounds__(256) fwd_keys_kernel(const uint2* __restrict__ post, const uint32_t* __restrict__ sflag,
+// compact the shared entries into sort keys (gene << 33 | list class << 31 | entry): sorted on the gene AND the
+// class, a gene's forward list holds its short posting lists first, then the long ones, then the huge ones, ranks
+// ascending in each part
+__global__ void __launch_bounds__(256) fwd_keys_kernel(const uint32_t* __restrict__ post, const uint32_t* __restrict__ sflag,
                                                         const uint32_t* __restrict__ excl, const uint32_t* __restrict__ ent_gid,
-                                                        const uint32_t* __restrict__ grp_head, uint32_t short_max, uint32_t U,
-                                                        uint64_t* __restrict__ fkeys) {
+                                                        const uint32_t* __restrict__ grp_head, uint32_t short_max, uint32_t huge_min,
+                                                        uint32_t U, uint64_t* __restrict__ fkeys) {
     const uint32_t e = blockIdx.x * 256u + threadIdx.x;
     if (e >= U) return;
     if (sflag[e]) {
         const uint32_t g = ent_gid[e];
         const uint32_t gl = grp_head[g + 1] - grp_head[g];
-        fkeys[excl[e]] = ((uint64_t)post[e].x << 32) | (gl > short_max ? 0x80000000ull : 0ull) | e;
+        const uint64_t cls = gl <= short_max ? 0ull : (gl > huge_min ? 2ull : 1ull);
+        fkeys[excl[e]] = ((uint64_t)(post[e] & 0x7FFFFFFFu) << 33) | (cls << 31) | e;
     }
 }
 
 // forward lists from the gene-sorted keys; bit 31 of the length flags an own multiplicity > 1 (then fwd_cnt is read)
-__global__ void __launch_bounds__(256) fwd_fill_kernel(const uint64_t* __restrict__ fkeys, uint32_t R, const uint2* __restrict__ post,
-                                                        const uint32_t* __restrict__ ent_gid, const uint32_t* __restrict__ grp_head,
-                                                        uint2* __restrict__ fwd, uint32_t* __restrict__ fwd_cnt) {
+__global__ void __launch_bounds__(256) fwd_fill_kernel(const uint64_t* __restrict__ fkeys, uint32_t R,
+                                                        const uint32_t* __restrict__ post_cnt, const uint32_t* __restrict__ ent_gid,
+                                                        const uint32_t* __restrict__ grp_head, uint2* __restrict__ fwd,
+                                                        uint32_t* __restrict__ fwd_cnt) {
     const uint32_t j = blockIdx.x * 256u + threadIdx.x;
     if (j >= R) return;
     const uint32_t e = (uint32_t)fkeys[j] & 0x7FFFFFFFu;
     const uint32_t g = ent_gid[e];
     const uint32_t gs = grp_head[g];
-    const uint32_t cnt = post[e].y;
+    const uint32_t cnt = post_cnt[e];
     fwd[j] = make_uint2(gs, (grp_head[g + 1] - gs) | (cnt > 1 ? 0x80000000u : 0u));
     fwd_cnt[j] = cnt;
 }

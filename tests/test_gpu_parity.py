@@ -58,6 +58,28 @@ def test_low_complexity_multiplicities():
     assert st["cells"] > 0
 
 
+def test_huge_posting_lists():
+    """A poly-A k-mer shared by more genes than kHugeList (2048): the CTA-wide walk of one list, plus rows whose
+    distinct columns overflow the first table and are re-run on the retry level."""
+    w = synth.generate(8, 900, 100.0, 0.1, 66, low_complexity=0.9)
+    data = native.PangeneIData(w.residues, w.offsets, w.genome_of)
+    pn = native.PangeneNative(4, data, keep_sorted=True)
+    _, _, _, _, gl = pn.entries()
+    pn.close()
+    assert gl.max() > 2048
+    st = check_workload(w, 4, genomes=[0, 3, 5], index=False)
+    assert st["cells"] > 0
+
+
+def test_long_genes_multi_segment_forward_lists():
+    """Genes with more shared k-mers than one staged segment of forward entries (fcap = 1024 at the largest level)."""
+    w = synth.generate(5, 60, 2500.0, 0.05, 67)
+    st = check_workload(w, 5)
+    assert st["cells"] > 0
+    kl = np.diff(w.offsets.astype(np.int64))
+    assert kl.max() > 3000
+
+
 def test_overflow_levels_and_dense_path(monkeypatch):
     monkeypatch.setenv("PD_SMEM_TOP", "2048")
     w = synth.generate(6, 200, 150.0, 0.1, 62, low_complexity=0.3)
