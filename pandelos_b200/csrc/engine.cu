@@ -163,7 +163,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     }
     key_off[S] = N;
     if (N >= (1ull << 31)) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more k-mers (the reference's own int index limit)");
-    if (S >= (1u << 31)) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more genes");
+    if (S >= 0x7FFFFFFFu) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more genes");
     info.S = S;
     info.G = G;
     info.k = k;

@@ -40,7 +40,10 @@ static const uint32_t kHugeList = 2048;         // lists longer than this are wa
 static const uint32_t kXSlots = 2048;           // side-table slots per CTA (global memory)
 static const uint32_t kXCap = kXSlots * 3 / 4;
 static const uint32_t kProbeLimit = 160;        // probes after which a row is declared too big for its table
-static const int kItems = 4;                    // postings per lane per round
+static const uint32_t kNone = 0x7FFFFFFFu;      // "no posting" in a lane's item (gene ids are < 2^31 - 1)
+static const int kItems = 8;                    // postings per lane per round of a long list
+static const int kItemsA = 4;                   // ... of the flattened short lists
+static const uint32_t kQueue = 64;              // per-warp queue of postings that missed their home bucket
 static const int kDenseThreads = 256;
 
 struct __align__(16) RowDesc {  // 32 B, built on the host per call
@@ -107,6 +110,35 @@ __device__ __forceinline__ void cp_async_wait_all() {
 #endif
 }
 
+// Shared-memory accesses of the hot loop by 32-bit shared-window address (no generic-address arithmetic per access).
+#ifdef PD_EMU
+typedef uintptr_t saddr_t;
+__device__ __forceinline__ saddr_t smem_addr(const void* p) { return reinterpret_cast<uintptr_t>(p); }
+__device__ __forceinline__ uint32_t lds_u32(saddr_t a) { return *reinterpret_cast<volatile uint32_t*>(a); }
+__device__ __forceinline__ uint4 lds_v4(saddr_t a) { return *reinterpret_cast<uint4*>(a); }
+__device__ __forceinline__ uint32_t atoms_cas(saddr_t a, uint32_t cmp, uint32_t val) { return atomicCAS(reinterpret_cast<uint32_t*>(a), cmp, val); }
+__device__ __forceinline__ void reds_inc(saddr_t a) { atomicAdd(reinterpret_cast<uint32_t*>(a), 1u); }
+#else
+typedef uint32_t saddr_t;
+__device__ __forceinline__ saddr_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t lds_u32(saddr_t a) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds_v4(saddr_t a) {
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t atoms_cas(saddr_t a, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;\n" : "=r"(old) : "r"(a), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ void reds_inc(saddr_t a) { asm volatile("red.shared.add.u32 [%0], 1;\n" ::"r"(a) : "memory"); }
+#endif
+
 // Validity gate (library.cpp:497-500) in integers:
 //   (float)pc / (float)K >= 1.0f / (2.0f * (float)k)   <=>   2k * pc >= K        for K < 2^20
 // (=>) division and reciprocal are correctly rounded and rounding is monotonic; (<=) if 2k*pc <= K - 1 the two reals
@@ -117,42 +149,51 @@ __device__ __forceinline__ bool gate(uint32_t k2, uint32_t pc, uint32_t tc, uint
     return (k2 * pc >= kr) || (k2 * tc >= kc);
 }
 
-struct Tab {
-    uint32_t* keys;
-    uint32_t* cnt;
-    uint32_t mask;
-    uint32_t shift;  // 32 - hbits
-    uint32_t limit;  // probe limit
-    // side table
-    uint32_t* xkeys;
-    uint32_t* xv0;
-    uint32_t* xv1;
-    uint32_t* xv2;
-    uint32_t* xtouched;
-    uint32_t* s_nx;
-    volatile int* s_over;
+// The accumulator: H slots in buckets of 4 (one 16-B shared-memory load reads a column's whole home bucket); a key
+// lives in the first free slot found by linear probing from the base of its home bucket.
+struct RowCtl {  // per-row control words in shared memory
+    uint32_t nx;      // side-table entries in use
+    int over;         // the row does not fit: stop, hand it to the next level
+    uint32_t ctr[2];  // work counters: batches of short lists, long lists
 };
 
-__device__ __forceinline__ uint32_t home_slot(const Tab& t, uint32_t c) { return (c * 0x9E3779B1u) >> t.shift; }
+struct Tab {
+    uint32_t* keys;   // cnt = keys + mask + 1
+    saddr_t keys_sa;  // the same two arrays by shared-window address
+    saddr_t cnt_sa;
+    uint32_t mask;
+    uint32_t shift;  // 32 - (hbits - 2): hash -> bucket
+    uint32_t limit;  // probe limit
+    uint32_t* xbase;  // side table: keys, d_inter, d_pc, d_tc, touched list (kXSlots each)
+    RowCtl* ctl;
+    __device__ __forceinline__ uint32_t* cnt() const { return keys + mask + 1; }
+    __device__ __forceinline__ uint32_t* xkeys() const { return xbase; }
+    __device__ __forceinline__ uint32_t* xv(int i) const { return xbase + (1 + i) * kXSlots; }
+    __device__ __forceinline__ uint32_t* xtouched() const { return xbase + 4 * kXSlots; }
+    __device__ __forceinline__ volatile int* over() const { return &ctl->over; }
+};
+
+// first slot of the column's home bucket
+__device__ __forceinline__ uint32_t home_slot(const Tab& t, uint32_t c) { return ((c * 0x9E3779B1u) >> t.shift) << 2; }
 
 __device__ __forceinline__ uint32_t x_find_or_insert(const Tab& t, uint32_t c) {
     uint32_t h = __umulhi(c * 0x85EBCA6Bu, kXSlots);
     for (uint32_t probe = 0; probe < kXSlots; probe++) {
-        const uint32_t k = *(volatile uint32_t*)(t.xkeys + h);
+        const uint32_t k = *(volatile uint32_t*)(t.xkeys() + h);
         if (k == c) return h;
         if (k == kEmpty) {
-            const uint32_t old = atomicCAS(t.xkeys + h, kEmpty, c);
+            const uint32_t old = atomicCAS(t.xkeys() + h, kEmpty, c);
             if (old == kEmpty) {
-                const uint32_t xi = atomicAdd(t.s_nx, 1u);
-                if (xi < kXCap) t.xtouched[xi] = h;
-                else *t.s_over = 1;
+                const uint32_t xi = atomicAdd(&t.ctl->nx, 1u);
+                if (xi < kXCap) t.xtouched()[xi] = h;
+                else *t.over() = 1;
                 return h;
             }
             if (old == c) return h;
         }
         h = (h + 1 == kXSlots) ? 0 : h + 1;
     }
-    *t.s_over = 1;
+    *t.over() = 1;
     return kEmpty;
 }
 
@@ -169,109 +210,137 @@ __device__ __noinline__ void add_general(const Tab& t, uint32_t c, uint32_t n, u
         if (k == c) break;
         h = (h + 1) & t.mask;
         if (++probes > t.limit) {
-            *t.s_over = 1;
+            *t.over() = 1;
             return;
         }
     }
-    atomicAdd(&t.cnt[h], 1u);
+    atomicAdd(&t.cnt()[h], 1u);
     if ((n | m) > 1u) {  // corrections for the repeated k-mer go to the side table
-        atomicOr(&t.cnt[h], kFlag);
+        atomicOr(&t.cnt()[h], kFlag);
         const uint32_t xs = x_find_or_insert(t, c);
         if (xs != kEmpty) {
             const uint32_t mn = n < m ? n : m;
-            if (mn > 1) atomicAdd(&t.xv0[xs], mn - 1);
-            if (m > 1) atomicAdd(&t.xv1[xs], m - 1);
-            if (n > 1) atomicAdd(&t.xv2[xs], n - 1);
+            if (mn > 1) atomicAdd(&t.xv(0)[xs], mn - 1);
+            if (m > 1) atomicAdd(&t.xv(1)[xs], m - 1);
+            if (n > 1) atomicAdd(&t.xv(2)[xs], n - 1);
         }
     }
 }
 
-// kItems postings per lane, all with n = m = 1 (c[u] == kEmpty: no posting).
-//   step 1  branch-free: the column already sits in its home slot -> one shared-memory load, one atomic
-//   step 2  what is left (first visit of a column in this row, or a displaced key): a per-lane state machine walks
-//           its postings one probe per iteration, so lanes with work left never wait for each other's probes
-__device__ __forceinline__ void add_ones(const Tab& t, const uint32_t (&c)[kItems]) {
-    uint32_t h[kItems], k[kItems];
-#pragma unroll
-    for (int u = 0; u < kItems; u++) h[u] = home_slot(t, c[u]);
-#pragma unroll
-    for (int u = 0; u < kItems; u++) k[u] = *(volatile uint32_t*)(t.keys + h[u]);
-    unsigned miss = 0;
-#pragma unroll
-    for (int u = 0; u < kItems; u++) {
-        if (c[u] != kEmpty) {
-            if (k[u] == c[u]) atomicAdd(&t.cnt[h[u]], 1u);
-            else miss |= 1u << u;
+// ---- accumulate, the common case: postings with n = m = 1
+//
+// One "item" is one posting per lane (c == kNone: no posting).  The branch-free step: the column already sits in its
+// home bucket -> one 16-B shared-memory load, four compares, one atomic.  What is left (first visit of a column in
+// this row, or a key pushed out of its bucket) is pushed to a small per-warp queue and probed / inserted later, 32
+// at a time with every lane busy, instead of on the spot by the few lanes concerned.
+struct WarpQueue {
+    uint32_t* q;  // kQueue entries of shared memory
+    uint32_t head, tail;
+};
+
+// probe / insert from the home bucket on, then count
+__device__ __forceinline__ void probe_add(const Tab& t, uint32_t cur) {
+    if (cur == kNone) return;
+    uint32_t hh = home_slot(t, cur), probes = 0;
+    for (;;) {
+        uint32_t kk = lds_u32(t.keys_sa + hh * 4u);
+        if (kk == kEmpty) {
+            const uint32_t old = atoms_cas(t.keys_sa + hh * 4u, kEmpty, cur);
+            kk = (old == kEmpty) ? cur : old;
+        }
+        if (kk == cur) {
+            reds_inc(t.cnt_sa + hh * 4u);
+            return;
+        }
+        hh = (hh + 1) & t.mask;
+        if (++probes > t.limit) {
+            *t.over() = 1;
+            return;
         }
     }
-    if (miss) {
-        uint32_t cur = kEmpty, hh = 0, probes = 0;
-        for (;;) {
-            if (cur == kEmpty) {
-                if (!miss) break;
-                const int u = __ffs((int)miss) - 1;
-                miss &= miss - 1;
-                cur = c[0];
-                hh = h[0];
-#pragma unroll
-                for (int v = 1; v < kItems; v++)
-                    if (u == v) {
-                        cur = c[v];
-                        hh = h[v];
-                    }
-                probes = 0;
-            }
-            uint32_t kk = *(volatile uint32_t*)(t.keys + hh);
-            if (kk == kEmpty) {
-                const uint32_t old = atomicCAS(t.keys + hh, kEmpty, cur);
-                kk = (old == kEmpty) ? cur : old;
-            }
-            if (kk == cur) {
-                atomicAdd(&t.cnt[hh], 1u);
-                cur = kEmpty;
-            } else {
-                hh = (hh + 1) & t.mask;
-                if (++probes > t.limit) {
-                    *t.s_over = 1;
-                    cur = kEmpty;
-                }
-            }
-        }
+}
+
+__device__ __forceinline__ void queue_drain32(const Tab& t, WarpQueue& wq) {
+    const unsigned lane = threadIdx.x & 31;
+    __syncwarp();
+    const uint32_t n = wq.tail - wq.head;
+    const uint32_t cur = lane < n ? wq.q[(wq.head + lane) & (kQueue - 1)] : kNone;
+    wq.head += n < 32u ? n : 32u;
+    probe_add(t, cur);
+    __syncwarp();
+}
+__device__ __forceinline__ void queue_flush(const Tab& t, WarpQueue& wq) {
+    while (wq.tail != wq.head) queue_drain32(t, wq);
+}
+
+// home-bucket slot of c given the bucket's four keys: byte offset 0/4/8/12, or 16 = not there
+__device__ __forceinline__ uint32_t bucket_find(const uint4& kb, uint32_t c) {
+    uint32_t off = 16u;
+    off = (kb.w == c) ? 12u : off;
+    off = (kb.z == c) ? 8u : off;
+    off = (kb.y == c) ? 4u : off;
+    off = (kb.x == c) ? 0u : off;
+    return off;
+}
+
+__device__ __forceinline__ void queue_push(const Tab& t, WarpQueue& wq, bool missed, uint32_t c) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned mb = __ballot_sync(0xffffffffu, missed);
+    if (mb) {
+        if (missed) wq.q[(wq.tail + __popc(mb & ((1u << lane) - 1u))) & (kQueue - 1)] = c;
+        wq.tail += __popc(mb);
+        if (wq.tail - wq.head >= 32u) queue_drain32(t, wq);
     }
+}
+
+// two items at a time: both bucket loads are in flight before either is compared
+__device__ __forceinline__ void items_add2(const Tab& t, WarpQueue& wq, uint32_t c0, uint32_t c1) {
+    const uint32_t h0 = home_slot(t, c0) * 4u, h1 = home_slot(t, c1) * 4u;
+    const uint4 k0 = lds_v4(t.keys_sa + h0);
+    const uint4 k1 = lds_v4(t.keys_sa + h1);
+    const uint32_t o0 = bucket_find(k0, c0), o1 = bucket_find(k1, c1);
+    const bool hit0 = o0 != 16u, hit1 = o1 != 16u;  // kNone is never a key: no hit
+    if (hit0) reds_inc(t.cnt_sa + h0 + o0);
+    if (hit1) reds_inc(t.cnt_sa + h1 + o1);
+    queue_push(t, wq, !hit0 && c0 != kNone, c0);
+    queue_push(t, wq, !hit1 && c1 != kNone, c1);
 }
 
 // Per-warp scratch of the flattened walk over short lists
 struct WarpScratch {
-    uint32_t bits[kShortList + kItems];  // 32 lists x kShortList postings = 2048 marks (+ the words a round reads ahead)
+    uint32_t bits[kShortList + kItemsA];  // 32 lists x kShortList postings = 2048 marks (+ the words a round reads ahead)
     uint32_t pre[32];
+    uint32_t queue[kQueue];
 };
 
-// One round of a list walk: postings pl[p0 + 32 u + lane], u < kItems, of a list of gl postings whose k-mer the row
-// holds mj times; base = index of pl[0] in the posting array (for post_cnt).
-__device__ __forceinline__ void list_round(const ScoreArgs& a, const Tab& t, const uint32_t* __restrict__ pl, uint32_t base,
-                                           uint32_t p0, uint32_t gl, uint32_t mj) {
+// A list walk in rounds of kItems x 32 consecutive postings: lane l holds postings p0 + 32 u + l, u < kItems, in e[u].
+// round_step consumes e pair by pair and refills each pair at once with the NEXT round's postings (list `nq`,
+// `nrem` postings from this lane's first to that list's end; nrem <= 0: nothing), so kItems loads per warp stay in
+// flight while the table is updated.  cnt = postings in this round (uniform), the row holds this list's k-mer mj
+// times; pos = index of this round's first posting in the posting array (for post_cnt).
+__device__ __forceinline__ void round_step(const ScoreArgs& a, const Tab& t, WarpQueue& wq, uint32_t (&e)[kItems], uint32_t cnt,
+                                           uint32_t pos, uint32_t mj, const uint32_t* __restrict__ nq, int nrem) {
     const unsigned lane = threadIdx.x & 31;
-    uint32_t e[kItems];
 #pragma unroll
-    for (int u = 0; u < kItems; u++) {
-        const uint32_t p = p0 + 32u * u + lane;
-        e[u] = p < gl ? pl[p] : kEmpty;
-    }
-    // bit 31: a repeated k-mer (or no posting at all); the row's own repeat count is uniform over the list
-    uint32_t any = 0;
-#pragma unroll
-    for (int u = 0; u < kItems; u++) any |= e[u];
-    if ((any & kMulti) || mj > 1) {
-#pragma unroll
-        for (int u = 0; u < kItems; u++) {
-            if (e[u] != kEmpty && ((e[u] & kMulti) || mj > 1)) {
-                const uint32_t n = (e[u] & kMulti) ? a.post_cnt[base + p0 + 32u * u + lane] : 1u;
-                add_general(t, e[u] & ~kMulti, n, mj);
-                e[u] = kEmpty;
+    for (int u = 0; u < kItems; u += 2) {
+        uint32_t c0 = e[u], c1 = e[u + 1];
+        e[u] = nrem > 32 * u ? nq[32 * u] : kNone;
+        e[u + 1] = nrem > 32 * (u + 1) ? nq[32 * (u + 1)] : kNone;
+        if (32u * u < cnt) {  // uniform: the tail of a list does not pay for empty items
+            // bit 31: a repeated k-mer; the row's own repeat count is uniform over the list
+            if (((c0 | c1) & kMulti) || mj > 1) {
+                if (c0 != kNone && ((c0 & kMulti) || mj > 1)) {
+                    add_general(t, c0 & ~kMulti, (c0 & kMulti) ? a.post_cnt[pos + 32u * u + lane] : 1u, mj);
+                    c0 = kNone;
+                }
+                if (c1 != kNone && ((c1 & kMulti) || mj > 1)) {
+                    add_general(t, c1 & ~kMulti, (c1 & kMulti) ? a.post_cnt[pos + 32u * (u + 1) + lane] : 1u, mj);
+                    c1 = kNone;
+                }
             }
+            items_add2(t, wq, c0, c1);
         }
     }
-    add_ones(t, e);
 }
 
 // Accumulates the staged forward entries fbuf[0, n_stage) = forward entries [f0, f0 + n_stage) of the row.
@@ -283,11 +352,14 @@ __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t, con
     constexpr int WARPS = THREADS / 32;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& ws = ws_all[warp];
+    WarpQueue wq;
+    wq.q = ws.queue;
+    wq.head = wq.tail = 0;
     const unsigned le = 0xffffffffu >> (31 - lane);  // lanes <= mine
     // ---- short lists: batches of 32, flattened
     for (;;) {
         uint32_t bi = 0;
-        if (lane == 0) bi = *t.s_over ? 0x03FFFFFFu : atomicAdd(ctr, 1u);  // one lane polls the stop flag: uniform exit
+        if (lane == 0) bi = *t.over() ? 0x03FFFFFFu : atomicAdd(ctr, 1u);  // one lane polls the stop flag: uniform exit
         bi = __shfl_sync(0xffffffffu, bi, 0);
         const uint32_t b0 = bi * 32;
         if (b0 >= ns) break;
@@ -304,34 +376,34 @@ __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t, con
         const uint32_t pre = incl - len;
         ws.bits[lane] = 0;
         ws.bits[lane + 32] = 0;
-        if (lane < kItems) ws.bits[64 + lane] = 0;
+        if (lane < kItemsA) ws.bits[64 + lane] = 0;
         ws.pre[lane] = pre;
         __syncwarp();
         if (has) atomicOr(&ws.bits[pre >> 5], 1u << (pre & 31));  // lists are >= 2 long: one mark per list
         __syncwarp();
         uint32_t seen = 0;  // marks before this round
-        for (uint32_t t0 = 0; t0 < total; t0 += 32 * kItems) {
-            uint32_t e[kItems], o[kItems];
+        for (uint32_t t0 = 0; t0 < total; t0 += 32 * kItemsA) {
+            uint32_t e[kItemsA], o[kItemsA];
 #pragma unroll
-            for (int u = 0; u < kItems; u++) {
+            for (int u = 0; u < kItemsA; u++) {
                 const uint32_t w = ws.bits[(t0 >> 5) + u];
                 o[u] = (seen + __popc(w & le) - 1u) & 31u;
                 seen += __popc(w);
             }
-            bool special = false;
+            uint32_t special = 0;
 #pragma unroll
-            for (int u = 0; u < kItems; u++) {
+            for (int u = 0; u < kItemsA; u++) {
                 const uint32_t tt = t0 + 32u * u + lane;
-                e[u] = kEmpty;
+                e[u] = kNone;
                 if (tt < total) {
                     const uint2 fw = fbuf[b0 + o[u]];
                     e[u] = a.post[fw.x + (tt - ws.pre[o[u]])];
-                    special |= ((fw.y | e[u]) & kMulti) != 0;
+                    special |= fw.y | e[u];
                 }
             }
-            if (special) {
+            if (special & kMulti) {
 #pragma unroll
-                for (int u = 0; u < kItems; u++) {
+                for (int u = 0; u < kItemsA; u++) {
                     const uint32_t tt = t0 + 32u * u + lane;
                     if (tt < total) {
                         const uint2 fw = fbuf[b0 + o[u]];
@@ -339,40 +411,77 @@ __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t, con
                             const uint32_t n = (e[u] & kMulti) ? a.post_cnt[fw.x + (tt - ws.pre[o[u]])] : 1u;
                             const uint32_t m = (fw.y & kMulti) ? a.fwd_cnt[f0 + b0 + o[u]] : 1u;
                             add_general(t, e[u] & ~kMulti, n, m);
-                            e[u] = kEmpty;
+                            e[u] = kNone;
                         }
                     }
                 }
             }
-            add_ones(t, e);
+#pragma unroll
+            for (int u = 0; u < kItemsA; u += 2) {
+                if (t0 + 32u * u >= total) break;
+                items_add2(t, wq, e[u], e[u + 1]);
+            }
         }
         __syncwarp();
     }
     // ---- long lists: one warp per list
-    for (;;) {
-        uint32_t li = 0;
-        if (lane == 0) li = *t.s_over ? 0x7FFFFFFFu : atomicAdd(ctr + 1, 1u);
-        li = __shfl_sync(0xffffffffu, li, 0);
-        if (li >= nl - ns) break;
-        const uint32_t j = ns + li;
-        const uint2 fw = fbuf[j];
-        const uint32_t mj = (fw.y & kMulti) ? a.fwd_cnt[f0 + j] : 1u;
-        const uint32_t gl = fw.y & ~kMulti;
-        const uint32_t* pl = a.post + fw.x;
-        for (uint32_t p0 = 0; p0 < gl; p0 += 32 * kItems) list_round(a, t, pl, fw.x, p0, gl, mj);
+    {
+        uint32_t e[kItems];
+        uint32_t gs = 0, gl = 0, mj = 1, p0 = 0;
+        auto claim = [&](uint32_t& cgs, uint32_t& cgl, uint32_t& cmj) -> bool {
+            uint32_t li = 0;
+            if (lane == 0) li = *t.over() ? 0x7FFFFFFFu : atomicAdd(ctr + 1, 1u);  // one lane polls the stop flag
+            li = __shfl_sync(0xffffffffu, li, 0);
+            if (li >= nl - ns) return false;
+            const uint2 fw = fbuf[ns + li];
+            cmj = (fw.y & kMulti) ? a.fwd_cnt[f0 + ns + li] : 1u;
+            cgl = fw.y & ~kMulti;
+            cgs = fw.x;
+            return true;
+        };
+        bool have = claim(gs, gl, mj);
+        if (have) {
+#pragma unroll
+            for (int u = 0; u < kItems; u++) e[u] = 32u * u + lane < gl ? a.post[gs + 32u * u + lane] : kNone;
+        }
+        while (have) {
+            uint32_t ngs = gs, ngl = gl, nmj = mj, np0 = p0 + 32 * kItems;
+            bool nhave = true;
+            if (np0 >= gl) {
+                nhave = claim(ngs, ngl, nmj);
+                np0 = 0;
+            }
+            const int nrem = nhave ? (int)(ngl - np0) - (int)lane : 0;
+            round_step(a, t, wq, e, gl - p0, gs + p0, mj, a.post + ngs + np0 + lane, nrem);
+            gs = ngs;
+            gl = ngl;
+            mj = nmj;
+            p0 = np0;
+            have = nhave;
+        }
     }
     // ---- huge lists: the whole CTA strides over each
     for (uint32_t j = nl; j < n_stage; j++) {
-        if (__any_sync(0xffffffffu, *t.s_over != 0)) break;
+        if (__any_sync(0xffffffffu, *t.over() != 0)) break;
         const uint2 fw = fbuf[j];
         const uint32_t mj = (fw.y & kMulti) ? a.fwd_cnt[f0 + j] : 1u;
         const uint32_t gl = fw.y & ~kMulti;
-        const uint32_t* pl = a.post + fw.x;
-        for (uint32_t p0 = warp * (32 * kItems); p0 < gl; p0 += WARPS * 32 * kItems) {
-            list_round(a, t, pl, fw.x, p0, gl, mj);
-            if ((p0 & 0x3FFFu) < WARPS * 32 * kItems && __any_sync(0xffffffffu, *t.s_over != 0)) break;  // poll now and then
+        const uint32_t stride = WARPS * 32 * kItems;
+        uint32_t p0 = warp * (32 * kItems);
+        if (p0 >= gl) continue;
+        uint32_t e[kItems];
+#pragma unroll
+        for (int u = 0; u < kItems; u++) e[u] = p0 + 32u * u + lane < gl ? a.post[fw.x + p0 + 32u * u + lane] : kNone;
+        for (;;) {
+            const uint32_t np0 = p0 + stride;
+            const bool more = np0 < gl && !((np0 & 0x7FFFu) < stride && __any_sync(0xffffffffu, *t.over() != 0));  // poll now and then
+            const int nrem = more ? (int)(gl - np0) - (int)lane : 0;
+            round_step(a, t, wq, e, gl - p0, fw.x + p0, mj, a.post + fw.x + np0 + lane, nrem);
+            if (!more) break;
+            p0 = np0;
         }
     }
+    queue_flush(t, wq);
 }
 
 // (inter, pc, tc) of a table slot
@@ -380,10 +489,10 @@ __device__ __forceinline__ void slot_sums(const Tab& t, uint32_t c, uint32_t v, 
     uint32_t i = v & ~kFlag, p = i, q = i;
     if (v & kFlag) {
         uint32_t xs = __umulhi(c * 0x85EBCA6Bu, kXSlots);
-        while (*(volatile uint32_t*)(t.xkeys + xs) != c) xs = (xs + 1 == kXSlots) ? 0 : xs + 1;
-        i += *(volatile uint32_t*)(t.xv0 + xs);
-        p += *(volatile uint32_t*)(t.xv1 + xs);
-        q += *(volatile uint32_t*)(t.xv2 + xs);
+        while (*(volatile uint32_t*)(t.xkeys() + xs) != c) xs = (xs + 1 == kXSlots) ? 0 : xs + 1;
+        i += *(volatile uint32_t*)(t.xv(0) + xs);
+        p += *(volatile uint32_t*)(t.xv(1) + xs);
+        q += *(volatile uint32_t*)(t.xv(2) + xs);
     }
     *inter = i;
     *pc = p;
@@ -413,7 +522,7 @@ __device__ __forceinline__ void emit_cell(const ScoreArgs& a, const RowCtx& rc, 
 // ------------------------------------------------------------------------------------------------ main kernel
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) score_rows_kernel(ScoreArgs a) {
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(ScoreArgs a) {
     constexpr int WARPS = THREADS / 32;
     PD_DYNAMIC_SMEM(smem_raw);
     const uint32_t H = 1u << a.hbits;
@@ -425,9 +534,7 @@ __global__ void __launch_bounds__(THREADS) score_rows_kernel(ScoreArgs a) {
     __shared__ uint4 s_desc[2][2];  // two RowDesc buffers
     // per-row control words, double-buffered like s_desc: a row uses [buf]; thread 0 clears [buf ^ 1] while the row
     // runs (its last readers finished before the row's opening barrier)
-    __shared__ uint32_t s_nx2[2];
-    __shared__ int s_over2[2];
-    __shared__ uint32_t s_ctr2[2][2];
+    __shared__ RowCtl s_ctl[2];
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -436,15 +543,12 @@ __global__ void __launch_bounds__(THREADS) score_rows_kernel(ScoreArgs a) {
 
     Tab t;
     t.keys = keys;
-    t.cnt = cnt;
+    t.keys_sa = smem_addr(keys);
+    t.cnt_sa = smem_addr(cnt);
     t.mask = H - 1;
-    t.shift = 32 - a.hbits;
+    t.shift = 34 - a.hbits;
     t.limit = H < kProbeLimit ? H : kProbeLimit;
-    t.xkeys = xbase;
-    t.xv0 = xbase + kXSlots;
-    t.xv1 = xbase + 2 * kXSlots;
-    t.xv2 = xbase + 3 * kXSlots;
-    t.xtouched = xbase + 4 * kXSlots;
+    t.xbase = xbase;
 
     for (uint32_t i = tid; i < H; i += THREADS) {
         keys[i] = kEmpty;
@@ -462,9 +566,9 @@ __global__ void __launch_bounds__(THREADS) score_rows_kernel(ScoreArgs a) {
         }
         s_desc[0][0] = d0;
         s_desc[0][1] = d1;
-        s_nx2[0] = s_nx2[1] = 0;
-        s_over2[0] = s_over2[1] = 0;
-        s_ctr2[0][0] = s_ctr2[0][1] = s_ctr2[1][0] = s_ctr2[1][1] = 0;
+        s_ctl[0].nx = s_ctl[1].nx = 0;
+        s_ctl[0].over = s_ctl[1].over = 0;
+        s_ctl[0].ctr[0] = s_ctl[0].ctr[1] = s_ctl[1].ctr[0] = s_ctl[1].ctr[1] = 0;
     }
     __syncthreads();
     {
@@ -482,8 +586,7 @@ __global__ void __launch_bounds__(THREADS) score_rows_kernel(ScoreArgs a) {
         __syncthreads();  // the row's descriptor and first forward segment are staged; the table is clean
         const uint4 rw0 = s_desc[buf][0], rw1 = s_desc[buf][1];  // (gene, bh_row, fb, fe), (kr, gr, fm, fh)
         if (rw0.x == kEmpty) break;
-        t.s_nx = &s_nx2[buf];
-        t.s_over = &s_over2[buf];
+        t.ctl = &s_ctl[buf];
         uint4 nd0 = make_uint4(kEmpty, 0u, 0u, 0u), nd1 = make_uint4(0u, 0u, 0u, 0u);
         uint32_t idx_after = 0;
         if (tid == 0) {  // both are consumed after the accumulate phase
@@ -506,22 +609,22 @@ __global__ void __launch_bounds__(THREADS) score_rows_kernel(ScoreArgs a) {
             const uint32_t f1 = fe - f0 < fcap ? fe : f0 + fcap;
             const uint32_t ns = fm > f0 ? (fm < f1 ? fm - f0 : f1 - f0) : 0u;
             const uint32_t nl = fh > f0 ? (fh < f1 ? fh - f0 : f1 - f0) : 0u;
-            accumulate<THREADS>(a, t, fbuf, f0, ns, nl, f1 - f0, ws, s_ctr2[buf]);
+            accumulate<THREADS>(a, t, fbuf, f0, ns, nl, f1 - f0, ws, s_ctl[buf].ctr);
             if (f1 >= fe) break;
             __syncthreads();
             f0 = f1;
             const uint32_t f2 = fe - f0 < fcap ? fe : f0 + fcap;
             for (uint32_t f = f0 + tid; f < f2; f += THREADS) fbuf[f - f0] = a.fwd[f];
-            if (tid == 0) s_ctr2[buf][0] = s_ctr2[buf][1] = 0;
+            if (tid == 0) s_ctl[buf].ctr[0] = s_ctl[buf].ctr[1] = 0;
             __syncthreads();
         }
         if (tid == 0) {
             s_desc[buf ^ 1][0] = nd0;
             s_desc[buf ^ 1][1] = nd1;
-            s_nx2[buf ^ 1] = 0;
-            s_over2[buf ^ 1] = 0;
-            s_ctr2[buf ^ 1][0] = 0;
-            s_ctr2[buf ^ 1][1] = 0;
+            s_ctl[buf ^ 1].nx = 0;
+            s_ctl[buf ^ 1].over = 0;
+            s_ctl[buf ^ 1].ctr[0] = 0;
+            s_ctl[buf ^ 1].ctr[1] = 0;
             idx_next = idx_after;
         }
         __threadfence_block();
@@ -535,8 +638,8 @@ __global__ void __launch_bounds__(THREADS) score_rows_kernel(ScoreArgs a) {
                 for (uint32_t f = d0.z + tid; f < f1; f += THREADS) cp_async8(&nbuf[f - d0.z], &a.fwd[f]);
             }
         }
-        const bool over = *t.s_over != 0;
-        const uint32_t nx = *t.s_nx < kXCap ? *t.s_nx : kXCap;
+        const bool over = *t.over() != 0;
+        const uint32_t nx = t.ctl->nx < kXCap ? t.ctl->nx : kXCap;
         // each warp owns a slice of the table
         const uint32_t spw = H >= 32u * WARPS ? H / WARPS : 32u;
         const uint32_t lo = warp * spw;
@@ -552,12 +655,12 @@ __global__ void __launch_bounds__(THREADS) score_rows_kernel(ScoreArgs a) {
                 keys[i] = kEmpty;
                 cnt[i] = 0;
             }
-            if (*t.s_nx) {
+            if (t.ctl->nx) {
                 for (uint32_t i = tid; i < kXSlots; i += THREADS) {
-                    t.xkeys[i] = kEmpty;
-                    t.xv0[i] = 0;
-                    t.xv1[i] = 0;
-                    t.xv2[i] = 0;
+                    t.xkeys()[i] = kEmpty;
+                    t.xv(0)[i] = 0;
+                    t.xv(1)[i] = 0;
+                    t.xv(2)[i] = 0;
                 }
                 __threadfence();
             }
@@ -621,11 +724,11 @@ __global__ void __launch_bounds__(THREADS) score_rows_kernel(ScoreArgs a) {
             if (nx) {  // side-table slots are released only after every reader is done (linear probing)
                 __syncthreads();
                 for (uint32_t i = tid; i < nx; i += THREADS) {
-                    const uint32_t xs = t.xtouched[i];
-                    t.xkeys[xs] = kEmpty;
-                    t.xv0[xs] = 0;
-                    t.xv1[xs] = 0;
-                    t.xv2[xs] = 0;
+                    const uint32_t xs = t.xtouched()[i];
+                    t.xkeys()[xs] = kEmpty;
+                    t.xv(0)[xs] = 0;
+                    t.xv(1)[xs] = 0;
+                    t.xv(2)[xs] = 0;
                 }
                 __threadfence();
             }
