@@ -79,10 +79,13 @@ int pd_info(const pd_index* ix, pd_index_info* out) {
 
 int pd_gene_stats(const pd_index* ix, uint32_t* kseq_len, uint64_t* total_visited) {
     if (!ix) return PD_ERR_INVALID;
-    const uint32_t S = ix->ix.info.S;
-    if (kseq_len && S) memcpy(kseq_len, ix->ix.kseq.data(), sizeof(uint32_t) * S);
-    if (total_visited && S) memcpy(total_visited, ix->ix.visited.data(), sizeof(uint64_t) * S);
-    return PD_OK;
+    return guarded([&] {
+        pd::Index& x = const_cast<pd_index*>(ix)->ix;
+        x.host_mirrors();
+        const uint32_t S = x.info.S;
+        if (kseq_len && S) memcpy(kseq_len, x.kseq.data(), sizeof(uint32_t) * S);
+        if (total_visited && S) memcpy(total_visited, x.visited.data(), sizeof(uint64_t) * S);
+    });
 }
 
 int pd_entries(const pd_index* ix, uint64_t* rank, uint32_t* seq, uint32_t* count, uint32_t* group_start, uint32_t* group_len) {
@@ -119,7 +122,7 @@ int pd_score_partition_device(pd_index* ix, uint32_t row_begin, uint32_t row_end
 
 int pd_partition_rows(const pd_index* ix, uint32_t parts, int32_t snap_to_genomes, uint32_t* bounds) {
     if (!ix || !bounds) return PD_ERR_INVALID;
-    return guarded([&] { ix->ix.partition_rows(parts, snap_to_genomes != 0, bounds); });
+    return guarded([&] { const_cast<pd_index*>(ix)->ix.partition_rows(parts, snap_to_genomes != 0, bounds); });
 }
 
 }  // extern "C"

@@ -69,6 +69,7 @@ struct ScoreContext {
     rt::PinBuf<float> h_score, h_perc, h_trperc, h_bh, h_colmax;
     rt::PinBuf<int32_t> h_row, h_col, h_g1, h_g2, h_map;
     pd_score_stats stats;
+    uint32_t map_r0 = 0, map_rows = 0;  // rows currently set in h_map
 
     explicit ScoreContext(Index* i) : ix(i) {
         st = rt::stream_create();
@@ -119,6 +120,8 @@ ScoreContext* Index::acquire() {
 }
 
 void Index::release(ScoreContext* c) {
+    for (uint32_t i = 0; i < c->map_rows; i++) c->h_map.p[genome_rows[c->map_r0 + i]] = INT32_MAX;
+    c->map_rows = 0;
     {
         std::lock_guard<std::mutex> lk(mu);
         free_ctx.push_back(c);
@@ -144,53 +147,18 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     smem_optin = rt::max_optin_smem();
 
     if (offsets[0] != 0) throw Error(PD_ERR_INVALID, "offsets[0] must be 0");
-    const uint64_t total = offsets[S];
-    kseq.assign(S, 0);
-    genome_of.assign(genome_ids, genome_ids + S);
-    std::vector<uint64_t> key_off((size_t)S + 1, 0);
-    uint64_t N = 0;
-    uint32_t G = 0, max_kseq = 0;
-    for (uint32_t s = 0; s < S; s++) {
-        if (offsets[s + 1] < offsets[s]) throw Error(PD_ERR_INVALID, "offsets must be ascending");
-        const uint64_t len = offsets[s + 1] - offsets[s];
-        if (len >= (1ull << 20)) throw Error(PD_ERR_UNSUPPORTED, "a gene of 2^20 or more residues");
-        const int64_t kl = (int64_t)len - k + 1;  // library.cpp:250
-        kseq[s] = kl > 0 ? (uint32_t)kl : 0;
-        max_kseq = std::max(max_kseq, kseq[s]);
-        key_off[s] = N;
-        N += kseq[s];
-        G = std::max(G, genome_ids[s] + 1);  // library.cpp:242
-    }
-    key_off[S] = N;
-    if (N >= (1ull << 31)) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more k-mers (the reference's own int index limit)");
     if (S >= 0x7FFFFFFFu) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more genes");
+    const uint64_t total = offsets[S];
     info.S = S;
-    info.G = G;
     info.k = k;
-    info.N = N;
-    info.max_kseq = max_kseq;
     thr = 1.0f / (2.0f * (float)k);
-
-    // genes of each genome in input order (genome_sequences, library.cpp:245)
-    genome_ptr.assign((size_t)G + 1, 0);
-    for (uint32_t s = 0; s < S; s++) genome_ptr[genome_ids[s] + 1]++;
-    for (uint32_t g = 0; g < G; g++) genome_ptr[g + 1] += genome_ptr[g];
-    genome_rows.assign(S, 0);
-    {
-        std::vector<uint32_t> cur(genome_ptr.begin(), genome_ptr.end() - (G ? 1 : 0));
-        for (uint32_t s = 0; s < S; s++) genome_rows[cur[genome_ids[s]]++] = s;
-    }
-    visited.assign(S, 0);
-    fwd_ptr_h.assign((size_t)S + 1, 0);
-    fwd_short_h.assign((size_t)S + 1, 0);
-    fwd_huge_h.assign((size_t)S + 1, 0);
 
     rt::stream_t st = rt::stream_create();
     uint64_t launches = 0;
     Timer t_all(st), t_h2d(st), t_hist(st), t_enc(st), t_sort(st), t_grp(st), t_fwd(st);
     t_all.start();
 
-    // ---- residues to HBM
+    // ---- residues and gene table to HBM; per gene: k-mer count, (count, genome), input checks (library.cpp:242-262)
     rt::DevBuf<uint8_t> d_res_own;
     const uint8_t* d_res = residues;
     t_h2d.start();
@@ -199,15 +167,29 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         rt::h2d(d_res_own.p, residues, total, st);
         d_res = d_res_own.p;
     }
-    rt::DevBuf<uint64_t> d_gene_off((size_t)S + 1), d_key_off((size_t)S + 1);
+    rt::DevBuf<uint64_t> d_gene_off((size_t)S + 1);
+    rt::DevBuf<uint32_t> d_gid(std::max<size_t>(S, 1)), d_kseq((size_t)S + 1), d_key_off((size_t)S + 1), d_flags(4), d_total(4);
     rt::h2d(d_gene_off.p, offsets, sizeof(uint64_t) * ((size_t)S + 1), st);
-    rt::h2d(d_key_off.p, key_off.data(), sizeof(uint64_t) * ((size_t)S + 1), st);
-    {
-        std::vector<uint2> m(S);
-        for (uint32_t s = 0; s < S; s++) m[s] = make_uint2(kseq[s], genome_ids[s]);
-        meta.alloc(std::max<size_t>(S, 1));
-        rt::h2d(meta.p, m.data(), sizeof(uint2) * S, st);
-        rt::sync(st);  // m goes out of scope
+    rt::h2d(d_gid.p, genome_ids, sizeof(uint32_t) * S, st);
+    rt::zero(d_flags.p, 4 * sizeof(uint32_t), st);
+    meta.alloc(std::max<size_t>(S, 1));
+    PD_LAUNCH(ik::gene_meta_kernel, blocks_for((uint64_t)S + 1), 256, 0, st, (const uint64_t*)d_gene_off.p, (const uint32_t*)d_gid.p, S, (int)k,
+              d_kseq.p, meta.p, d_flags.p);
+    launches++;
+    rt::DevBuf<uint32_t> scratch(prims::scan_tmp_words((uint64_t)S + 1) + 16);
+    prims::exclusive_scan_u32(d_kseq.p, d_key_off.p, (uint64_t)S + 1, scratch.p, nullptr, st, &launches);
+    uint32_t h_flags[4] = {0, 0, 0, 0}, h_N = 0;
+    rt::d2h(h_flags, d_flags.p, sizeof(h_flags), st);
+    rt::d2h(&h_N, d_key_off.p + S, sizeof(uint32_t), st);
+    // a k-mer total of 2^31 or more would wrap the 32-bit scan: bound it on the host from the residue total
+    if (total >= (1ull << 31) + (uint64_t)S * (uint64_t)(k - 1)) {
+        uint64_t Nh = 0;
+        for (uint32_t s = 0; s < S && Nh < (1ull << 31); s++) {
+            if (offsets[s + 1] < offsets[s]) throw Error(PD_ERR_INVALID, "offsets must be ascending");
+            const uint64_t len = offsets[s + 1] - offsets[s];
+            if (len >= (uint64_t)k) Nh += len - k + 1;
+        }
+        if (Nh >= (1ull << 31)) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more k-mers (the reference's own int index limit)");
     }
     t_h2d.stop();
 
@@ -224,6 +206,12 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     rt::d2h(h_hist, d_hist.p, sizeof(h_hist), st);
     rt::sync(st);
     t_hist.stop();
+    if (h_flags[0] & 1u) throw Error(PD_ERR_INVALID, "offsets must be ascending");
+    if (h_flags[0] & 2u) throw Error(PD_ERR_UNSUPPORTED, "a gene of 2^20 or more residues");
+    const uint64_t N = h_N;
+    const uint32_t G = S ? h_flags[1] + 1 : 0;  // library.cpp:242
+    info.G = G;
+    info.N = N;
     ik::ValTable vt;
     memset(&vt, 0, sizeof(vt));
     uint32_t base = 0;
@@ -244,7 +232,13 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     info.seq_bits = seq_bits;
 
     fwd_ptr.alloc((size_t)S + 1);
+    cls.alloc(std::max<size_t>(S, 1));
+    d_visited.alloc(std::max<size_t>(S, 1));
     rt::zero(fwd_ptr.p, sizeof(uint32_t) * ((size_t)S + 1), st);
+    rt::zero(cls.p, sizeof(unsigned long long) * S, st);
+    rt::zero(d_visited.p, sizeof(unsigned long long) * S, st);
+    uint32_t U = 0, n_groups = 0, R = 0;
+    unsigned long long lookups = 0;
 
     if (N > 0) {
         // ---- encode (library.cpp:234-265)
@@ -253,103 +247,71 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         {
             unsigned grid = std::min<uint64_t>((uint64_t)sms * 16, ((uint64_t)S + 7) / 8);
             PD_LAUNCH(ik::encode_kernel, std::max(1u, grid), 256, 0, st, d_res, (const uint64_t*)d_gene_off.p,
-                      (const uint64_t*)d_key_off.p, S, (int)k, base, seq_bits, vt, keys_a.p);
+                      (const uint32_t*)d_key_off.p, S, (int)k, base, seq_bits, vt, keys_a.p);
             launches++;
         }
         t_enc.stop();
-        d_res_own.release();  // stream-ordered free happens after the kernel (cudaFree synchronises)
 
         // ---- sort by rank; stability keeps genes ascending inside a rank (library.cpp:270-278)
         t_sort.start();
-        rt::DevBuf<uint32_t> sort_tmp(prims::radix_tmp_words(N) + 16);
-        uint64_t* sorted = prims::radix_sort_u64(keys_a.p, keys_b.p, N, seq_bits, seq_bits + rank_bits, sort_tmp.p, st, &launches);
+        scratch.ensure(prims::radix_tmp_words(N) + 16);
+        uint64_t* sorted = prims::radix_sort_u64(keys_a.p, keys_b.p, N, seq_bits, seq_bits + rank_bits, scratch.p, st, &launches);
         t_sort.stop();
 
         // ---- count dedup (library.cpp:280-287) and rank groups incl. the tail merge (library.cpp:297-306)
         t_grp.start();
-        rt::DevBuf<uint32_t>& scratch = sort_tmp;
-        rt::DevBuf<uint32_t> d_total(4);
-        uint32_t U = 0, n_groups = 0;
-        rt::DevBuf<uint32_t> ent_pos;
-        {
-            rt::DevBuf<uint32_t> flags(N);
-            scratch.ensure(prims::scan_tmp_words(N) + 16);
-            PD_LAUNCH(ik::head_flag_kernel, blocks_for(N), 256, 0, st, (const uint64_t*)sorted, N, flags.p);
-            prims::exclusive_scan_u32(flags.p, flags.p, N, scratch.p, d_total.p, st, &launches);
-            rt::d2h(&U, d_total.p, sizeof(uint32_t), st);
-            rt::sync(st);
-            ent_pos.alloc(U);
-            PD_LAUNCH(ik::head_scatter_kernel, blocks_for(N), 256, 0, st, (const uint64_t*)sorted, N, (const uint32_t*)flags.p, ent_pos.p);
-            launches += 2;
-            rt::sync(st);
-        }
-        info.U = U;
+        const uint32_t tiles = (uint32_t)((N + ik::kEntTile - 1) / ik::kEntTile);
+        rt::DevBuf<uint32_t> tile_h((size_t)tiles + 1), tile_g((size_t)tiles + 1), d_spur(4);
+        rt::zero(d_spur.p, 4 * sizeof(uint32_t), st);
+        PD_LAUNCH(ik::entry_count_kernel, tiles, ik::kEntThreads, 0, st, (const uint64_t*)sorted, N, seq_bits, tile_h.p, tile_g.p);
+        launches++;
+        scratch.ensure(prims::scan_tmp_words(tiles) + 16);
+        prims::exclusive_scan_u32(tile_h.p, tile_h.p, tiles, scratch.p, d_total.p, st, &launches);
+        prims::exclusive_scan_u32(tile_g.p, tile_g.p, tiles, scratch.p, d_total.p + 1, st, &launches);
+        uint32_t h_tot[2] = {0, 0};
+        rt::d2h(h_tot, d_total.p, sizeof(h_tot), st);
+        rt::sync(st);
+        U = h_tot[0];
+        const uint32_t g_counted = h_tot[1];
         post.alloc(U);
         post_cnt.alloc(U);
-        rt::DevBuf<uint32_t> rflag(U);
-        if (opt.keep_sorted) ent_rank.alloc(U);
-        PD_LAUNCH(ik::entries_kernel, blocks_for(U), 256, 0, st, (const uint64_t*)sorted, (const uint32_t*)ent_pos.p, U, N, seq_bits,
-                  post.p, post_cnt.p, rflag.p, opt.keep_sorted ? ent_rank.p : (uint64_t*)nullptr);
-        launches++;
-        rt::DevBuf<uint32_t> gexcl(U);
-        prims::exclusive_scan_u32(rflag.p, gexcl.p, U, scratch.p, d_total.p, st, &launches);
-        rt::d2h(&n_groups, d_total.p, sizeof(uint32_t), st);
-        rt::sync(st);
-        keys_a.release();
-        keys_b.release();
-        ent_pos.release();
-        info.groups = n_groups;
-        grp_head.alloc((size_t)n_groups + 1);
         ent_gid.alloc(U);
-        PD_LAUNCH(ik::group_heads_kernel, blocks_for(U), 256, 0, st, (const uint32_t*)rflag.p, (const uint32_t*)gexcl.p, U, grp_head.p,
-                  ent_gid.p);
-        launches++;
-        rt::h2d(grp_head.p + n_groups, &U, sizeof(uint32_t), st);
+        grp_head.alloc((size_t)g_counted + 1);
+        if (opt.keep_sorted) ent_rank.alloc(U);
+        PD_LAUNCH(ik::entry_apply_kernel, tiles, ik::kEntThreads, 0, st, (const uint64_t*)sorted, N, seq_bits, (const uint32_t*)tile_h.p,
+                  (const uint32_t*)tile_g.p, U, post.p, post_cnt.p, ent_gid.p, grp_head.p, opt.keep_sorted ? ent_rank.p : (uint64_t*)nullptr,
+                  d_spur.p);
+        PD_LAUNCH(ik::group_tail_kernel, 1, 32, 0, st, grp_head.p, g_counted, (const uint32_t*)d_spur.p, U);
+        launches += 2;
         t_grp.stop();
 
-        // ---- forward lists and the cost model (library.cpp:308-330)
+        // ---- forward lists by counting sort on the gene, and the cost model (library.cpp:308-330)
         t_fwd.start();
-        rt::DevBuf<uint32_t>& sflag = rflag;   // reuse
-        rt::DevBuf<uint32_t>& sexcl = gexcl;   // reuse
-        rt::DevBuf<uint32_t> gene_cnt((size_t)S + 1), gene_short((size_t)S + 1), gene_huge((size_t)S + 1);
-        rt::DevBuf<unsigned long long> d_visited(S);
-        rt::zero(gene_cnt.p, sizeof(uint32_t) * ((size_t)S + 1), st);
-        rt::zero(gene_short.p, sizeof(uint32_t) * ((size_t)S + 1), st);
-        rt::zero(gene_huge.p, sizeof(uint32_t) * ((size_t)S + 1), st);
-        rt::zero(d_visited.p, sizeof(unsigned long long) * S, st);
-        PD_LAUNCH(ik::shared_mark_kernel, blocks_for(U), 256, 0, st, (const uint32_t*)post.p, (const uint32_t*)ent_gid.p,
-                  (const uint32_t*)grp_head.p, U, sflag.p, gene_cnt.p, gene_short.p, sk::kShortList, gene_huge.p, sk::kHugeList,
-                  d_visited.p);
-        launches++;
-        prims::exclusive_scan_u32(sflag.p, sexcl.p, U, scratch.p, d_total.p, st, &launches);
-        uint32_t R = 0;
-        rt::d2h(&R, d_total.p, sizeof(uint32_t), st);
-        rt::sync(st);
-        info.R = R;
+        rt::DevBuf<unsigned long long> cursor(std::max<size_t>(S, 1)), d_lookups(2);
+        rt::DevBuf<uint32_t> gene_tot((size_t)S + 1);
+        rt::zero(cursor.p, sizeof(unsigned long long) * S, st);
+        rt::zero(d_lookups.p, 2 * sizeof(unsigned long long), st);
+        PD_LAUNCH(ik::fwd_count_kernel, blocks_for(U), 256, 0, st, (const uint32_t*)post.p, (const uint32_t*)ent_gid.p,
+                  (const uint32_t*)grp_head.p, U, sk::kShortList, sk::kHugeList, cls.p);
+        PD_LAUNCH(ik::fwd_totals_kernel, blocks_for((uint64_t)S + 1), 256, 0, st, (const unsigned long long*)cls.p, S, gene_tot.p);
+        launches += 2;
         scratch.ensure(prims::scan_tmp_words((uint64_t)S + 1) + 16);
-        prims::exclusive_scan_u32(gene_cnt.p, fwd_ptr.p, (uint64_t)S + 1, scratch.p, nullptr, st, &launches);
-        fwd.alloc(std::max<size_t>(R, 1));
-        fwd_cnt.alloc(std::max<size_t>(R, 1));
-        if (R) {
-            rt::DevBuf<uint64_t> fk_a(R), fk_b(R);
-            PD_LAUNCH(ik::fwd_keys_kernel, blocks_for(U), 256, 0, st, (const uint32_t*)post.p, (const uint32_t*)sflag.p,
-                      (const uint32_t*)sexcl.p, (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, sk::kShortList, sk::kHugeList,
-                      U, fk_a.p);
-            launches++;
-            scratch.ensure(prims::radix_tmp_words(R) + 16);
-            uint64_t* fsorted = prims::radix_sort_u64(fk_a.p, fk_b.p, R, 31, 33 + seq_bits, scratch.p, st, &launches);
-            PD_LAUNCH(ik::fwd_fill_kernel, blocks_for(R), 256, 0, st, (const uint64_t*)fsorted, R, (const uint32_t*)post_cnt.p,
-                      (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, fwd.p, fwd_cnt.p);
-            launches++;
-            rt::sync(st);
-        }
-        static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
-        rt::d2h(visited.data(), d_visited.p, sizeof(uint64_t) * S, st);
-        rt::d2h(fwd_ptr_h.data(), fwd_ptr.p, sizeof(uint32_t) * ((size_t)S + 1), st);
-        rt::d2h(fwd_short_h.data(), gene_short.p, sizeof(uint32_t) * S, st);
-        rt::d2h(fwd_huge_h.data(), gene_huge.p, sizeof(uint32_t) * S, st);
-        rt::sync(st);
+        prims::exclusive_scan_u32(gene_tot.p, fwd_ptr.p, (uint64_t)S + 1, scratch.p, nullptr, st, &launches);
+        fwd.alloc(U);  // R <= U: sized without waiting for R
+        fwd_cnt.alloc(U);
+        PD_LAUNCH(ik::fwd_scatter_kernel, blocks_for(U), 256, 0, st, (const uint32_t*)post.p, (const uint32_t*)post_cnt.p,
+                  (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, U, sk::kShortList, sk::kHugeList, (const unsigned long long*)cls.p,
+                  (const uint32_t*)fwd_ptr.p, cursor.p, fwd.p, fwd_cnt.p);
+        PD_LAUNCH(ik::gene_visited_kernel, blocks_for((uint64_t)S * 32), 256, 0, st, (const uint2*)fwd.p, (const uint32_t*)fwd_ptr.p, S,
+                  d_visited.p, d_lookups.p);
+        launches += 2;
+        uint32_t h_spur = 0;
+        rt::d2h(&h_spur, d_spur.p, sizeof(uint32_t), st);
+        rt::d2h(&R, fwd_ptr.p + S, sizeof(uint32_t), st);
+        rt::d2h(&lookups, d_lookups.p, sizeof(unsigned long long), st);
         t_fwd.stop();
+        rt::sync(st);
+        n_groups = g_counted - h_spur;
         if (!opt.keep_sorted) {
             ent_gid.release();
             grp_head.release();
@@ -362,10 +324,18 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     }
     t_all.stop();
     rt::sync(st);
-
-    uint64_t lookups = 0;
-    for (uint32_t s = 0; s < S; s++) lookups += visited[s];
+    info.U = U;
+    info.groups = n_groups;
+    info.R = R;
     info.lookups = lookups;
+    {   // longest gene in k-mers: only reported
+        uint32_t mk = 0;
+        for (uint32_t s = 0; s < S; s++) {
+            const uint64_t len = offsets[s + 1] - offsets[s];
+            if (len >= (uint64_t)k) mk = std::max<uint32_t>(mk, (uint32_t)(len - k + 1));
+        }
+        info.max_kseq = mk;
+    }
     info.build_ms[0] = total ? t_hist.ms() : 0;
     if (N) {
         info.build_ms[1] = t_enc.ms();
@@ -387,6 +357,56 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         printf("------------\n\n");
         fflush(stdout);
     }
+}
+
+// Host copies of the per-gene tables, on first use (pd_gene_stats, pd_partition_rows, pd_compute_scores).
+void Index::host_mirrors() {
+    std::lock_guard<std::mutex> lk(mirror_mu);
+    if (have_mirrors) return;
+    rt::set_device(device);
+    const uint32_t S = info.S;
+    kseq.assign(S, 0);
+    genome_of.assign(S, 0);
+    visited.assign(S, 0);
+    if (S) {
+        std::vector<uint2> m(S);
+        rt::stream_t st = rt::stream_create();
+        rt::d2h(m.data(), meta.p, sizeof(uint2) * S, st);
+        static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
+        rt::d2h(visited.data(), d_visited.p, sizeof(uint64_t) * S, st);
+        rt::sync(st);
+        rt::stream_destroy(st);
+        for (uint32_t s = 0; s < S; s++) {
+            kseq[s] = m[s].x;
+            genome_of[s] = m[s].y;
+        }
+    }
+    have_mirrors = true;
+}
+
+// genes of each genome in input order (genome_sequences, library.cpp:245), host and device
+void Index::genome_lists() {
+    host_mirrors();
+    std::lock_guard<std::mutex> lk(mirror_mu);
+    if (have_genome_lists) return;
+    rt::set_device(device);
+    const uint32_t S = info.S, G = info.G;
+    genome_ptr.assign((size_t)G + 1, 0);
+    for (uint32_t s = 0; s < S; s++) genome_ptr[genome_of[s] + 1]++;
+    for (uint32_t g = 0; g < G; g++) genome_ptr[g + 1] += genome_ptr[g];
+    genome_rows.assign(S, 0);
+    {
+        std::vector<uint32_t> cur(genome_ptr.begin(), genome_ptr.end() - (G ? 1 : 0));
+        for (uint32_t s = 0; s < S; s++) genome_rows[cur[genome_of[s]]++] = s;
+    }
+    d_genome_rows.alloc(std::max<size_t>(S, 1));
+    if (S) {
+        rt::stream_t st = rt::stream_create();
+        rt::h2d(d_genome_rows.p, genome_rows.data(), sizeof(uint32_t) * S, st);
+        rt::sync(st);
+        rt::stream_destroy(st);
+    }
+    have_genome_lists = true;
 }
 
 // ------------------------------------------------------------------------------------------------ scoring
@@ -485,15 +505,12 @@ void launch_rows(ScoreContext& c, sk::ScoreArgs a, const Level& lv, int cursor_i
     c.stats.launches++;
 }
 
-struct RowLists {
-    uint32_t begin[kLevels];  // rows of first-try level i: [begin[i], begin[i+1])
-};
-
 }  // namespace
 
-// Scores the `n` rows of c.h_rows (already ordered into the lists of `rl`).  Returns the number of non-zero
-// cells; cells beyond c.cap are counted but not stored (caller grows and re-runs).
-static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32_t* d_bh, uint32_t* d_colmax, uint64_t* pairs) {
+// Scores the `n` rows gene(i) = genes[i] (device array) or gene_base + i; row i writes best hits to row i of d_bh.
+// Returns the number of non-zero cells; cells beyond c.cap are counted but not stored (caller grows and re-runs).
+static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, uint32_t gene_base, uint32_t* d_bh, uint32_t* d_colmax,
+                         uint64_t* pairs, uint64_t* lookups, uint64_t* fwd_entries) {
     Index& ix = *c.ix;
     Level lv[kLevels];
     levels_of(ix, lv);
@@ -505,9 +522,27 @@ static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32
     }
     rt::zero(c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
     rt::zero(c.d_cursors.p, 16 * sizeof(uint32_t), c.st);
-    c.d_rows.ensure(n);
+    c.d_rows.ensure((size_t)3 * n);
     c.d_ovf.ensure((size_t)2 * n);
-    rt::h2d(c.d_rows.p, c.h_rows.p, sizeof(sk::RowDesc) * n, c.st);
+
+    // ---- row descriptors, sorted into the first-try levels, on the device
+    sk::ClassifyArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.n = n;
+    ca.genes = d_genes;
+    ca.gene_base = gene_base;
+    ca.S = ix.info.S;
+    ca.visited = ix.d_visited.p;
+    ca.fwd_ptr = ix.fwd_ptr.p;
+    ca.cls = ix.cls.p;
+    ca.cls_bits = ik::kClsBits;
+    ca.meta = ix.meta.p;
+    for (int l = 0; l < 3; l++) ca.max_cols[l] = lv[l].max_cols;
+    ca.rows = c.d_rows.p;
+    ca.counts = c.d_cursors.p + 8;  // [8..10]
+    ca.stats = c.d_counters.p + 4;  // [4], [5]
+    PD_LAUNCH(sk::classify_rows_kernel, blocks_for(n), 256, 0, c.st, ca);
+    c.stats.launches++;
 
     sk::ScoreArgs a;
     memset(&a, 0, sizeof(a));
@@ -525,8 +560,9 @@ static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32
     rt::event_record(c.ev_k0, c.st);
     for (int level = 0; level < kLevels - 1; level++) {
         sk::ScoreArgs b = a;
-        b.rows = c.d_rows.p + rl.begin[level];
-        b.n_rows = rl.begin[level + 1] - rl.begin[level];
+        b.rows = c.d_rows.p + (size_t)level * n;
+        b.n_rows = n;  // upper bound: sizes the grid
+        b.n_rows_dev = c.d_cursors.p + 8 + level;
         b.overflow_rows = c.d_ovf.p;
         b.n_overflow = c.d_counters.p + 2;
         launch_rows(c, b, lv[level], level);
@@ -570,58 +606,15 @@ static uint64_t run_rows(ScoreContext& c, const RowLists& rl, uint32_t n, uint32
     rt::sync(c.st);
     c.stats.kernel_ms += rt::event_ms(c.ev_k0, c.ev_k1);
     *pairs = c.h_counters.p[1];
+    *lookups = c.h_counters.p[4];
+    *fwd_entries = c.h_counters.p[5];
     return c.h_counters.p[0];
-}
-
-// Builds the row descriptors of the `n` rows gene_at(i) (best-hit row i) in c.h_rows, grouped by first-try level.
-template <class F>
-static RowLists classify_rows(ScoreContext& c, uint32_t n, F gene_at, uint64_t* lookups, uint64_t* fwd_entries) {
-    Index& ix = *c.ix;
-    Level lv[kLevels];
-    levels_of(ix, lv);
-    c.h_rows.ensure(std::max<uint32_t>(n, 1));
-    auto level_of = [&](uint32_t g) {
-        const uint64_t cols = std::min<uint64_t>(ix.visited[g], ix.info.S);
-        for (int l = 0; l < kLevels - 2; l++)
-            if (cols <= lv[l].max_cols) return l;
-        return kLevels - 2;
-    };
-    uint32_t cnt[kLevels] = {0, 0, 0, 0};
-    uint64_t lk = 0, fe = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t g = gene_at(i);
-        cnt[level_of(g)]++;
-        lk += ix.visited[g];
-        fe += ix.fwd_ptr_h[g + 1] - ix.fwd_ptr_h[g];
-    }
-    *fwd_entries = fe;
-    RowLists rl;
-    uint32_t cur[kLevels];
-    rl.begin[0] = 0;
-    for (int l = 0; l < kLevels - 1; l++) {
-        cur[l] = rl.begin[l];
-        rl.begin[l + 1] = rl.begin[l] + cnt[l];
-    }
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t g = gene_at(i);
-        sk::RowDesc d;
-        d.gene = g;
-        d.bh_row = i;
-        d.fb = ix.fwd_ptr_h[g];
-        d.fe = ix.fwd_ptr_h[g + 1];
-        d.fm = d.fb + ix.fwd_short_h[g];
-        d.fh = d.fe - ix.fwd_huge_h[g];
-        d.kr = ix.kseq[g];
-        d.gr = ix.genome_of[g];
-        c.h_rows.p[cur[level_of(g)]++] = d;
-    }
-    *lookups = lk;
-    return rl;
 }
 
 void Index::compute_scores(uint32_t genome, pd_scores* out) {
     if (genome >= info.G) throw Error(PD_ERR_INVALID, "unknown genome");
     rt::set_device(device);
+    genome_lists();
     ScoreContext* cp = acquire();
     ScoreContext& c = *cp;
     try {
@@ -629,16 +622,14 @@ void Index::compute_scores(uint32_t genome, pd_scores* out) {
         const uint32_t S = info.S, G = info.G;
         const uint32_t r0 = genome_ptr[genome], rows = genome_ptr[genome + 1] - r0;
         rt::event_record(c.ev_call0, c.st);
-        uint64_t lookups = 0, fwd_entries = 0;
-        RowLists rl = classify_rows(c, rows, [&](uint32_t i) { return genome_rows[r0 + i]; }, &lookups, &fwd_entries);
         c.d_bh.ensure(std::max<size_t>((size_t)rows * G, 1));
         c.d_colmax.ensure(std::max<size_t>(S, 1));
-        if (c.cap == 0) c.ensure_cells(opt.cell_capacity ? opt.cell_capacity : std::max<uint64_t>(1u << 16, (uint64_t)rows * 256));
-        uint64_t cells = 0, pairs = 0;
+        if (c.cap == 0) c.ensure_cells(opt.cell_capacity ? opt.cell_capacity : std::max<uint64_t>(1u << 16, (uint64_t)rows * 1024));
+        uint64_t cells = 0, pairs = 0, lookups = 0, fwd_entries = 0;
         for (int attempt = 0; attempt < 3; attempt++) {
             rt::zero(c.d_bh.p, sizeof(uint32_t) * (size_t)rows * G, c.st);
             rt::zero(c.d_colmax.p, sizeof(uint32_t) * S, c.st);
-            cells = rows ? run_rows(c, rl, rows, c.d_bh.p, c.d_colmax.p, &pairs) : 0;
+            cells = rows ? run_rows(c, rows, d_genome_rows.p + r0, 0, c.d_bh.p, c.d_colmax.p, &pairs, &lookups, &fwd_entries) : 0;
             if (cells <= c.cap) break;
             c.ensure_cells(cells + cells / 8);
         }
@@ -650,7 +641,10 @@ void Index::compute_scores(uint32_t genome, pd_scores* out) {
         c.h_row.ensure(nc); c.h_col.ensure(nc); c.h_g1.ensure(nc); c.h_g2.ensure(nc);
         c.h_bh.ensure(std::max<size_t>((size_t)rows * G, 1));
         c.h_colmax.ensure(std::max<size_t>(S, 1));
-        c.h_map.ensure(std::max<size_t>(S, 1));
+        if (c.h_map.n < std::max<size_t>(S, 1)) {  // flat_map (library.cpp:428-432): all INT32_MAX between calls
+            c.h_map.ensure(std::max<size_t>(S, 1));
+            for (uint32_t s = 0; s < S; s++) c.h_map.p[s] = INT32_MAX;
+        }
         rt::d2h(c.h_score.p, c.d_score.p, sizeof(float) * cells, c.st);
         rt::d2h(c.h_perc.p, c.d_perc.p, sizeof(float) * cells, c.st);
         rt::d2h(c.h_trperc.p, c.d_trperc.p, sizeof(float) * cells, c.st);
@@ -661,10 +655,12 @@ void Index::compute_scores(uint32_t genome, pd_scores* out) {
         rt::d2h(c.h_bh.p, c.d_bh.p, sizeof(float) * (size_t)rows * G, c.st);
         rt::d2h(c.h_colmax.p, c.d_colmax.p, sizeof(float) * S, c.st);
         rt::event_record(c.ev_call1, c.st);
-        // flat_map (library.cpp:428-432) while the copies run
-        for (uint32_t s = 0; s < S; s++) c.h_map.p[s] = INT32_MAX;
+        // this genome's rows in flat_map while the copies run; release() puts INT32_MAX back
         for (uint32_t i = 0; i < rows; i++) c.h_map.p[genome_rows[r0 + i]] = (int32_t)i;
+        c.map_r0 = r0;
+        c.map_rows = rows;
         rt::sync(c.st);
+        rt::collect();
         c.stats.total_ms = rt::event_ms(c.ev_call0, c.ev_call1);
         c.stats.rows = rows;
         c.stats.lookups = lookups;
@@ -704,16 +700,15 @@ void Index::score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_
             c.d_bh.ensure(std::max<size_t>((size_t)total_rows * G, 1));
             bh = c.d_bh.p;
         }
-        if (c.cap == 0) c.ensure_cells(opt.cell_capacity ? opt.cell_capacity : std::max<uint64_t>(1u << 20, (uint64_t)rows_per_launch * 256));
+        if (c.cap == 0) c.ensure_cells(opt.cell_capacity ? opt.cell_capacity : std::max<uint64_t>(1u << 20, (uint64_t)rows_per_launch * 1024));
         rt::event_record(c.ev_call0, c.st);
         rt::zero(bh, sizeof(uint32_t) * (size_t)total_rows * G, c.st);
         for (uint32_t b0 = row_begin; b0 < row_end; b0 += rows_per_launch) {
             const uint32_t n = std::min(rows_per_launch, row_end - b0);
             uint64_t lookups = 0, pairs = 0, cells = 0, fwd_entries = 0;
-            RowLists rl = classify_rows(c, n, [&](uint32_t i) { return b0 + i; }, &lookups, &fwd_entries);
             uint32_t* bh_blk = bh + (size_t)(b0 - row_begin) * G;
             for (int attempt = 0; attempt < 3; attempt++) {
-                cells = run_rows(c, rl, n, bh_blk, nullptr, &pairs);
+                cells = run_rows(c, n, nullptr, b0, bh_blk, nullptr, &pairs, &lookups, &fwd_entries);
                 if (cells <= c.cap) break;
                 c.ensure_cells(cells + cells / 8);
             }
@@ -726,6 +721,7 @@ void Index::score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_
         }
         rt::event_record(c.ev_call1, c.st);
         rt::sync(c.st);
+        rt::collect();
         c.stats.total_ms = rt::event_ms(c.ev_call0, c.ev_call1);
         if (st_out) *st_out = c.stats;
     } catch (...) {
@@ -735,8 +731,9 @@ void Index::score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_
     release(cp);
 }
 
-void Index::partition_rows(uint32_t parts, bool snap, uint32_t* bounds) const {
+void Index::partition_rows(uint32_t parts, bool snap, uint32_t* bounds) {
     if (parts == 0) throw Error(PD_ERR_INVALID, "parts must be > 0");
+    host_mirrors();
     const uint32_t S = info.S;
     // cost of a row = postings it visits, +1 so that empty rows still spread
     std::vector<uint64_t> pre((size_t)S + 1, 0);

@@ -26,21 +26,25 @@ struct Index {
     rt::DevBuf<uint32_t> post_cnt;
     rt::DevBuf<uint2> fwd;
     rt::DevBuf<uint32_t> fwd_cnt;
-    rt::DevBuf<uint32_t> fwd_ptr;
-    rt::DevBuf<uint2> meta;
+    rt::DevBuf<uint32_t> fwd_ptr;              // S+1
+    rt::DevBuf<unsigned long long> cls;        // S: forward entries per list class (3 x 21 bits)
+    rt::DevBuf<unsigned long long> d_visited;  // S: total_visited
+    rt::DevBuf<uint2> meta;                    // S: (kseq_len, genome)
     rt::DevBuf<uint32_t> ent_gid;    // kept only with opt.keep_sorted
     rt::DevBuf<uint32_t> grp_head;   // kept only with opt.keep_sorted
     rt::DevBuf<uint64_t> ent_rank;   // kept only with opt.keep_sorted
+    rt::DevBuf<uint32_t> d_genome_rows;  // with genome_rows (below)
 
-    // host mirrors (O(S))
+    // host mirrors (O(S)), fetched from the device on first use: host_mirrors() / genome_lists()
+    std::mutex mirror_mu;
+    bool have_mirrors = false, have_genome_lists = false;
     std::vector<uint32_t> kseq;
     std::vector<uint32_t> genome_of;
     std::vector<uint64_t> visited;
-    std::vector<uint32_t> fwd_ptr_h;    // S+1
-    std::vector<uint32_t> fwd_short_h;  // per gene: forward entries whose posting list is short (they come first)
-    std::vector<uint32_t> fwd_huge_h;   // per gene: forward entries whose posting list is huge (they come last)
     std::vector<uint32_t> genome_ptr;   // G+1
     std::vector<uint32_t> genome_rows;  // genes grouped by genome, input order inside (genome_sequences, library.cpp:245)
+    void host_mirrors();
+    void genome_lists();
 
     // contexts
     std::mutex mu;
@@ -55,7 +59,7 @@ struct Index {
     void release(ScoreContext* c);
     void compute_scores(uint32_t genome, pd_scores* out);
     void score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_per_launch, float* d_best_hit, pd_score_stats* st);
-    void partition_rows(uint32_t parts, bool snap, uint32_t* bounds) const;
+    void partition_rows(uint32_t parts, bool snap, uint32_t* bounds);
     static void context_stats(ScoreContext* c, pd_score_stats* out);
     void entries(uint64_t* rank, uint32_t* seq, uint32_t* count, uint32_t* gs, uint32_t* gl);
 };

@@ -1,20 +1,23 @@
 // Index-construction kernels: the device counterpart of preprocessSequences (reference ig/native/library.cpp:189-335).
 //
-//   byte_hist_kernel      alphabet histogram                      library.cpp:216-228
-//   encode_kernel         positional k-mer rank -> 64-bit key     library.cpp:75-79,134-150,234-265
-//   (prims.cuh)           stable LSD radix sort on the rank bits   library.cpp:270-278
-//   head_scatter_kernel   run heads of equal (rank, seq)          library.cpp:280-287   (count dedup, part 1)
-//   entries_kernel        count per entry + rank-run heads         library.cpp:280-287, 297-306 (incl. the tail merge)
-//   group_*_kernel        rank groups -> inverted index CSR        library.cpp:297-335
-//   fwd_*_kernel          per-gene forward lists + cost model      library.cpp:314-328
+//   gene_meta_kernel      per gene: k-mer count, (count, genome), input checks   library.cpp:250-262
+//   byte_hist_kernel      alphabet histogram                                     library.cpp:216-228
+//   encode_kernel         positional k-mer rank -> 64-bit key                    library.cpp:75-79,134-150,234-265
+//   (prims.cuh)           stable LSD radix sort on the rank bits                  library.cpp:270-278
+//   entry_count_kernel /  one read of the sorted keys each: count dedup          library.cpp:280-287
+//   entry_apply_kernel    (equal (rank, gene) -> one entry with its multiplicity) and rank groups incl. the tail
+//                         merge                                                  library.cpp:297-306
+//   fwd_count_kernel /    per-gene forward lists (the transpose of the posting   library.cpp:314-328
+//   fwd_scatter_kernel    lists) by counting sort on the gene: count, scan, place
+//   gene_visited_kernel   cost model: total_visited per gene                      library.cpp:327
 //
 // HBM layout produced (all SoA, 32-bit indices; the reference's 16-B kmer_rank / 24-B kmers_range records are gone):
 //   post[U]     uint32 seq | bit 31 (count > 1)   entries sorted by (rank, seq): the posting lists, group after group
 //   post_cnt[U] uint32 count                      read by the scoring kernels only where bit 31 is set (U/N > 0.999: rare)
 //   fwd[R]      uint2 (group start, group length | own-count>1 flag) one per (gene, shared k-mer), genes ascending;
-//               inside a gene: short posting lists first, then long, then huge ones, ranks ascending in each class
-//   fwd_cnt[R]  uint32 the gene's own multiplicity of that k-mer
-//   fwd_ptr[S+1], gene_short[S], gene_huge[S], meta[S] = (kseq_len, genome), visited[S] (uint64)
+//               inside a gene: short posting lists first, then long, then huge ones (order inside a class is free)
+//   fwd_cnt[R]  uint32 the gene's own multiplicity of that k-mer (written only where the flag is set)
+//   fwd_ptr[S+1], cls[S] (three 21-bit class counts), meta[S] = (kseq_len, genome), visited[S] (uint64)
 #pragma once
 
 #include "pd_rt.h"
@@ -26,6 +29,44 @@ namespace ik {
 struct ValTable {
     uint8_t v[256];
 };
+
+static const int kClsBits = 21;  // a gene holds < 2^20 k-mers
+static const unsigned long long kClsMask = (1ull << kClsBits) - 1ull;
+
+// ---- per gene: kseq_lengths, meta, checks.  flags[0]: bit 0 = offsets descend, bit 1 = a gene of 2^20 or more
+// residues; flags[1] = largest genome id.  kseq has S + 1 entries (the last one 0) so its exclusive scan ends in N.
+__global__ void __launch_bounds__(256) gene_meta_kernel(const uint64_t* __restrict__ off, const uint32_t* __restrict__ genome_ids,
+                                                         uint32_t S, int k, uint32_t* __restrict__ kseq, uint2* __restrict__ meta,
+                                                         uint32_t* __restrict__ flags) {
+    const uint32_t s = blockIdx.x * 256u + threadIdx.x;
+    uint32_t err = 0, gid = 0;
+    if (s < S) {
+        const uint64_t o0 = off[s], o1 = off[s + 1];
+        uint32_t kl = 0;
+        if (o1 < o0) {
+            err = 1;
+        } else {
+            const uint64_t len = o1 - o0;
+            if (len >= (1ull << 20)) err = 2;
+            else if (len >= (uint64_t)k) kl = (uint32_t)(len - (uint64_t)k + 1);  // library.cpp:250
+        }
+        gid = genome_ids[s];
+        kseq[s] = kl;
+        meta[s] = make_uint2(kl, gid);
+    } else if (s == S) {
+        kseq[S] = 0;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        err |= __shfl_xor_sync(0xffffffffu, err, d);
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, gid, d);
+        gid = o > gid ? o : gid;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (err) atomicOr(&flags[0], err);
+        atomicMax(&flags[1], gid);
+    }
+}
 
 // ---- alphabet histogram: 16-B loads, per-warp privatised shared histograms
 __global__ void __launch_bounds__(256) byte_hist_kernel(const uint8_t* __restrict__ res, uint64_t n,
@@ -64,7 +105,7 @@ __global__ void __launch_bounds__(256) byte_hist_kernel(const uint8_t* __restric
 
 // ---- k-mer encode: one warp per gene, lanes stride over positions; key = rank << seq_bits | gene
 __global__ void __launch_bounds__(256) encode_kernel(const uint8_t* __restrict__ res, const uint64_t* __restrict__ gene_off,
-                                                      const uint64_t* __restrict__ key_off, uint32_t S, int k, uint32_t base,
+                                                      const uint32_t* __restrict__ key_off, uint32_t S, int k, uint32_t base,
                                                       int seq_bits, ValTable vt, uint64_t* __restrict__ keys) {
     __shared__ uint8_t val[256];
     val[threadIdx.x] = vt.v[threadIdx.x];
@@ -72,121 +113,195 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t* __restrict__
     const unsigned lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * 256u) >> 5;
     for (uint32_t g = (blockIdx.x * 256u + threadIdx.x) >> 5; g < S; g += warps) {
-        const uint64_t ko = key_off[g];
-        const uint32_t nk = (uint32_t)(key_off[g + 1] - ko);
+        const uint32_t ko = key_off[g];
+        const uint32_t nk = key_off[g + 1] - ko;
         const uint8_t* p = res + gene_off[g];
         for (uint32_t i = lane; i < nk; i += 32) {
             uint64_t r = 0;
             for (int j = 0; j < k; j++) r = r * base + val[p[i + j]];
-            keys[ko + i] = (r << seq_bits) | g;
+            keys[(uint64_t)ko + i] = (r << seq_bits) | g;
         }
     }
 }
 
-// ---- dedup part 1: flags[i] = 1 iff key i starts a run of equal keys
-__global__ void __launch_bounds__(256) head_flag_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ flags) {
-    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+// ---- count dedup + rank groups, two reads of the sorted keys
+//
+// A key position is an entry head if its (rank, gene) differs from the position before, and a group head if its rank
+// differs.  entry_count_kernel counts both per tile; after a scan of the tile counts entry_apply_kernel writes, per
+// entry e: post[e] (gene, bit 31 if the key repeats), post_cnt[e], ent_gid[e] = its rank group, and grp_head[g] for
+// the entry that opens group g.  The tail merge of the reference (library.cpp:300-306: at the last entry the open run
+// [start, i+1) is closed whatever its rank) means the LAST entry never opens a group of its own unless it is the only
+// entry: it joins the group before it, and *spurious tells the host that one counted group head was dropped.
+static const int kEntThreads = 512;
+static const int kEntItems = 8;
+static const int kEntTile = kEntThreads * kEntItems;  // 4096 keys per block
+
+// flags of the kEntItems consecutive keys of this thread: bit j of hm / gm = key j is an entry / group head
+__device__ __forceinline__ void entry_flags(const uint64_t* __restrict__ keys, uint64_t N, int seq_bits, uint64_t base,
+                                            uint64_t (&kv)[kEntItems], unsigned& hm, unsigned& gm) {
+    uint64_t prev = 0;
+    if (base > 0 && base <= N) prev = keys[base - 1];
+    hm = gm = 0;
+#pragma unroll
+    for (int j = 0; j < kEntItems; j++) {
+        const uint64_t idx = base + j;
+        kv[j] = idx < N ? keys[idx] : 0ull;
+        if (idx < N) {
+            const bool first = idx == 0;
+            if (first || kv[j] != prev) hm |= 1u << j;
+            if (first || (kv[j] >> seq_bits) != (prev >> seq_bits)) gm |= 1u << j;
+        }
+        prev = kv[j];
+    }
 }
 
-// ent_pos[e] = position in the sorted key list of the e-th distinct key
-__global__ void __launch_bounds__(256) head_scatter_kernel(const uint64_t* __restrict__ keys, uint64_t n,
-                                                            const uint32_t* __restrict__ excl, uint32_t* __restrict__ ent_pos) {
-    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i < n && (i == 0 || keys[i] != keys[i - 1])) ent_pos[excl[i]] = (uint32_t)i;
+__global__ void __launch_bounds__(kEntThreads) entry_count_kernel(const uint64_t* __restrict__ keys, uint64_t N, int seq_bits,
+                                                                   uint32_t* __restrict__ tile_heads, uint32_t* __restrict__ tile_gheads) {
+    __shared__ uint32_t scratch[33];
+    const uint64_t base = (uint64_t)blockIdx.x * kEntTile + (uint64_t)threadIdx.x * kEntItems;
+    uint64_t kv[kEntItems];
+    unsigned hm, gm;
+    entry_flags(keys, N, seq_bits, base, kv, hm, gm);
+    uint32_t tot;
+    prims::block_excl_scan<kEntThreads>((uint32_t)__popc(hm) | ((uint32_t)__popc(gm) << 16), scratch, &tot);
+    if (threadIdx.x == 0) {
+        tile_heads[blockIdx.x] = tot & 0xFFFFu;
+        tile_gheads[blockIdx.x] = tot >> 16;
+    }
 }
 
-// per entry: posting (seq, count); rflag = 1 iff the entry opens a rank group.  The tail merge of the reference
-// (library.cpp:300-306: at the last entry the open run [start, i+1) is closed whatever its rank) means the last
-// entry never opens a group of its own unless it is the only entry.
-__global__ void __launch_bounds__(256) entries_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ent_pos,
-                                                       uint32_t U, uint64_t N, int seq_bits, uint32_t* __restrict__ post,
-                                                       uint32_t* __restrict__ post_cnt, uint32_t* __restrict__ rflag,
-                                                       uint64_t* __restrict__ ent_rank) {
-    const uint32_t e = blockIdx.x * 256u + threadIdx.x;
-    if (e >= U) return;
-    const uint32_t p = ent_pos[e];
-    const uint32_t pn = (e + 1 < U) ? ent_pos[e + 1] : (uint32_t)N;
-    const uint64_t key = keys[p];
-    const uint64_t rank = key >> seq_bits;
-    const uint32_t cnt = pn - p;
-    post[e] = (uint32_t)(key & ((1ull << seq_bits) - 1ull)) | (cnt > 1 ? 0x80000000u : 0u);
-    post_cnt[e] = cnt;
-    uint32_t f;
-    if (e == 0)
-        f = 1;
-    else if (e == U - 1)
-        f = 0;
-    else
-        f = ((keys[ent_pos[e - 1]] >> seq_bits) != rank) ? 1u : 0u;
-    rflag[e] = f;
-    if (ent_rank) ent_rank[e] = rank;
+__global__ void __launch_bounds__(kEntThreads) entry_apply_kernel(const uint64_t* __restrict__ keys, uint64_t N, int seq_bits,
+                                                                   const uint32_t* __restrict__ tile_head_off,
+                                                                   const uint32_t* __restrict__ tile_ghead_off, uint32_t U,
+                                                                   uint32_t* __restrict__ post, uint32_t* __restrict__ post_cnt,
+                                                                   uint32_t* __restrict__ ent_gid, uint32_t* __restrict__ grp_head,
+                                                                   uint64_t* __restrict__ ent_rank, uint32_t* __restrict__ spurious) {
+    __shared__ uint32_t scratch[33];
+    const uint64_t base = (uint64_t)blockIdx.x * kEntTile + (uint64_t)threadIdx.x * kEntItems;
+    uint64_t kv[kEntItems];
+    unsigned hm, gm;
+    entry_flags(keys, N, seq_bits, base, kv, hm, gm);
+    uint32_t tot;
+    const uint32_t ex = prims::block_excl_scan<kEntThreads>((uint32_t)__popc(hm) | ((uint32_t)__popc(gm) << 16), scratch, &tot);
+    uint32_t e = tile_head_off[blockIdx.x] + (ex & 0xFFFFu);       // entries before this thread's keys
+    uint32_t gcount = tile_ghead_off[blockIdx.x] + (ex >> 16);     // group heads before this thread's keys
+    const uint64_t seq_mask = (1ull << seq_bits) - 1ull;
+#pragma unroll
+    for (int j = 0; j < kEntItems; j++) {
+        const uint64_t idx = base + j;
+        if (idx >= N) break;
+        bool gh = (gm >> j) & 1u;
+        if ((hm >> j) & 1u) {
+            if (gh && e == U - 1 && e != 0) {  // the tail merge
+                gh = false;
+                *spurious = 1;
+            } else if (gh) {
+                gcount++;
+            }
+            const uint32_t gid = gcount - 1;
+            // multiplicity: equal keys follow each other
+            uint64_t nxt = ~kv[j];
+            if (j + 1 < kEntItems) {
+                if (idx + 1 < N) nxt = kv[j + 1 < kEntItems ? j + 1 : j];
+            } else if (idx + 1 < N) {
+                nxt = keys[idx + 1];
+            }
+            uint32_t cnt = 1;
+            if (nxt == kv[j]) {
+                cnt = 2;
+                while (idx + cnt < N && keys[idx + cnt] == kv[j]) cnt++;
+            }
+            post[e] = (uint32_t)(kv[j] & seq_mask) | (cnt > 1 ? 0x80000000u : 0u);
+            post_cnt[e] = cnt;
+            ent_gid[e] = gid;
+            if (gh) grp_head[gid] = e;
+            if (ent_rank) ent_rank[e] = kv[j] >> seq_bits;
+            e++;
+        }
+    }
 }
 
-// grp_head[g] = first entry of group g; ent_gid[e] = group of entry e
-__global__ void __launch_bounds__(256) group_heads_kernel(const uint32_t* __restrict__ rflag, const uint32_t* __restrict__ excl,
-                                                           uint32_t U, uint32_t* __restrict__ grp_head, uint32_t* __restrict__ ent_gid) {
-    const uint32_t e = blockIdx.x * 256u + threadIdx.x;
-    if (e >= U) return;
-    const uint32_t f = rflag[e];
-    const uint32_t g = excl[e] + f - 1u;
-    ent_gid[e] = g;
-    if (f) grp_head[g] = e;
+// grp_head[groups] = U, with groups = counted group heads minus the one the tail merge dropped
+__global__ void group_tail_kernel(uint32_t* __restrict__ grp_head, uint32_t counted, const uint32_t* __restrict__ spurious, uint32_t U) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) grp_head[counted - *spurious] = U;
 }
 
-// per entry in a shared group (length >= 2): mark it, count it for its gene, add the group length to the gene's
-// cost (computation_costs[].total_visited, library.cpp:327).
-__global__ void __launch_bounds__(256) shared_mark_kernel(const uint32_t* __restrict__ post, const uint32_t* __restrict__ ent_gid,
-                                                           const uint32_t* __restrict__ grp_head, uint32_t U,
-                                                           uint32_t* __restrict__ sflag, uint32_t* __restrict__ gene_cnt,
-                                                           uint32_t* __restrict__ gene_short, uint32_t short_max,
-                                                           uint32_t* __restrict__ gene_huge, uint32_t huge_min,
-                                                           unsigned long long* __restrict__ visited) {
+// ---- forward lists by counting sort on the gene.  List classes: 0 short (<= short_max), 1 long, 2 huge (> huge_min).
+__device__ __forceinline__ uint32_t list_class(uint32_t gl, uint32_t short_max, uint32_t huge_min) {
+    return gl <= short_max ? 0u : (gl > huge_min ? 2u : 1u);
+}
+
+// cls[gene] += 1 in the field of the entry's list class, for every entry of a shared group (length >= 2)
+__global__ void __launch_bounds__(256) fwd_count_kernel(const uint32_t* __restrict__ post, const uint32_t* __restrict__ ent_gid,
+                                                         const uint32_t* __restrict__ grp_head, uint32_t U, uint32_t short_max,
+                                                         uint32_t huge_min, unsigned long long* __restrict__ cls) {
     const uint32_t e = blockIdx.x * 256u + threadIdx.x;
     if (e >= U) return;
     const uint32_t g = ent_gid[e];
     const uint32_t gl = grp_head[g + 1] - grp_head[g];
-    const uint32_t gene = post[e] & 0x7FFFFFFFu;
-    const uint32_t s = gl >= 2 ? 1u : 0u;
-    sflag[e] = s;
-    if (s) {
-        atomicAdd(&gene_cnt[gene], 1u);
-        if (gl <= short_max) atomicAdd(&gene_short[gene], 1u);
-        if (gl > huge_min) atomicAdd(&gene_huge[gene], 1u);
-        atomicAdd(&visited[gene], (unsigned long long)gl);
-    }
+    if (gl >= 2) atomicAdd(&cls[post[e] & 0x7FFFFFFFu], 1ull << (kClsBits * list_class(gl, short_max, huge_min)));
 }
 
-// compact the shared entries into sort keys (gene << 33 | list class << 31 | entry): sorted on the gene AND the
-// class, a gene's forward list holds its short posting lists first, then the long ones, then the huge ones, ranks
-// ascending in each part
-__global__ void __launch_bounds__(256) fwd_keys_kernel(const uint32_t* __restrict__ post, const uint32_t* __restrict__ sflag,
-                                                        const uint32_t* __restrict__ excl, const uint32_t* __restrict__ ent_gid,
-                                                        const uint32_t* __restrict__ grp_head, uint32_t short_max, uint32_t huge_min,
-                                                        uint32_t U, uint64_t* __restrict__ fkeys) {
+// tot[s] = forward entries of gene s (tot has S + 1 entries, the last one 0: its exclusive scan is fwd_ptr)
+__global__ void __launch_bounds__(256) fwd_totals_kernel(const unsigned long long* __restrict__ cls, uint32_t S, uint32_t* __restrict__ tot) {
+    const uint32_t s = blockIdx.x * 256u + threadIdx.x;
+    if (s > S) return;
+    uint32_t t = 0;
+    if (s < S) {
+        const unsigned long long c = cls[s];
+        t = (uint32_t)(c & kClsMask) + (uint32_t)((c >> kClsBits) & kClsMask) + (uint32_t)((c >> (2 * kClsBits)) & kClsMask);
+    }
+    tot[s] = t;
+}
+
+// places every shared entry in its gene's forward list: class segment from cls, slot inside the segment from a
+// running cursor (same packing as cls, zero at entry)
+__global__ void __launch_bounds__(256) fwd_scatter_kernel(const uint32_t* __restrict__ post, const uint32_t* __restrict__ post_cnt,
+                                                           const uint32_t* __restrict__ ent_gid, const uint32_t* __restrict__ grp_head,
+                                                           uint32_t U, uint32_t short_max, uint32_t huge_min,
+                                                           const unsigned long long* __restrict__ cls, const uint32_t* __restrict__ fwd_ptr,
+                                                           unsigned long long* __restrict__ cursor, uint2* __restrict__ fwd,
+                                                           uint32_t* __restrict__ fwd_cnt) {
     const uint32_t e = blockIdx.x * 256u + threadIdx.x;
     if (e >= U) return;
-    if (sflag[e]) {
-        const uint32_t g = ent_gid[e];
-        const uint32_t gl = grp_head[g + 1] - grp_head[g];
-        const uint64_t cls = gl <= short_max ? 0ull : (gl > huge_min ? 2ull : 1ull);
-        fkeys[excl[e]] = ((uint64_t)(post[e] & 0x7FFFFFFFu) << 33) | (cls << 31) | e;
-    }
-}
-
-// forward lists from the gene-sorted keys; bit 31 of the length flags an own multiplicity > 1 (then fwd_cnt is read)
-__global__ void __launch_bounds__(256) fwd_fill_kernel(const uint64_t* __restrict__ fkeys, uint32_t R,
-                                                        const uint32_t* __restrict__ post_cnt, const uint32_t* __restrict__ ent_gid,
-                                                        const uint32_t* __restrict__ grp_head, uint2* __restrict__ fwd,
-                                                        uint32_t* __restrict__ fwd_cnt) {
-    const uint32_t j = blockIdx.x * 256u + threadIdx.x;
-    if (j >= R) return;
-    const uint32_t e = (uint32_t)fkeys[j] & 0x7FFFFFFFu;
     const uint32_t g = ent_gid[e];
     const uint32_t gs = grp_head[g];
-    const uint32_t cnt = post_cnt[e];
-    fwd[j] = make_uint2(gs, (grp_head[g + 1] - gs) | (cnt > 1 ? 0x80000000u : 0u));
-    fwd_cnt[j] = cnt;
+    const uint32_t gl = grp_head[g + 1] - gs;
+    if (gl < 2) return;
+    const uint32_t p = post[e];
+    const uint32_t gene = p & 0x7FFFFFFFu;
+    const uint32_t c = list_class(gl, short_max, huge_min);
+    const unsigned long long old = atomicAdd(&cursor[gene], 1ull << (kClsBits * c));
+    const unsigned long long cl = cls[gene];
+    uint32_t slot = fwd_ptr[gene] + (uint32_t)((old >> (kClsBits * c)) & kClsMask);
+    if (c >= 1) slot += (uint32_t)(cl & kClsMask);
+    if (c == 2) slot += (uint32_t)((cl >> kClsBits) & kClsMask);
+    fwd[slot] = make_uint2(gs, gl | (p & 0x80000000u));  // bit 31: the gene's own multiplicity > 1 (then fwd_cnt is read)
+    if (p & 0x80000000u) fwd_cnt[slot] = post_cnt[e];
+}
+
+// visited[s] = sum of the posting-list lengths of gene s's forward entries (computation_costs[].total_visited,
+// library.cpp:327); *total += the sum over all genes ("Total cost: N lookups", library.cpp:349).  One warp per gene.
+__global__ void __launch_bounds__(256) gene_visited_kernel(const uint2* __restrict__ fwd, const uint32_t* __restrict__ fwd_ptr, uint32_t S,
+                                                            unsigned long long* __restrict__ visited, unsigned long long* __restrict__ total) {
+    __shared__ unsigned long long s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t s = (blockIdx.x * 256u + threadIdx.x) >> 5;
+    if (s < S) {
+        const uint32_t f0 = fwd_ptr[s], f1 = fwd_ptr[s + 1];
+        unsigned long long v = 0;
+        for (uint32_t f = f0 + lane; f < f1; f += 32) v += fwd[f].y & 0x7FFFFFFFu;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) {
+            visited[s] = v;
+            if (v) atomicAdd(&s_sum, v);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_sum) atomicAdd(total, s_sum);
 }
 
 // per-entry group (start, length) for pd_entries (tests / diagnostics)

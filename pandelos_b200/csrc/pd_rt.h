@@ -19,6 +19,11 @@
 #include <chrono>
 #else
 #include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
 #endif
 
 namespace pd {
@@ -61,8 +66,99 @@ inline size_t max_optin_smem() {
     PD_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, d));
     return static_cast<size_t>(n);
 }
-inline void* dmalloc(size_t n) { void* p = nullptr; PD_CUDA(cudaMalloc(&p, n ? n : 1)); return p; }
-inline void dfree(void* p) { if (p) cudaFree(p); }
+// Device memory comes from a small caching allocator: an index build allocates ~20 multi-gigabyte buffers, and
+// cudaMalloc / cudaFree of those cost milliseconds each (cudaFree also synchronises the device).  dfree() only
+// queues a block; collect() — called where the engine has synchronised anyway — waits for the device and makes the
+// queued blocks reusable by later dmalloc() calls of a similar size.  Blocks are cached per device.
+struct BlockCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks;                      // size -> block
+    std::unordered_map<void*, std::pair<size_t, int>> live;        // block -> (size, device), handed out or queued
+    std::vector<void*> pending;                                    // freed, possibly still in use by queued kernels
+    size_t cached = 0;
+};
+inline BlockCache& block_cache(int dev) {
+    static BlockCache caches[16];
+    return caches[dev & 15];
+}
+inline size_t round_block(size_t n) {
+    if (n == 0) n = 1;
+    const size_t g = n >= (size_t(8) << 20) ? (size_t(2) << 20) : 512;
+    return (n + g - 1) / g * g;
+}
+inline void trim_cache(BlockCache& c, size_t keep) {  // c.mu held
+    while (c.cached > keep && !c.free_blocks.empty()) {
+        auto it = std::prev(c.free_blocks.end());
+        c.cached -= it->first;
+        cudaFree(it->second);
+        c.live.erase(it->second);
+        c.free_blocks.erase(it);
+    }
+}
+inline void collect() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    BlockCache& c = block_cache(dev);
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        if (c.pending.empty()) return;
+    }
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(c.mu);
+    for (void* p : c.pending) {
+        const size_t sz = c.live[p].first;
+        c.free_blocks.emplace(sz, p);
+        c.cached += sz;
+    }
+    c.pending.clear();
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) trim_cache(c, total_b / 2);
+}
+inline void* dmalloc(size_t n) {
+    n = round_block(n);
+    int dev = current_device();
+    BlockCache& c = block_cache(dev);
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.free_blocks.lower_bound(n);
+        if (it != c.free_blocks.end() && it->first <= n + n / 8 + (size_t(1) << 20)) {
+            void* p = it->second;
+            c.cached -= it->first;
+            c.free_blocks.erase(it);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {  // give everything cached back to the driver and try once more
+        cudaGetLastError();
+        collect();
+        {
+            std::lock_guard<std::mutex> lk(c.mu);
+            trim_cache(c, 0);
+        }
+        e = cudaMalloc(&p, n);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        throw pd::Error(-5, std::string("cudaMalloc of ") + std::to_string(n) + " bytes: " + cudaGetErrorString(e));
+    }
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.live[p] = std::make_pair(n, dev);
+    return p;
+}
+inline void dfree(void* p) {
+    if (!p) return;
+    for (int d = 0; d < 16; d++) {
+        BlockCache& c = block_cache(d);
+        std::lock_guard<std::mutex> lk(c.mu);
+        if (c.live.count(p)) {
+            c.pending.push_back(p);
+            return;
+        }
+    }
+    cudaFree(p);
+}
 inline void* hmalloc(size_t n) { void* p = nullptr; PD_CUDA(cudaMallocHost(&p, n ? n : 1)); return p; }
 inline void hfree(void* p) { if (p) cudaFreeHost(p); }
 inline stream_t stream_create() { stream_t s; PD_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return s; }
@@ -117,6 +213,7 @@ inline void* dmalloc(size_t n) {
     return p;
 }
 inline void dfree(void* p) { free(p); }
+inline void collect() {}
 inline void* hmalloc(size_t n) { return malloc(n ? n : 1); }
 inline void hfree(void* p) { free(p); }
 inline stream_t stream_create() { return 0; }

@@ -60,6 +60,7 @@ struct ScoreArgs {
     // work
     const RowDesc* rows;
     uint32_t n_rows;
+    const uint32_t* n_rows_dev;  // non-null: the row count lives on the device (lists built by classify_rows_kernel)
     uint32_t* cursor;
     // parameters
     uint32_t G;
@@ -555,12 +556,13 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
         cnt[i] = 0;
     }
     const uint4* rows4 = reinterpret_cast<const uint4*>(a.rows);
+    const uint32_t n_rows = a.n_rows_dev ? *a.n_rows_dev : a.n_rows;
     uint32_t idx_next = 0;  // thread 0: row claimed for the iteration after this one
     if (tid == 0) {
         const uint32_t ri = atomicAdd(a.cursor, 1u);
         idx_next = atomicAdd(a.cursor, 1u);
         uint4 d0 = make_uint4(kEmpty, 0u, 0u, 0u), d1 = make_uint4(0u, 0u, 0u, 0u);
-        if (ri < a.n_rows) {
+        if (ri < n_rows) {
             d0 = rows4[2 * (size_t)ri];
             d1 = rows4[2 * (size_t)ri + 1];
         }
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
         uint4 nd0 = make_uint4(kEmpty, 0u, 0u, 0u), nd1 = make_uint4(0u, 0u, 0u, 0u);
         uint32_t idx_after = 0;
         if (tid == 0) {  // both are consumed after the accumulate phase
-            if (idx_next < a.n_rows) {
+            if (idx_next < n_rows) {
                 nd0 = rows4[2 * (size_t)idx_next];
                 nd1 = rows4[2 * (size_t)idx_next + 1];
             }
@@ -758,6 +760,7 @@ __global__ void __launch_bounds__(kDenseThreads) score_rows_dense_kernel(ScoreAr
     uint32_t* tcv = pcv + d.S;
     uint32_t* touched = tcv + d.S;
     unsigned long long pairs = 0;
+    const uint32_t n_rows = a.n_rows_dev ? *a.n_rows_dev : a.n_rows;
 
     for (;;) {
         if (tid == 0) {
@@ -766,7 +769,7 @@ __global__ void __launch_bounds__(kDenseThreads) score_rows_dense_kernel(ScoreAr
         }
         __syncthreads();
         const uint32_t ri = s_row;
-        if (ri >= a.n_rows) break;
+        if (ri >= n_rows) break;
         const RowDesc rw = a.rows[ri];
         RowCtx rc;
         rc.r = rw.gene;
@@ -825,6 +828,62 @@ __global__ void __launch_bounds__(kDenseThreads) score_rows_dense_kernel(ScoreAr
 #pragma unroll
     for (int dd = 16; dd > 0; dd >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, dd);
     if (lane == 0 && pairs) atomicAdd(a.n_pairs, pairs);
+}
+
+// ------------------------------------------------------------------------------------------------ row lists
+
+// Builds the row descriptors of one scoring call on the device and sorts them into the first-try table levels by
+// their bound on distinct columns, min(total_visited, S).  Row i is gene genes[i] (or gene_base + i) and writes
+// best hits to row i of the call's table.
+struct ClassifyArgs {
+    uint32_t n;
+    const uint32_t* genes;
+    uint32_t gene_base;
+    uint32_t S;
+    const unsigned long long* visited;
+    const uint32_t* fwd_ptr;
+    const unsigned long long* cls;   // forward entries per list class, 3 x cls_bits
+    uint32_t cls_bits;
+    const uint2* meta;
+    unsigned long long max_cols[3];
+    RowDesc* rows;                   // three lists of capacity n: rows + level * n
+    uint32_t* counts;                // [3]
+    unsigned long long* stats;       // [0] += postings the rows visit, [1] += their forward entries
+};
+
+__global__ void __launch_bounds__(256) classify_rows_kernel(ClassifyArgs a) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    unsigned long long lk = 0, fe = 0;
+    if (i < a.n) {
+        const uint32_t g = a.genes ? a.genes[i] : a.gene_base + i;
+        const unsigned long long v = a.visited[g];
+        const unsigned long long cols = v < a.S ? v : a.S;
+        const int level = cols <= a.max_cols[0] ? 0 : (cols <= a.max_cols[1] ? 1 : 2);
+        const unsigned long long cl = a.cls[g];
+        const unsigned long long m = (1ull << a.cls_bits) - 1ull;
+        const uint2 mg = a.meta[g];
+        RowDesc d;
+        d.gene = g;
+        d.bh_row = i;
+        d.fb = a.fwd_ptr[g];
+        d.fe = a.fwd_ptr[g + 1];
+        d.fm = d.fb + (uint32_t)(cl & m);
+        d.fh = d.fe - (uint32_t)((cl >> (2 * a.cls_bits)) & m);
+        d.kr = mg.x;
+        d.gr = mg.y;
+        a.rows[(size_t)level * a.n + atomicAdd(&a.counts[level], 1u)] = d;
+        lk = v;
+        fe = d.fe - d.fb;
+    }
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) {
+        lk += __shfl_xor_sync(0xffffffffu, lk, dd);
+        fe += __shfl_xor_sync(0xffffffffu, fe, dd);
+    }
+    if ((threadIdx.x & 31) == 0 && fe) {
+        atomicAdd(&a.stats[0], lk);
+        atomicAdd(&a.stats[1], fe);
+    }
 }
 
 }  // namespace sk
