@@ -297,17 +297,30 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         launches += 2;
         scratch.ensure(prims::scan_tmp_words((uint64_t)S + 1) + 16);
         prims::exclusive_scan_u32(gene_tot.p, fwd_ptr.p, (uint64_t)S + 1, scratch.p, nullptr, st, &launches);
-        fwd.alloc(U);  // R <= U: sized without waiting for R
-        fwd_cnt.alloc(U);
-        PD_LAUNCH(ik::fwd_scatter_kernel, blocks_for(U), 256, 0, st, (const uint32_t*)post.p, (const uint32_t*)post_cnt.p,
-                  (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, U, sk::kShortList, sk::kHugeList, (const unsigned long long*)cls.p,
-                  (const uint32_t*)fwd_ptr.p, cursor.p, fwd.p, fwd_cnt.p);
+        uint32_t h_R = 0;
+        rt::d2h(&h_R, fwd_ptr.p + S, sizeof(uint32_t), st);
+        rt::sync(st);
+        R = h_R;
+        fwd.alloc(std::max<size_t>(R, 1));
+        fwd_cnt.alloc(std::max<size_t>(R, 1));
+        if (R) {
+            // transpose in two steps: records partitioned by gene bucket, then placed bucket after bucket
+            const uint32_t bshift = (uint32_t)std::max(0, seq_bits - 8);
+            rt::DevBuf<uint4> records(R);
+            rt::DevBuf<uint32_t> bucket_cur(ik::kMaxBuckets);
+            rt::zero(bucket_cur.p, sizeof(uint32_t) * ik::kMaxBuckets, st);
+            PD_LAUNCH(ik::fwd_partition_kernel, blocks_for(U, ik::kPartTile), ik::kPartThreads, 0, st, (const uint32_t*)post.p,
+                      (const uint32_t*)post_cnt.p, (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, U, S, sk::kShortList, sk::kHugeList,
+                      bshift, (const uint32_t*)fwd_ptr.p, bucket_cur.p, records.p);
+            PD_LAUNCH(ik::fwd_place_kernel, blocks_for(R), 256, 0, st, (const uint4*)records.p, R, (const unsigned long long*)cls.p,
+                      (const uint32_t*)fwd_ptr.p, cursor.p, fwd.p, fwd_cnt.p);
+            launches += 2;
+        }
         PD_LAUNCH(ik::gene_visited_kernel, blocks_for((uint64_t)S * 32), 256, 0, st, (const uint2*)fwd.p, (const uint32_t*)fwd_ptr.p, S,
                   d_visited.p, d_lookups.p);
-        launches += 2;
+        launches += 1;
         uint32_t h_spur = 0;
         rt::d2h(&h_spur, d_spur.p, sizeof(uint32_t), st);
-        rt::d2h(&R, fwd_ptr.p + S, sizeof(uint32_t), st);
         rt::d2h(&lookups, d_lookups.p, sizeof(unsigned long long), st);
         t_fwd.stop();
         rt::sync(st);

@@ -8,7 +8,8 @@
 //   entry_apply_kernel    (equal (rank, gene) -> one entry with its multiplicity) and rank groups incl. the tail
 //                         merge                                                  library.cpp:297-306
 //   fwd_count_kernel /    per-gene forward lists (the transpose of the posting   library.cpp:314-328
-//   fwd_scatter_kernel    lists) by counting sort on the gene: count, scan, place
+//   fwd_partition_kernel/ lists) by counting sort on the gene: count, scan, partition by gene bucket, place
+//   fwd_place_kernel
 //   gene_visited_kernel   cost model: total_visited per gene                      library.cpp:327
 //
 // HBM layout produced (all SoA, 32-bit indices; the reference's 16-B kmer_rank / 24-B kmers_range records are gone):
@@ -254,30 +255,91 @@ __global__ void __launch_bounds__(256) fwd_totals_kernel(const unsigned long lon
     tot[s] = t;
 }
 
-// places every shared entry in its gene's forward list: class segment from cls, slot inside the segment from a
-// running cursor (same packing as cls, zero at entry)
-__global__ void __launch_bounds__(256) fwd_scatter_kernel(const uint32_t* __restrict__ post, const uint32_t* __restrict__ post_cnt,
-                                                           const uint32_t* __restrict__ ent_gid, const uint32_t* __restrict__ grp_head,
-                                                           uint32_t U, uint32_t short_max, uint32_t huge_min,
-                                                           const unsigned long long* __restrict__ cls, const uint32_t* __restrict__ fwd_ptr,
-                                                           unsigned long long* __restrict__ cursor, uint2* __restrict__ fwd,
-                                                           uint32_t* __restrict__ fwd_cnt) {
-    const uint32_t e = blockIdx.x * 256u + threadIdx.x;
-    if (e >= U) return;
+// Placing ~R records at random 8-byte slots of a multi-gigabyte array is DRAM-page-miss bound, so the transpose runs
+// in two steps: (1) fwd_partition_kernel appends one 16-byte record per shared entry to the region of its gene
+// BUCKET (2^bshift consecutive genes; the region of bucket b is exactly the forward-list range of its genes, so
+// fwd_ptr gives the region bounds for free); (2) fwd_place_kernel reads the records region after region and places
+// them: now all writes of the CTAs in flight fall into one bucket's window of `fwd`, which the L2 holds.
+static const int kPartThreads = 256;
+static const int kPartItems = 8;
+static const int kPartTile = kPartThreads * kPartItems;
+static const int kMaxBuckets = 512;
+
+struct FwdRecord {  // 16 B
+    uint32_t gene, gs, gl_multi, cls_cnt;  // gl | own-count>1 flag; list class | own count << 2
+};
+
+__device__ __forceinline__ bool fwd_record_of(const uint32_t* __restrict__ post, const uint32_t* __restrict__ post_cnt,
+                                              const uint32_t* __restrict__ ent_gid, const uint32_t* __restrict__ grp_head, uint32_t e,
+                                              uint32_t short_max, uint32_t huge_min, FwdRecord* r) {
     const uint32_t g = ent_gid[e];
     const uint32_t gs = grp_head[g];
     const uint32_t gl = grp_head[g + 1] - gs;
-    if (gl < 2) return;
+    if (gl < 2) return false;
     const uint32_t p = post[e];
-    const uint32_t gene = p & 0x7FFFFFFFu;
-    const uint32_t c = list_class(gl, short_max, huge_min);
+    r->gene = p & 0x7FFFFFFFu;
+    r->gs = gs;
+    r->gl_multi = gl | (p & 0x80000000u);
+    r->cls_cnt = list_class(gl, short_max, huge_min) | ((p & 0x80000000u) ? (post_cnt[e] << 2) : (1u << 2));
+    return true;
+}
+
+__global__ void __launch_bounds__(kPartThreads) fwd_partition_kernel(const uint32_t* __restrict__ post, const uint32_t* __restrict__ post_cnt,
+                                                                      const uint32_t* __restrict__ ent_gid,
+                                                                      const uint32_t* __restrict__ grp_head, uint32_t U, uint32_t S,
+                                                                      uint32_t short_max, uint32_t huge_min, uint32_t bshift,
+                                                                      const uint32_t* __restrict__ fwd_ptr, uint32_t* __restrict__ bucket_cur,
+                                                                      uint4* __restrict__ records) {
+    __shared__ uint32_t cnt[kMaxBuckets];
+    __shared__ uint32_t base[kMaxBuckets];
+    const unsigned tid = threadIdx.x;
+    for (unsigned i = tid; i < kMaxBuckets; i += kPartThreads) cnt[i] = 0;
+    __syncthreads();
+    const uint32_t e0 = blockIdx.x * (uint32_t)kPartTile;
+    FwdRecord rec[kPartItems];
+    uint32_t pos[kPartItems];
+    unsigned have = 0;
+#pragma unroll
+    for (int j = 0; j < kPartItems; j++) {
+        const uint32_t e = e0 + j * kPartThreads + tid;
+        if (e < U && fwd_record_of(post, post_cnt, ent_gid, grp_head, e, short_max, huge_min, &rec[j])) {
+            have |= 1u << j;
+            pos[j] = atomicAdd(&cnt[rec[j].gene >> bshift], 1u);
+        }
+    }
+    __syncthreads();
+    const uint32_t nb = ((S - 1) >> bshift) + 1;
+    for (unsigned b = tid; b < nb; b += kPartThreads) {
+        const uint32_t c = cnt[b];
+        base[b] = c ? fwd_ptr[b << bshift] + atomicAdd(&bucket_cur[b], c) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPartItems; j++) {
+        if (have & (1u << j)) {
+            const FwdRecord& r = rec[j];
+            records[base[r.gene >> bshift] + pos[j]] = make_uint4(r.gene, r.gs, r.gl_multi, r.cls_cnt);
+        }
+    }
+}
+
+// record -> its gene's forward list: class segment from cls, slot inside the segment from a running cursor (same
+// packing as cls, zero at entry)
+__global__ void __launch_bounds__(256) fwd_place_kernel(const uint4* __restrict__ records, uint32_t R,
+                                                         const unsigned long long* __restrict__ cls, const uint32_t* __restrict__ fwd_ptr,
+                                                         unsigned long long* __restrict__ cursor, uint2* __restrict__ fwd,
+                                                         uint32_t* __restrict__ fwd_cnt) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= R) return;
+    const uint4 r = records[i];
+    const uint32_t gene = r.x, c = r.w & 3u;
     const unsigned long long old = atomicAdd(&cursor[gene], 1ull << (kClsBits * c));
     const unsigned long long cl = cls[gene];
     uint32_t slot = fwd_ptr[gene] + (uint32_t)((old >> (kClsBits * c)) & kClsMask);
     if (c >= 1) slot += (uint32_t)(cl & kClsMask);
     if (c == 2) slot += (uint32_t)((cl >> kClsBits) & kClsMask);
-    fwd[slot] = make_uint2(gs, gl | (p & 0x80000000u));  // bit 31: the gene's own multiplicity > 1 (then fwd_cnt is read)
-    if (p & 0x80000000u) fwd_cnt[slot] = post_cnt[e];
+    fwd[slot] = make_uint2(r.y, r.z);  // bit 31 of the length: the gene's own multiplicity > 1 (then fwd_cnt is read)
+    if (r.z & 0x80000000u) fwd_cnt[slot] = r.w >> 2;
 }
 
 // visited[s] = sum of the posting-list lengths of gene s's forward entries (computation_costs[].total_visited,

@@ -16,9 +16,9 @@ static const int kScanThreads = 512;
 static const int kScanItems = 8;
 static const int kScanTile = kScanThreads * kScanItems;  // 4096
 
-static const int kSortThreads = 512;
+static const int kSortThreads = 256;
 static const int kSortItems = 16;
-static const int kSortTile = kSortThreads * kSortItems;  // 8192 keys per block
+static const int kSortTile = kSortThreads * kSortItems;  // 4096 keys per block
 static const int kSortWarps = kSortThreads / 32;
 static const int kRadix = 256;
 
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t
 // Stable scatter of one tile.  `offs` is the exclusive scan of the digit-major histogram, i.e.
 // offs[d * tiles + tile] = first output slot of this tile's digit-d keys.
 // Order inside the tile: warp w owns keys [w*512, (w+1)*512); round j covers 32 consecutive keys, one per lane.
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint64_t* __restrict__ keys, uint64_t* __restrict__ out,
+__global__ void __launch_bounds__(kSortThreads, 4) radix_scatter_kernel(const uint64_t* __restrict__ keys, uint64_t* __restrict__ out,
                                                                       uint64_t n, int shift, uint32_t tiles,
                                                                       const uint32_t* __restrict__ offs) {
     PD_DYNAMIC_SMEM(smem_raw);

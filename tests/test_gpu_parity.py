@@ -159,3 +159,25 @@ def test_full_size_properties():
     assert o.total_lookups == pn.info.lookups and o.num_entries == pn.info.U
     check_scores(pn.generateScoresPart(3), o.compute_scores(3), "ecoli10 genome 3")
     pn.close()
+
+
+def test_jni_dropin_against_unmodified_reference_library():
+    """libnative.so (JNI shim over the engine) and the UNMODIFIED reference library, both driven through the same
+    fake JNIEnv (oracle/fakejni.cpp): every Scores field the Java side reads must be identical."""
+    import os
+    from oracle import refjni
+    from pandelos_b200 import build
+    if not refjni.available() or not os.path.exists(build.JNI_LIB):
+        pytest.skip("oracle/_ref or libnative.so not built")
+    w = synth.generate(5, 120, 150.0, 0.1, 71, low_complexity=0.2)
+    k = 4
+    ref = refjni.RefJni()
+    ref.preprocess(w.residues, w.offsets, w.genome_of, k)
+    mine = refjni.RefJni(build.JNI_LIB)
+    mine.preprocess(w.residues, w.offsets, w.genome_of, k)
+    cells = 0
+    for g in range(w.G):
+        a, b = mine.compute_scores(g), ref.compute_scores(g)
+        check_scores(a, b, "jni genome %d" % g)
+        cells += a.scoresCount
+    assert cells > 0
