@@ -7,8 +7,10 @@ A STEP is one pass of the hot path over the rank's share of one synthetic pan-ge
 index build from residues already in HBM (k-mer encode, sort, dedup, groups, forward lists = preprocessSequences)
 followed by scoring of the rank's query genes against the whole index (computeScores: accumulate along posting
 lists, float32 Jaccard, best hits), cells left in HBM.  With N > 1 every rank holds the whole index (built
-redundantly, "built once and replicated") and scores its own block of query genomes; the best-hit slices are then
-all-gathered over NCCL.  Per-rank work is fixed as N grows (scaling "weak"): N = 8 covers the whole data set.
+redundantly, "built once and replicated"); the query genomes of the job (N x 125 of the 1,000) are split into N
+genome-aligned blocks of equal posting-list volume (pandelos_b200/multigpu.py), each rank scores its block, and the
+best-hit slices are all-gathered over NCCL.  Per-rank work is fixed as N grows (scaling "weak"): N = 8 covers the
+whole data set.
 
 metric  = candidate gene pairs scored per second (distinct (row, col != row) cells evaluated, library.cpp:493)
 e2e     = the same through the reference-facing C ABI with HOST buffers: pd_build from host residues, then one
@@ -34,7 +36,7 @@ DEFAULT_WORKLOAD = "scaleout1000"
 # genomes scored per rank (weak scaling); None = all genomes on every rank count once (N must be 1)
 QUERY_GENOMES = {"scaleout1000": 125}
 # genomes of the workload the CPU reference is timed on (bounded sample: ~10-30 s of host work)
-CPU_SAMPLE_GENOMES = {"scaleout1000": 12, "mycoplasma64": 64}
+CPU_SAMPLE_GENOMES = {"scaleout1000": 48, "mycoplasma64": 64}
 
 
 def log(*a):
@@ -199,16 +201,25 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     native.load()
 
+    from pandelos_b200 import multigpu
     name = args.workload
     w, k = make_workload(name)
-    gb = genome_bounds(w)
+    gb = multigpu.genome_bounds(w.genome_of, w.G)
     q = args.query_genomes or QUERY_GENOMES.get(name) or w.G
     q = min(q, w.G)
     if world * q > w.G:
         q = max(1, w.G // world)
-    g0, g1 = rank * q, (rank + 1) * q
-    row0, row1 = int(gb[g0]), int(gb[g1])
     data = native.PangeneIData(w.residues, w.offsets, w.genome_of)
+    # the job's query genes = the first world x q genomes, split by posting-list volume at genome boundaries
+    if world > 1:
+        pn0 = native.PangeneNative(k, data, device=local)
+        _, visited = pn0.gene_stats()
+        pn0.close()
+        bounds = multigpu.balanced_bounds(visited, 0, int(gb[world * q]), world, snap=gb)
+    else:
+        bounds = np.array([0, int(gb[q])], np.int64)
+    row0, row1 = int(bounds[rank]), int(bounds[rank + 1])
+    g0, g1 = int(np.searchsorted(gb, row0)), int(np.searchsorted(gb, row1))
 
     # residues resident in HBM before the timed region
     res_host = torch.from_numpy(w.residues).pin_memory()
@@ -216,20 +227,14 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     G = w.G
-    bh_local = torch.zeros((row1 - row0, G), dtype=torch.float32, device=dev)
-    bh_all = torch.zeros((world * (row1 - row0), G), dtype=torch.float32, device=dev) if world > 1 else None
-    if world > 1:
-        rows_all = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(rows_all, torch.tensor([row1 - row0], dtype=torch.int64, device=dev))
-        max_rows = int(max(int(x.item()) for x in rows_all))
-        bh_local = torch.zeros((max_rows, G), dtype=torch.float32, device=dev)   # padded to the largest slice
-        bh_all = torch.zeros((world * max_rows, G), dtype=torch.float32, device=dev)
+    rows_of_rank = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
+    bh_local = torch.zeros((max(rows_of_rank), G), dtype=torch.float32, device=dev)  # padded to the largest slice
 
     def step():
         pn = native.PangeneNative(k, data, device=local, residues_device_ptr=res_dev.data_ptr())
         st = pn.score_partition_device(row0, row1, best_hit_ptr=bh_local.data_ptr())
         if world > 1:
-            dist.all_gather_into_tensor(bh_all, bh_local)
+            multigpu.allgather_best_hits(dist, bh_local, rows_of_rank, G, dev)
         return pn, st
 
     def barrier():
@@ -281,11 +286,13 @@ def main():
     # ---- roofline of the scoring kernels on this rank (algorithmic bytes)
     rows_n = row1 - row0
     kms = kernel_ms / args.steps
-    # 8 B per posting visited + 8 B per forward entry + 28 B per emitted cell + best-hit table + gene metadata once
-    alg_bytes = 8.0 * stats["lookups"] + 8.0 * stats["fwd_entries"] + 28.0 * stats["cells"] + 4.0 * rows_n * G + 8.0 * info.S
+    # 8 B per posting visited + 12 B per forward entry + 20 B per emitted cell + best-hit table
+    # + gene metadata once (the kernel itself reads 4-byte postings: DESIGN.md "algorithmic bytes")
+    alg_bytes = 8.0 * stats["lookups"] + 12.0 * stats["fwd_entries"] + 20.0 * stats["cells"] + 4.0 * rows_n * G + 8.0 * info.S
     peak, peak_kind = peaks()
     achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "bytes_per_lookup_model": 8, "bytes_per_lookup_read": 4,
                 "kernel": "score_rows_kernel", "kernel_ms_per_step": kms, "peak_kind": peak_kind,
                 "lookups_per_s": stats["lookups"] / (kms * 1e-3) if kms > 0 else 0.0}
 
@@ -346,7 +353,9 @@ def main():
                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "int32+f32", "data": "synthetic",
                "config": {"workload": name, "k": int(k), "genes": int(w.S), "genomes": int(G), "kmers": int(info.N),
-                          "query_genomes_per_rank": int(q), "query_rows_per_rank": int(rows_n), "l2": "flushed between timed steps (256 MiB fill)",
+                          "query_genomes_per_rank": int(q), "query_rows_per_rank": int(rows_n), "query_genomes_this_rank": [g0, g1],
+                          "parallelism": "index replicated, query genomes split by posting-list volume" if world > 1 else "single GPU",
+                          "l2": "flushed between timed steps (256 MiB fill)",
                           "step": "index build from HBM-resident residues + scoring of the rank's query rows" + (" + NCCL allgather of best-hit slices" if world > 1 else "")},
                "lookups_per_s": lookups_all / (ms * 1e-3), "cells_per_step": cells_all, "pairs_per_step": pairs_all,
                "build_ms_per_step": build_ms / args.steps, "score_kernel_ms_per_step": kms,

@@ -13,10 +13,13 @@
 //                forward entries are staged in shared memory (cp.async, double buffered across rows) and split by the
 //                index build into three classes:
 //                  short lists  (<= kShortList)  flattened in batches of 32 lists so every lane has a posting,
-//                  long lists                    one warp walks one list, 4 x 32 consecutive postings per round,
+//                  long lists                    one warp walks one list, 8 x 32 consecutive postings per round,
+//                                                the next round's loads issued while this round is accumulated,
 //                  huge lists   (> kHugeList)    all warps of the CTA stride over the same list.
-//                Every round first tries the branch-free case for its 4 postings per lane (column already in its
-//                home slot: one LDS + one ATOMS), then a per-lane state machine probes / inserts what is left.
+//   table        buckets of 4 slots: a posting's column is hashed to its home bucket, read with one 16-byte shared
+//                load, matched branch-free against the 4 keys and counted with one shared-memory atomic; postings
+//                that miss (first visit of a column in this row, bucket overflow) go to a per-warp queue that is
+//                probed / inserted 32 postings at a time, every lane busy.
 //   finalize     warp-local: each warp compacts the occupied slots of its slice of the table, applies the exact
 //                integer validity gate, reserves output space with one atomic per warp and row, then computes the
 //                float32 Jaccard only for the cells that pass                             library.cpp:493-505
