@@ -509,6 +509,11 @@ void launch_rows_t(ScoreContext& c, sk::ScoreArgs& a, size_t smem) {
 void launch_rows(ScoreContext& c, sk::ScoreArgs a, const Level& lv, int cursor_id) {
     if (a.n_rows == 0) return;
     a.hbits = lv.hbits;
+    {   // umulhi(c, hmul) < buckets for every c < S
+        const uint64_t buckets = (1ull << lv.hbits) / 4;
+        const uint64_t S = std::max<uint64_t>(c.ix->info.S, 1);
+        a.hmul = (uint32_t)std::min<uint64_t>((buckets << 32) / S, 0xFFFFFFFFull);
+    }
     a.fcap = lv.fcap;
     a.cursor = c.d_cursors.p + cursor_id;
     const size_t smem = sk::score_smem_bytes(lv.hbits, lv.fcap, lv.threads);

@@ -69,6 +69,11 @@ struct ScoreArgs {
     uint32_t G;
     uint32_t k2;      // 2k: perc >= thr  <=>  2k * pc >= K  (exact for K < 2^20, see gate())
     uint32_t hbits;   // log2 of the hash table slots
+    // Home bucket of column c = floor(c * buckets / S) = umulhi(c, hmul): ORDER PRESERVING on purpose.  Posting lists
+    // are sorted by gene and a row's homologs are spread over the genomes, so the lanes of a warp, which hold
+    // consecutive postings, hit ascending, well separated buckets: few shared-memory bank conflicts, where a mixing
+    // hash makes every access a random one.  Columns that crowd one bucket spill by linear probing as before.
+    uint32_t hmul;
     uint32_t fcap;    // forward entries staged per segment
     // outputs
     float* o_score;
@@ -166,7 +171,7 @@ struct Tab {
     saddr_t keys_sa;  // the same two arrays by shared-window address
     saddr_t cnt_sa;
     uint32_t mask;
-    uint32_t shift;  // 32 - (hbits - 2): hash -> bucket
+    uint32_t hmul;   // column -> home bucket: umulhi(c, hmul), see ScoreArgs::hmul
     uint32_t limit;  // probe limit
     uint32_t* xbase;  // side table: keys, d_inter, d_pc, d_tc, touched list (kXSlots each)
     RowCtl* ctl;
@@ -178,7 +183,8 @@ struct Tab {
 };
 
 // first slot of the column's home bucket
-__device__ __forceinline__ uint32_t home_slot(const Tab& t, uint32_t c) { return ((c * 0x9E3779B1u) >> t.shift) << 2; }
+// (clamped: kNone items, which are never counted, still compute an address)
+__device__ __forceinline__ uint32_t home_slot(const Tab& t, uint32_t c) { return min(__umulhi(c, t.hmul) << 2, t.mask & ~3u); }
 
 __device__ __forceinline__ uint32_t x_find_or_insert(const Tab& t, uint32_t c) {
     uint32_t h = __umulhi(c * 0x85EBCA6Bu, kXSlots);
@@ -550,7 +556,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
     t.keys_sa = smem_addr(keys);
     t.cnt_sa = smem_addr(cnt);
     t.mask = H - 1;
-    t.shift = 34 - a.hbits;
+    t.hmul = a.hmul;
     t.limit = H < kProbeLimit ? H : kProbeLimit;
     t.xbase = xbase;
 
