@@ -62,7 +62,8 @@ struct ScoreContext {
     rt::DevBuf<unsigned long long> d_counters;  // 8
     rt::DevBuf<uint32_t> d_cursors;             // 16
     rt::DevBuf<sk::RowDesc> d_rows, d_ovf;
-    rt::DevBuf<uint32_t> d_dense, d_xtab;
+    rt::DevBuf<uint32_t> d_dense, d_xtab, d_sorttmp;
+    rt::DevBuf<uint64_t> d_rowkeys;
     uint32_t xtab_ctas = 0;
     rt::PinBuf<unsigned long long> h_counters;
     rt::PinBuf<sk::RowDesc> h_rows;
@@ -234,6 +235,8 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     fwd_ptr.alloc((size_t)S + 1);
     cls.alloc(std::max<size_t>(S, 1));
     d_visited.alloc(std::max<size_t>(S, 1));
+    fam_key.alloc(std::max<size_t>(S, 1));
+    rt::fill_byte(fam_key.p, 0x7F, sizeof(uint32_t) * S, st);
     rt::zero(fwd_ptr.p, sizeof(uint32_t) * ((size_t)S + 1), st);
     rt::zero(cls.p, sizeof(unsigned long long) * S, st);
     rt::zero(d_visited.p, sizeof(unsigned long long) * S, st);
@@ -317,7 +320,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
             launches += 2;
         }
         PD_LAUNCH(ik::gene_visited_kernel, blocks_for((uint64_t)S * 32), 256, 0, st, (const uint2*)fwd.p, (const uint32_t*)fwd_ptr.p, S,
-                  d_visited.p, d_lookups.p);
+                  sk::kShortList, d_visited.p, fam_key.p, d_lookups.p);
         launches += 1;
         uint32_t h_spur = 0;
         rt::d2h(&h_spur, d_spur.p, sizeof(uint32_t), st);
@@ -540,10 +543,10 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
     }
     rt::zero(c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
     rt::zero(c.d_cursors.p, 16 * sizeof(uint32_t), c.st);
-    c.d_rows.ensure((size_t)3 * n);
+    c.d_rows.ensure(n);
     c.d_ovf.ensure((size_t)2 * n);
 
-    // ---- row descriptors, sorted into the first-try levels, on the device
+    // ---- row descriptors on the device: sorted by (first-try level, family key)
     sk::ClassifyArgs ca;
     memset(&ca, 0, sizeof(ca));
     ca.n = n;
@@ -551,16 +554,21 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
     ca.gene_base = gene_base;
     ca.S = ix.info.S;
     ca.visited = ix.d_visited.p;
+    ca.fam_key = ix.fam_key.p;
     ca.fwd_ptr = ix.fwd_ptr.p;
     ca.cls = ix.cls.p;
     ca.cls_bits = ik::kClsBits;
     ca.meta = ix.meta.p;
     for (int l = 0; l < 3; l++) ca.max_cols[l] = lv[l].max_cols;
-    ca.rows = c.d_rows.p;
     ca.counts = c.d_cursors.p + 8;  // [8..10]
     ca.stats = c.d_counters.p + 4;  // [4], [5]
-    PD_LAUNCH(sk::classify_rows_kernel, blocks_for(n), 256, 0, c.st, ca);
-    c.stats.launches++;
+    c.d_rowkeys.ensure((size_t)2 * n);
+    c.d_sorttmp.ensure(prims::radix_tmp_words(n) + 16);
+    PD_LAUNCH(sk::row_keys_kernel, blocks_for(n), 256, 0, c.st, ca, c.d_rowkeys.p);
+    uint64_t nl = 0;
+    const uint64_t* sorted_keys = prims::radix_sort_u64(c.d_rowkeys.p, c.d_rowkeys.p + n, n, 31, 64, c.d_sorttmp.p, c.st, &nl);
+    PD_LAUNCH(sk::row_desc_kernel, blocks_for(n), 256, 0, c.st, ca, sorted_keys, c.d_rows.p);
+    c.stats.launches += 2 + nl;
 
     sk::ScoreArgs a;
     memset(&a, 0, sizeof(a));
@@ -578,9 +586,10 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
     rt::event_record(c.ev_k0, c.st);
     for (int level = 0; level < kLevels - 1; level++) {
         sk::ScoreArgs b = a;
-        b.rows = c.d_rows.p + (size_t)level * n;
+        b.rows = c.d_rows.p;
         b.n_rows = n;  // upper bound: sizes the grid
-        b.n_rows_dev = c.d_cursors.p + 8 + level;
+        b.n_rows_dev = c.d_cursors.p + 8;
+        b.level = (uint32_t)level;
         b.overflow_rows = c.d_ovf.p;
         b.n_overflow = c.d_counters.p + 2;
         launch_rows(c, b, lv[level], level);
@@ -712,7 +721,7 @@ void Index::score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_
         memset(&c.stats, 0, sizeof(c.stats));
         const uint32_t G = info.G;
         const uint32_t total_rows = row_end - row_begin;
-        if (rows_per_launch == 0) rows_per_launch = 16384;
+        if (rows_per_launch == 0) rows_per_launch = 65536;
         uint32_t* bh = reinterpret_cast<uint32_t*>(d_best_hit);
         if (!bh) {
             c.d_bh.ensure(std::max<size_t>((size_t)total_rows * G, 1));

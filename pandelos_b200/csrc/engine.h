@@ -29,6 +29,7 @@ struct Index {
     rt::DevBuf<uint32_t> fwd_ptr;              // S+1
     rt::DevBuf<unsigned long long> cls;        // S: forward entries per list class (3 x 21 bits)
     rt::DevBuf<unsigned long long> d_visited;  // S: total_visited
+    rt::DevBuf<uint32_t> fam_key;              // S: row scheduling key (see gene_visited_kernel)
     rt::DevBuf<uint2> meta;                    // S: (kseq_len, genome)
     rt::DevBuf<uint32_t> ent_gid;    // kept only with opt.keep_sorted
     rt::DevBuf<uint32_t> grp_head;   // kept only with opt.keep_sorted

@@ -343,9 +343,14 @@ __global__ void __launch_bounds__(256) fwd_place_kernel(const uint4* __restrict_
 }
 
 // visited[s] = sum of the posting-list lengths of gene s's forward entries (computation_costs[].total_visited,
-// library.cpp:327); *total += the sum over all genes ("Total cost: N lookups", library.cpp:349).  One warp per gene.
+// library.cpp:327); *total += the sum over all genes ("Total cost: N lookups", library.cpp:349).
+// fam_key[s] = the smallest posting-list start among the gene's long lists (all lists if it has no long one): genes
+// of one family share their conserved k-mers, hence mostly this key; scoring calls process their rows in fam_key
+// order so that rows running at the same time read the same posting lists (L2 hits instead of HBM reads).
+// One warp per gene.
 __global__ void __launch_bounds__(256) gene_visited_kernel(const uint2* __restrict__ fwd, const uint32_t* __restrict__ fwd_ptr, uint32_t S,
-                                                            unsigned long long* __restrict__ visited, unsigned long long* __restrict__ total) {
+                                                            uint32_t short_max, unsigned long long* __restrict__ visited,
+                                                            uint32_t* __restrict__ fam_key, unsigned long long* __restrict__ total) {
     __shared__ unsigned long long s_sum;
     if (threadIdx.x == 0) s_sum = 0;
     __syncthreads();
@@ -354,11 +359,24 @@ __global__ void __launch_bounds__(256) gene_visited_kernel(const uint2* __restri
     if (s < S) {
         const uint32_t f0 = fwd_ptr[s], f1 = fwd_ptr[s + 1];
         unsigned long long v = 0;
-        for (uint32_t f = f0 + lane; f < f1; f += 32) v += fwd[f].y & 0x7FFFFFFFu;
+        uint32_t kl = 0x7FFFFFFFu, ka = 0x7FFFFFFFu;
+        for (uint32_t f = f0 + lane; f < f1; f += 32) {
+            const uint2 fw = fwd[f];
+            const uint32_t gl = fw.y & 0x7FFFFFFFu;
+            v += gl;
+            ka = fw.x < ka ? fw.x : ka;
+            if (gl > short_max) kl = fw.x < kl ? fw.x : kl;
+        }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        for (int d = 16; d > 0; d >>= 1) {
+            v += __shfl_xor_sync(0xffffffffu, v, d);
+            const uint32_t ol = __shfl_xor_sync(0xffffffffu, kl, d), oa = __shfl_xor_sync(0xffffffffu, ka, d);
+            kl = ol < kl ? ol : kl;
+            ka = oa < ka ? oa : ka;
+        }
         if (lane == 0) {
             visited[s] = v;
+            fam_key[s] = kl != 0x7FFFFFFFu ? kl : ka;
             if (v) atomicAdd(&s_sum, v);
         }
     }

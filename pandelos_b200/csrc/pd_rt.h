@@ -159,8 +159,53 @@ inline void dfree(void* p) {
     }
     cudaFree(p);
 }
-inline void* hmalloc(size_t n) { void* p = nullptr; PD_CUDA(cudaMallocHost(&p, n ? n : 1)); return p; }
-inline void hfree(void* p) { if (p) cudaFreeHost(p); }
+// pinned host blocks are cached the same way (cudaMallocHost of the per-call result buffers costs milliseconds)
+struct HostCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks;
+    std::unordered_map<void*, size_t> live;
+    size_t cached = 0;
+};
+inline HostCache& host_cache() {
+    static HostCache c;
+    return c;
+}
+inline void* hmalloc(size_t n) {
+    n = round_block(n);
+    HostCache& c = host_cache();
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.free_blocks.lower_bound(n);
+        if (it != c.free_blocks.end() && it->first <= n + n / 4 + (size_t(1) << 20)) {
+            void* p = it->second;
+            c.cached -= it->first;
+            c.free_blocks.erase(it);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    PD_CUDA(cudaMallocHost(&p, n));
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.live[p] = n;
+    return p;
+}
+inline void hfree(void* p) {
+    if (!p) return;
+    HostCache& c = host_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.live.find(p);
+    if (it == c.live.end()) {
+        cudaFreeHost(p);
+        return;
+    }
+    if (c.cached + it->second > (size_t(16) << 30)) {  // keep at most 16 GiB of pinned memory around
+        cudaFreeHost(p);
+        c.live.erase(it);
+        return;
+    }
+    c.free_blocks.emplace(it->second, p);
+    c.cached += it->second;
+}
 inline stream_t stream_create() { stream_t s; PD_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return s; }
 inline void stream_destroy(stream_t s) { cudaStreamDestroy(s); }
 inline void sync(stream_t s) { PD_CUDA(cudaStreamSynchronize(s)); }

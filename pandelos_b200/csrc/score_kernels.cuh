@@ -63,7 +63,8 @@ struct ScoreArgs {
     // work
     const RowDesc* rows;
     uint32_t n_rows;
-    const uint32_t* n_rows_dev;  // non-null: the row count lives on the device (lists built by classify_rows_kernel)
+    const uint32_t* n_rows_dev;  // non-null: rows per level live on the device (row_keys_kernel); this launch takes
+    uint32_t level;              // the rows of level `level`: [sum of the counts before it, + n_rows_dev[level])
     uint32_t* cursor;
     // parameters
     uint32_t G;
@@ -564,8 +565,12 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
         keys[i] = kEmpty;
         cnt[i] = 0;
     }
-    const uint4* rows4 = reinterpret_cast<const uint4*>(a.rows);
-    const uint32_t n_rows = a.n_rows_dev ? *a.n_rows_dev : a.n_rows;
+    uint32_t n_rows = a.n_rows, row0 = 0;
+    if (a.n_rows_dev) {
+        n_rows = a.n_rows_dev[a.level];
+        for (uint32_t l = 0; l < a.level; l++) row0 += a.n_rows_dev[l];
+    }
+    const uint4* rows4 = reinterpret_cast<const uint4*>(a.rows + row0);
     uint32_t idx_next = 0;  // thread 0: row claimed for the iteration after this one
     if (tid == 0) {
         const uint32_t ri = atomicAdd(a.cursor, 1u);
@@ -841,48 +846,40 @@ __global__ void __launch_bounds__(kDenseThreads) score_rows_dense_kernel(ScoreAr
 
 // ------------------------------------------------------------------------------------------------ row lists
 
-// Builds the row descriptors of one scoring call on the device and sorts them into the first-try table levels by
-// their bound on distinct columns, min(total_visited, S).  Row i is gene genes[i] (or gene_base + i) and writes
-// best hits to row i of the call's table.
+// The rows of one scoring call are sorted on the device by (table level, family key) and turned into descriptors.
+//   row_keys_kernel   key_i = level << 62 | fam_key << 31 | i ; level by the row's bound on distinct columns,
+//                     min(total_visited, S); counts rows per level and the call's posting / forward-entry totals
+//   (radix sort of the keys on bits [31, 64))
+//   row_desc_kernel   descriptor j from sorted key j: levels end up contiguous, rows of a family adjacent
+// Row i is gene genes[i] (or gene_base + i) and writes best hits to row i of the call's table.
 struct ClassifyArgs {
     uint32_t n;
     const uint32_t* genes;
     uint32_t gene_base;
     uint32_t S;
     const unsigned long long* visited;
+    const uint32_t* fam_key;
     const uint32_t* fwd_ptr;
     const unsigned long long* cls;   // forward entries per list class, 3 x cls_bits
     uint32_t cls_bits;
     const uint2* meta;
     unsigned long long max_cols[3];
-    RowDesc* rows;                   // three lists of capacity n: rows + level * n
-    uint32_t* counts;                // [3]
+    uint32_t* counts;                // [3] rows per level
     unsigned long long* stats;       // [0] += postings the rows visit, [1] += their forward entries
 };
 
-__global__ void __launch_bounds__(256) classify_rows_kernel(ClassifyArgs a) {
+__global__ void __launch_bounds__(256) row_keys_kernel(ClassifyArgs a, uint64_t* __restrict__ keys) {
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
     unsigned long long lk = 0, fe = 0;
     if (i < a.n) {
         const uint32_t g = a.genes ? a.genes[i] : a.gene_base + i;
         const unsigned long long v = a.visited[g];
         const unsigned long long cols = v < a.S ? v : a.S;
-        const int level = cols <= a.max_cols[0] ? 0 : (cols <= a.max_cols[1] ? 1 : 2);
-        const unsigned long long cl = a.cls[g];
-        const unsigned long long m = (1ull << a.cls_bits) - 1ull;
-        const uint2 mg = a.meta[g];
-        RowDesc d;
-        d.gene = g;
-        d.bh_row = i;
-        d.fb = a.fwd_ptr[g];
-        d.fe = a.fwd_ptr[g + 1];
-        d.fm = d.fb + (uint32_t)(cl & m);
-        d.fh = d.fe - (uint32_t)((cl >> (2 * a.cls_bits)) & m);
-        d.kr = mg.x;
-        d.gr = mg.y;
-        a.rows[(size_t)level * a.n + atomicAdd(&a.counts[level], 1u)] = d;
+        const unsigned long long level = cols <= a.max_cols[0] ? 0 : (cols <= a.max_cols[1] ? 1 : 2);
+        keys[i] = (level << 62) | ((unsigned long long)(a.fam_key[g] & 0x7FFFFFFFu) << 31) | i;
+        atomicAdd(&a.counts[level], 1u);
         lk = v;
-        fe = d.fe - d.fb;
+        fe = a.fwd_ptr[g + 1] - a.fwd_ptr[g];
     }
 #pragma unroll
     for (int dd = 16; dd > 0; dd >>= 1) {
@@ -893,6 +890,26 @@ __global__ void __launch_bounds__(256) classify_rows_kernel(ClassifyArgs a) {
         atomicAdd(&a.stats[0], lk);
         atomicAdd(&a.stats[1], fe);
     }
+}
+
+__global__ void __launch_bounds__(256) row_desc_kernel(ClassifyArgs a, const uint64_t* __restrict__ keys, RowDesc* __restrict__ rows) {
+    const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+    if (j >= a.n) return;
+    const uint32_t i = (uint32_t)(keys[j] & 0x7FFFFFFFull);
+    const uint32_t g = a.genes ? a.genes[i] : a.gene_base + i;
+    const unsigned long long cl = a.cls[g];
+    const unsigned long long m = (1ull << a.cls_bits) - 1ull;
+    const uint2 mg = a.meta[g];
+    RowDesc d;
+    d.gene = g;
+    d.bh_row = i;
+    d.fb = a.fwd_ptr[g];
+    d.fe = a.fwd_ptr[g + 1];
+    d.fm = d.fb + (uint32_t)(cl & m);
+    d.fh = d.fe - (uint32_t)((cl >> (2 * a.cls_bits)) & m);
+    d.kr = mg.x;
+    d.gr = mg.y;
+    rows[j] = d;
 }
 
 }  // namespace sk
