@@ -443,7 +443,8 @@ __global__ void __launch_bounds__(256) xtab_init_kernel(uint32_t* xtab, uint32_t
 // bound on distinct columns, min(total_visited, S); rows that overflow their table are re-run on the last level and
 // then, if need be, on the dense global path.
 struct Level {
-    uint32_t hbits;     // log2 hash slots
+    uint32_t t1;        // tier-1 (direct-mapped) slots, a multiple of 32
+    uint32_t hbits;     // log2 tier-2 (probing) slots
     int threads;        // CTA size: 128, 256 or 512
     uint32_t fcap;      // forward entries staged per segment
     uint64_t max_cols;  // first-try rows: bound on distinct columns
@@ -458,19 +459,19 @@ inline uint32_t log2_floor(uint64_t v) {
     return b;
 }
 
-// Defaults: tables of 1 Ki / 4 Ki / 8 Ki slots tried by row size, 16 Ki slots for the retry.  pd_options.hash_log2
-// replaces the first-try ladder by one table of that size; PD_SMEM_TOP (tests) caps the bytes of the retry table.
+// Defaults: three first-try table sizes by row size and a large retry table.  pd_options.hash_log2 replaces the
+// first-try ladder by one small table of that many tier-2 slots; PD_SMEM_TOP (tests) caps the bytes of the retry table.
 inline void levels_of(const Index& ix, Level lv[kLevels]) {
-    lv[0] = {10, 128, 256, 256};
-    lv[1] = {12, 256, 512, 1536};
-    lv[2] = {13, 512, 1024, ~0ull};
-    lv[3] = {14, 512, 1024, 0};
-    if (const char* e = getenv("PD_LEVELS")) {  // tuning: "hbits:threads:fcap:maxcols,..." for the four levels
-        unsigned h, t, f;
+    lv[0] = {512, 9, 128, 256, 256};
+    lv[1] = {2048, 11, 256, 512, 1536};
+    lv[2] = {4096, 12, 512, 1024, ~0ull};
+    lv[3] = {2048, 14, 512, 1024, 0};
+    if (const char* e = getenv("PD_LEVELS")) {  // tuning: "t1:hbits:threads:fcap:maxcols,..." for the four levels
+        unsigned t1, h, t, f;
         unsigned long long m;
         int i = 0;
-        while (i < kLevels && sscanf(e, "%u:%u:%u:%llu", &h, &t, &f, &m) == 4) {
-            lv[i++] = {h, (int)t, f, m};
+        while (i < kLevels && sscanf(e, "%u:%u:%u:%u:%llu", &t1, &h, &t, &f, &m) == 5) {
+            lv[i++] = {t1, h, (int)t, f, m};
             e = strchr(e, ',');
             if (!e) break;
             e++;
@@ -479,24 +480,22 @@ inline void levels_of(const Index& ix, Level lv[kLevels]) {
     }
     if (ix.opt.hash_log2 > 0) {
         const uint32_t hb = std::min<uint32_t>(std::max<uint32_t>((uint32_t)ix.opt.hash_log2, 5), 14);
-        lv[0] = {hb, 128, 256, 0};   // unused
-        lv[1] = {hb, 128, 256, 0};   // unused
-        lv[2] = {hb, hb >= 12 ? 256 : 128, 256, ~0ull};
-        lv[3] = {std::max<uint32_t>(hb, 14), 512, 1024, 0};
+        const uint32_t t1 = std::min<uint32_t>(1u << hb, 4096);
+        lv[0] = {t1, hb, 128, 256, 0};   // unused
+        lv[1] = {t1, hb, 128, 256, 0};   // unused
+        lv[2] = {t1, hb, hb >= 12 ? 256 : 128, 256, ~0ull};
+        lv[3] = {2048, std::max<uint32_t>(hb, 14), 512, 1024, 0};
     }
     if (const char* e = getenv("PD_SMEM_TOP")) {  // tests: shrink the retry table to force the dense path
         const size_t v = (size_t)atoll(e);
         if (v >= 64) {
-            const uint32_t hb = std::max<uint32_t>(5, log2_floor(v / 8));
-            lv[3].hbits = std::min(lv[3].hbits, hb);
-            lv[3].threads = 128;
-            lv[3].fcap = 256;
+            const uint32_t hb = std::max<uint32_t>(5, log2_floor(v / 8) - 1);
+            if (hb < lv[3].hbits) lv[3] = {32, hb, 128, 256, 0};
         }
     }
     for (int i = 0; i < kLevels; i++) {
-        // the finalize pass gives every warp a 32-aligned slice of the table
-        while (lv[i].threads > 128 && (1u << lv[i].hbits) < 32u * (lv[i].threads / 32)) lv[i].threads /= 2;
-        while (sk::score_smem_bytes(lv[i].hbits, lv[i].fcap, lv[i].threads) > ix.smem_optin && lv[i].hbits > 5) lv[i].hbits--;
+        lv[i].t1 = std::max<uint32_t>(32, lv[i].t1 / 32 * 32);
+        while (sk::score_smem_bytes(lv[i].t1, lv[i].hbits, lv[i].fcap, lv[i].threads) > ix.smem_optin && lv[i].hbits > 5) lv[i].hbits--;
     }
 }
 
@@ -512,14 +511,18 @@ void launch_rows_t(ScoreContext& c, sk::ScoreArgs& a, size_t smem) {
 void launch_rows(ScoreContext& c, sk::ScoreArgs a, const Level& lv, int cursor_id) {
     if (a.n_rows == 0) return;
     a.hbits = lv.hbits;
-    {   // umulhi(c, hmul) < buckets for every c < S
-        const uint64_t buckets = (1ull << lv.hbits) / 4;
+    a.hmask = (1u << lv.hbits) - 1;
+    a.plimit = std::min<uint32_t>(1u << lv.hbits, sk::kProbeLimit);
+    a.nslots = lv.t1 + (1u << lv.hbits);
+    a.t1 = lv.t1;
+    {   // order-preserving slot functions: umulhi(c, mul) = floor(c * slots / S) < slots for every c < S
         const uint64_t S = std::max<uint64_t>(c.ix->info.S, 1);
-        a.hmul = (uint32_t)std::min<uint64_t>((buckets << 32) / S, 0xFFFFFFFFull);
+        a.hmul = (uint32_t)std::min<uint64_t>(((1ull << lv.hbits) << 32) / S, 0xFFFFFFFFull);
+        a.t1mul = (uint32_t)std::min<uint64_t>(((uint64_t)lv.t1 << 32) / S, 0xFFFFFFFFull);
     }
     a.fcap = lv.fcap;
     a.cursor = c.d_cursors.p + cursor_id;
-    const size_t smem = sk::score_smem_bytes(lv.hbits, lv.fcap, lv.threads);
+    const size_t smem = sk::score_smem_bytes(lv.t1, lv.hbits, lv.fcap, lv.threads);
     if (lv.threads >= 512) launch_rows_t<512>(c, a, smem);
     else if (lv.threads >= 256) launch_rows_t<256>(c, a, smem);
     else launch_rows_t<128>(c, a, smem);

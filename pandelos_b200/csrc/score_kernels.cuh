@@ -46,7 +46,7 @@ static const uint32_t kProbeLimit = 160;        // probes after which a row is d
 static const uint32_t kNone = 0x7FFFFFFFu;      // "no posting" in a lane's item (gene ids are < 2^31 - 1)
 static const int kItems = 8;                    // postings per lane per round of a long list
 static const int kItemsA = 4;                   // ... of the flattened short lists
-static const uint32_t kQueue = 64;              // per-warp queue of postings that missed their home bucket
+static const uint32_t kQueue = 128;             // per-warp ring of postings that missed tier 1
 static const int kDenseThreads = 256;
 
 struct __align__(16) RowDesc {  // 32 B, built on the host per call
@@ -69,12 +69,13 @@ struct ScoreArgs {
     // parameters
     uint32_t G;
     uint32_t k2;      // 2k: perc >= thr  <=>  2k * pc >= K  (exact for K < 2^20, see gate())
-    uint32_t hbits;   // log2 of the hash table slots
-    // Home bucket of column c = floor(c * buckets / S) = umulhi(c, hmul): ORDER PRESERVING on purpose.  Posting lists
-    // are sorted by gene and a row's homologs are spread over the genomes, so the lanes of a warp, which hold
-    // consecutive postings, hit ascending, well separated buckets: few shared-memory bank conflicts, where a mixing
-    // hash makes every access a random one.  Columns that crowd one bucket spill by linear probing as before.
-    uint32_t hmul;
+    uint32_t hbits;   // log2 of the tier-2 slots H
+    uint32_t hmul;    // tier-2 home slot of column c = floor(c * H / S) = umulhi(c, hmul)
+    uint32_t hmask;   // H - 1
+    uint32_t plimit;  // tier-2 probe limit
+    uint32_t nslots;  // T1 + H
+    uint32_t t1;      // tier-1 slots (a multiple of 32)
+    uint32_t t1mul;   // tier-1 slot of column c = floor(c * T1 / S) = umulhi(c, t1mul): ORDER PRESERVING on purpose, see Tab
     uint32_t fcap;    // forward entries staged per segment
     // outputs
     float* o_score;
@@ -159,162 +160,223 @@ __device__ __forceinline__ bool gate(uint32_t k2, uint32_t pc, uint32_t tc, uint
     return (k2 * pc >= kr) || (k2 * tc >= kc);
 }
 
-// The accumulator: H slots in buckets of 4 (one 16-B shared-memory load reads a column's whole home bucket); a key
-// lives in the first free slot found by linear probing from the base of its home bucket.
+// The accumulator has two tiers, both (key, count) arrays in shared memory:
+//   tier 1  T1 slots, DIRECT MAPPED by an order-preserving function of the column, slot = floor(c * T1 / S).  Posting
+//           lists are sorted by gene and a row's homologs sit in different genomes, i.e. far apart in gene order: the
+//           lanes of a warp, which hold consecutive postings, hit ascending, well separated slots (no bank conflicts),
+//           and a homolog column keeps its slot for the whole row.  One 4-byte shared load + one shared atomic.
+//   tier 2  H slots, linear probing.  Takes the columns whose tier-1 slot belongs to another column.  Postings that
+//           miss tier 1 go to a per-warp queue and are probed / inserted here 32 at a time, every lane busy.
+// A column lives in exactly one place: a tier-1 slot is claimed once (CAS on empty) and never changes owner during a
+// row, so a column that lost its slot goes to tier 2 every time.  Slots are numbered [0, T1) and [T1, T1 + H).
 struct RowCtl {  // per-row control words in shared memory
     uint32_t nx;      // side-table entries in use
     int over;         // the row does not fit: stop, hand it to the next level
     uint32_t ctr[2];  // work counters: batches of short lists, long lists
 };
 
+// Launch-uniform geometry (tier sizes, slot functions) is read from the kernel arguments (constant bank), not carried
+// in registers; Tab holds only what is per CTA / per row.
 struct Tab {
-    uint32_t* keys;   // cnt = keys + mask + 1
-    saddr_t keys_sa;  // the same two arrays by shared-window address
-    saddr_t cnt_sa;
-    uint32_t mask;
-    uint32_t hmul;   // column -> home bucket: umulhi(c, hmul), see ScoreArgs::hmul
-    uint32_t limit;  // probe limit
-    uint32_t* xbase;  // side table: keys, d_inter, d_pc, d_tc, touched list (kXSlots each)
+    uint32_t* keys;   // nslots keys, then nslots counts (generic address, finalize)
+    saddr_t keys_sa;  // the same by shared-window address (hot loop)
     RowCtl* ctl;
-    __device__ __forceinline__ uint32_t* cnt() const { return keys + mask + 1; }
-    __device__ __forceinline__ uint32_t* xkeys() const { return xbase; }
-    __device__ __forceinline__ uint32_t* xv(int i) const { return xbase + (1 + i) * kXSlots; }
-    __device__ __forceinline__ uint32_t* xtouched() const { return xbase + 4 * kXSlots; }
     __device__ __forceinline__ volatile int* over() const { return &ctl->over; }
 };
+__device__ __forceinline__ saddr_t cnt_sa(const ScoreArgs& a, const Tab& t) { return t.keys_sa + a.nslots * 4u; }
+__device__ __forceinline__ uint32_t* cnt_of(const ScoreArgs& a, const Tab& t) { return t.keys + a.nslots; }
 
-// first slot of the column's home bucket
+// side table of this CTA: keys, d_inter, d_pc, d_tc, touched list (kXSlots each)
+struct XTab {
+    uint32_t* base;
+    RowCtl* ctl;
+    __device__ __forceinline__ uint32_t* keys() const { return base; }
+    __device__ __forceinline__ uint32_t* v(int i) const { return base + (1 + i) * kXSlots; }
+    __device__ __forceinline__ uint32_t* touched() const { return base + 4 * kXSlots; }
+};
+__device__ __forceinline__ XTab xtab_of(const ScoreArgs& a, const Tab& t) {
+    XTab x;
+    x.base = a.xtab + (size_t)blockIdx.x * (5 * kXSlots);
+    x.ctl = t.ctl;
+    return x;
+}
+
 // (clamped: kNone items, which are never counted, still compute an address)
-__device__ __forceinline__ uint32_t home_slot(const Tab& t, uint32_t c) { return min(__umulhi(c, t.hmul) << 2, t.mask & ~3u); }
+__device__ __forceinline__ uint32_t t1_slot(const ScoreArgs& a, uint32_t c) { return min(__umulhi(c, a.t1mul), a.t1 - 1); }
+__device__ __forceinline__ uint32_t t2_home(const ScoreArgs& a, uint32_t c) { return min(__umulhi(c, a.hmul), a.hmask); }
 
-__device__ __forceinline__ uint32_t x_find_or_insert(const Tab& t, uint32_t c) {
+__device__ __forceinline__ uint32_t x_find_or_insert(const XTab& x, uint32_t c) {
     uint32_t h = __umulhi(c * 0x85EBCA6Bu, kXSlots);
     for (uint32_t probe = 0; probe < kXSlots; probe++) {
-        const uint32_t k = *(volatile uint32_t*)(t.xkeys() + h);
+        const uint32_t k = *(volatile uint32_t*)(x.keys() + h);
         if (k == c) return h;
         if (k == kEmpty) {
-            const uint32_t old = atomicCAS(t.xkeys() + h, kEmpty, c);
+            const uint32_t old = atomicCAS(x.keys() + h, kEmpty, c);
             if (old == kEmpty) {
-                const uint32_t xi = atomicAdd(&t.ctl->nx, 1u);
-                if (xi < kXCap) t.xtouched()[xi] = h;
-                else *t.over() = 1;
+                const uint32_t xi = atomicAdd(&x.ctl->nx, 1u);
+                if (xi < kXCap) x.touched()[xi] = h;
+                else x.ctl->over = 1;
                 return h;
             }
             if (old == c) return h;
         }
         h = (h + 1 == kXSlots) ? 0 : h + 1;
     }
-    *t.over() = 1;
+    x.ctl->over = 1;
     return kEmpty;
 }
 
-// The general case of one posting: column c held n times by its gene, m times by the row (n | m > 1: rare).
-__device__ __noinline__ void add_general(const Tab& t, uint32_t c, uint32_t n, uint32_t m) {
-    uint32_t h = home_slot(t, c);
-    uint32_t probes = 0;
+// tier 2: finds column c or claims the first free slot of its probe path; returns the slot (T1-based), kEmpty if the
+// row does not fit
+__device__ __forceinline__ uint32_t t2_find_or_insert(const ScoreArgs& a, const Tab& t, uint32_t c) {
+    uint32_t hh = t2_home(a, c), probes = 0;
     for (;;) {
-        uint32_t k = *(volatile uint32_t*)(t.keys + h);
+        const saddr_t addr = t.keys_sa + (a.t1 + hh) * 4u;
+        uint32_t kk = lds_u32(addr);
+        if (kk == kEmpty) {
+            const uint32_t old = atoms_cas(addr, kEmpty, c);
+            kk = (old == kEmpty) ? c : old;
+        }
+        if (kk == c) return a.t1 + hh;
+        hh = (hh + 1) & a.hmask;
+        if (++probes > a.plimit) {
+            *t.over() = 1;
+            return kEmpty;
+        }
+    }
+}
+
+// The general case of one posting: column c held n times by its gene, m times by the row (n | m > 1: rare).
+// Never inlined, and handed everything it needs BY VALUE: a reference to the kernel arguments or to the hot loop's
+// state would force them into local memory.
+struct GenArgs {
+    uint32_t* keys;
+    saddr_t keys_sa;
+    RowCtl* ctl;
+    uint32_t* xbase;
+    uint32_t t1, t1mul, hmask, hmul, plimit, nslots;
+};
+__device__ __noinline__ void add_general(const GenArgs g, uint32_t c, uint32_t n, uint32_t m) {
+    // the slot of column c in either tier (claimed if new)
+    uint32_t h = min(__umulhi(c, g.t1mul), g.t1 - 1);
+    {
+        const saddr_t a1 = g.keys_sa + h * 4u;
+        uint32_t k = lds_u32(a1);
         if (k == kEmpty) {
-            const uint32_t old = atomicCAS(t.keys + h, kEmpty, c);
+            const uint32_t old = atoms_cas(a1, kEmpty, c);
             k = (old == kEmpty) ? c : old;
         }
-        if (k == c) break;
-        h = (h + 1) & t.mask;
-        if (++probes > t.limit) {
-            *t.over() = 1;
-            return;
+        if (k != c) {
+            uint32_t hh = min(__umulhi(c, g.hmul), g.hmask), probes = 0;
+            for (;;) {
+                const saddr_t addr = g.keys_sa + (g.t1 + hh) * 4u;
+                uint32_t kk = lds_u32(addr);
+                if (kk == kEmpty) {
+                    const uint32_t old = atoms_cas(addr, kEmpty, c);
+                    kk = (old == kEmpty) ? c : old;
+                }
+                if (kk == c) break;
+                hh = (hh + 1) & g.hmask;
+                if (++probes > g.plimit) {
+                    g.ctl->over = 1;
+                    return;
+                }
+            }
+            h = g.t1 + hh;
         }
     }
-    atomicAdd(&t.cnt()[h], 1u);
+    uint32_t* cnt = g.keys + g.nslots;
+    atomicAdd(&cnt[h], 1u);
     if ((n | m) > 1u) {  // corrections for the repeated k-mer go to the side table
-        atomicOr(&t.cnt()[h], kFlag);
-        const uint32_t xs = x_find_or_insert(t, c);
+        atomicOr(&cnt[h], kFlag);
+        XTab x;
+        x.base = g.xbase;
+        x.ctl = g.ctl;
+        const uint32_t xs = x_find_or_insert(x, c);
         if (xs != kEmpty) {
             const uint32_t mn = n < m ? n : m;
-            if (mn > 1) atomicAdd(&t.xv(0)[xs], mn - 1);
-            if (m > 1) atomicAdd(&t.xv(1)[xs], m - 1);
-            if (n > 1) atomicAdd(&t.xv(2)[xs], n - 1);
+            if (mn > 1) atomicAdd(&x.v(0)[xs], mn - 1);
+            if (m > 1) atomicAdd(&x.v(1)[xs], m - 1);
+            if (n > 1) atomicAdd(&x.v(2)[xs], n - 1);
         }
     }
 }
+__device__ __forceinline__ GenArgs gen_args(const ScoreArgs& a, const Tab& t) {
+    GenArgs g;
+    g.keys = t.keys;
+    g.keys_sa = t.keys_sa;
+    g.ctl = t.ctl;
+    g.xbase = a.xtab + (size_t)blockIdx.x * (5 * kXSlots);
+    g.t1 = a.t1;
+    g.t1mul = a.t1mul;
+    g.hmask = a.hmask;
+    g.hmul = a.hmul;
+    g.plimit = a.plimit;
+    g.nslots = a.nslots;
+    return g;
+}
 
-// ---- accumulate, the common case: postings with n = m = 1
+// ---- accumulate, the common case: postings with n = m = 1.  One "item" is one posting per lane (kNone: none).
 //
-// One "item" is one posting per lane (c == kNone: no posting).  The branch-free step: the column already sits in its
-// home bucket -> one 16-B shared-memory load, four compares, one atomic.  What is left (first visit of a column in
-// this row, or a key pushed out of its bucket) is pushed to a small per-warp queue and probed / inserted later, 32
-// at a time with every lane busy, instead of on the spot by the few lanes concerned.
+// Per-warp queue of the postings that missed tier 1: a ring of kQueue words; the tail lives in shared memory (lanes
+// push on their own, one shared atomic each), the head in a register (drains are warp-wide).
 struct WarpQueue {
-    uint32_t* q;  // kQueue entries of shared memory
-    uint32_t head, tail;
+    uint32_t* q;
+    uint32_t* tail;
+    uint32_t head;
 };
 
-// probe / insert from the home bucket on, then count
-__device__ __forceinline__ void probe_add(const Tab& t, uint32_t cur) {
-    if (cur == kNone) return;
-    uint32_t hh = home_slot(t, cur), probes = 0;
-    for (;;) {
-        uint32_t kk = lds_u32(t.keys_sa + hh * 4u);
-        if (kk == kEmpty) {
-            const uint32_t old = atoms_cas(t.keys_sa + hh * 4u, kEmpty, cur);
-            kk = (old == kEmpty) ? cur : old;
-        }
-        if (kk == cur) {
-            reds_inc(t.cnt_sa + hh * 4u);
-            return;
-        }
-        hh = (hh + 1) & t.mask;
-        if (++probes > t.limit) {
-            *t.over() = 1;
-            return;
-        }
-    }
-}
-
-__device__ __forceinline__ void queue_drain32(const Tab& t, WarpQueue& wq) {
+__device__ __forceinline__ void queue_drain32(const ScoreArgs& a, const Tab& t, WarpQueue& wq, uint32_t n) {  // n queued (uniform)
     const unsigned lane = threadIdx.x & 31;
-    __syncwarp();
-    const uint32_t n = wq.tail - wq.head;
     const uint32_t cur = lane < n ? wq.q[(wq.head + lane) & (kQueue - 1)] : kNone;
     wq.head += n < 32u ? n : 32u;
-    probe_add(t, cur);
+    if (cur != kNone) {
+        const uint32_t h = t2_find_or_insert(a, t, cur);
+        if (h != kEmpty) reds_inc(cnt_sa(a, t) + h * 4u);
+    }
     __syncwarp();
 }
-__device__ __forceinline__ void queue_flush(const Tab& t, WarpQueue& wq) {
-    while (wq.tail != wq.head) queue_drain32(t, wq);
-}
-
-// home-bucket slot of c given the bucket's four keys: byte offset 0/4/8/12, or 16 = not there
-__device__ __forceinline__ uint32_t bucket_find(const uint4& kb, uint32_t c) {
-    uint32_t off = 16u;
-    off = (kb.w == c) ? 12u : off;
-    off = (kb.z == c) ? 8u : off;
-    off = (kb.y == c) ? 4u : off;
-    off = (kb.x == c) ? 0u : off;
-    return off;
-}
-
-__device__ __forceinline__ void queue_push(const Tab& t, WarpQueue& wq, bool missed, uint32_t c) {
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned mb = __ballot_sync(0xffffffffu, missed);
-    if (mb) {
-        if (missed) wq.q[(wq.tail + __popc(mb & ((1u << lane) - 1u))) & (kQueue - 1)] = c;
-        wq.tail += __popc(mb);
-        if (wq.tail - wq.head >= 32u) queue_drain32(t, wq);
+__device__ __forceinline__ void queue_flush(const ScoreArgs& a, const Tab& t, WarpQueue& wq) {
+    __syncwarp();
+    for (;;) {
+        const uint32_t n = *(volatile uint32_t*)wq.tail - wq.head;
+        if (n == 0) break;
+        queue_drain32(a, t, wq, n);
     }
 }
 
-// two items at a time: both bucket loads are in flight before either is compared
-__device__ __forceinline__ void items_add2(const Tab& t, WarpQueue& wq, uint32_t c0, uint32_t c1) {
-    const uint32_t h0 = home_slot(t, c0) * 4u, h1 = home_slot(t, c1) * 4u;
-    const uint4 k0 = lds_v4(t.keys_sa + h0);
-    const uint4 k1 = lds_v4(t.keys_sa + h1);
-    const uint32_t o0 = bucket_find(k0, c0), o1 = bucket_find(k1, c1);
-    const bool hit0 = o0 != 16u, hit1 = o1 != 16u;  // kNone is never a key: no hit
-    if (hit0) reds_inc(t.cnt_sa + h0 + o0);
-    if (hit1) reds_inc(t.cnt_sa + h1 + o1);
-    queue_push(t, wq, !hit0 && c0 != kNone, c0);
-    queue_push(t, wq, !hit1 && c1 != kNone, c1);
+// a posting that did not find its column in tier 1: claim the slot if it is free, else queue for tier 2
+__device__ __forceinline__ void item_miss(const ScoreArgs& a, const Tab& t, WarpQueue& wq, uint32_t c, uint32_t s1, uint32_t k1) {
+    if (k1 == kEmpty) {
+        const uint32_t old = atoms_cas(t.keys_sa + s1 * 4u, kEmpty, c);
+        if (old == kEmpty || old == c) {
+            reds_inc(cnt_sa(a, t) + s1 * 4u);
+            return;
+        }
+    }
+    wq.q[atomicAdd(wq.tail, 1u) & (kQueue - 1)] = c;
+}
+
+// two items at a time: both tier-1 loads are in flight before either is compared
+__device__ __forceinline__ void items_add2(const ScoreArgs& a, const Tab& t, WarpQueue& wq, uint32_t c0, uint32_t c1) {
+    const uint32_t s0 = t1_slot(a, c0), s1 = t1_slot(a, c1);
+    const uint32_t k0 = lds_u32(t.keys_sa + s0 * 4u);
+    const uint32_t k1 = lds_u32(t.keys_sa + s1 * 4u);
+    const bool hit0 = k0 == c0, hit1 = k1 == c1;  // kNone is never a key: no hit
+    if (hit0) reds_inc(cnt_sa(a, t) + s0 * 4u);
+    if (hit1) reds_inc(cnt_sa(a, t) + s1 * 4u);
+    const bool miss0 = !hit0 && c0 != kNone, miss1 = !hit1 && c1 != kNone;
+    if (__any_sync(0xffffffffu, miss0 | miss1)) {
+        if (miss0) item_miss(a, t, wq, c0, s0, k0);
+        if (miss1) item_miss(a, t, wq, c1, s1, k1);
+        __syncwarp();
+        // at most 31 entries stay queued between calls, a call adds at most 64: the ring (kQueue = 128) never laps
+        for (;;) {
+            const uint32_t n = *(volatile uint32_t*)wq.tail - wq.head;
+            if (n < 32u) break;
+            queue_drain32(a, t, wq, n);
+        }
+    }
 }
 
 // Per-warp scratch of the flattened walk over short lists
@@ -322,6 +384,8 @@ struct WarpScratch {
     uint32_t bits[kShortList + kItemsA];  // 32 lists x kShortList postings = 2048 marks (+ the words a round reads ahead)
     uint32_t pre[32];
     uint32_t queue[kQueue];
+    uint32_t qtail;
+    uint32_t pad[3];
 };
 
 // A list walk in rounds of kItems x 32 consecutive postings: lane l holds postings p0 + 32 u + l, u < kItems, in e[u].
@@ -341,22 +405,24 @@ __device__ __forceinline__ void round_step(const ScoreArgs& a, const Tab& t, War
             // bit 31: a repeated k-mer; the row's own repeat count is uniform over the list
             if (((c0 | c1) & kMulti) || mj > 1) {
                 if (c0 != kNone && ((c0 & kMulti) || mj > 1)) {
-                    add_general(t, c0 & ~kMulti, (c0 & kMulti) ? a.post_cnt[pos + 32u * u + lane] : 1u, mj);
+                    add_general(gen_args(a, t), c0 & ~kMulti, (c0 & kMulti) ? a.post_cnt[pos + 32u * u + lane] : 1u, mj);
                     c0 = kNone;
                 }
                 if (c1 != kNone && ((c1 & kMulti) || mj > 1)) {
-                    add_general(t, c1 & ~kMulti, (c1 & kMulti) ? a.post_cnt[pos + 32u * (u + 1) + lane] : 1u, mj);
+                    add_general(gen_args(a, t), c1 & ~kMulti, (c1 & kMulti) ? a.post_cnt[pos + 32u * (u + 1) + lane] : 1u, mj);
                     c1 = kNone;
                 }
             }
-            items_add2(t, wq, c0, c1);
+            items_add2(a, t, wq, c0, c1);
         }
     }
 }
 
 // Accumulates the staged forward entries fbuf[0, n_stage) = forward entries [f0, f0 + n_stage) of the row.
 // Classes by position: [0, ns) short, [ns, nl) long, [nl, n_stage) huge.  ctr[0..1] are shared work counters, zero
-// at entry.  No ordering is needed between the three parts: every update is an atomic on the table.
+// at entry.  No ordering is needed between the three parts (every update is an atomic on the table); the long lists
+// go first so that the row's frequent columns — its homologs — claim the tier-1 slots before the chance hits of the
+// short lists arrive.
 template <int THREADS>
 __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t, const uint2* fbuf, uint32_t f0, uint32_t ns, uint32_t nl,
                                            uint32_t n_stage, WarpScratch* ws_all, uint32_t* ctr) {
@@ -365,76 +431,11 @@ __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t, con
     WarpScratch& ws = ws_all[warp];
     WarpQueue wq;
     wq.q = ws.queue;
-    wq.head = wq.tail = 0;
+    wq.tail = &ws.qtail;
+    wq.head = 0;
+    if (lane == 0) ws.qtail = 0;
+    __syncwarp();
     const unsigned le = 0xffffffffu >> (31 - lane);  // lanes <= mine
-    // ---- short lists: batches of 32, flattened
-    for (;;) {
-        uint32_t bi = 0;
-        if (lane == 0) bi = *t.over() ? 0x03FFFFFFu : atomicAdd(ctr, 1u);  // one lane polls the stop flag: uniform exit
-        bi = __shfl_sync(0xffffffffu, bi, 0);
-        const uint32_t b0 = bi * 32;
-        if (b0 >= ns) break;
-        const uint32_t j = b0 + lane;
-        const bool has = j < ns;
-        const uint32_t len = has ? (fbuf[j].y & ~kMulti) : 0u;
-        uint32_t incl = len;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (unsigned)d) incl += o;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t pre = incl - len;
-        ws.bits[lane] = 0;
-        ws.bits[lane + 32] = 0;
-        if (lane < kItemsA) ws.bits[64 + lane] = 0;
-        ws.pre[lane] = pre;
-        __syncwarp();
-        if (has) atomicOr(&ws.bits[pre >> 5], 1u << (pre & 31));  // lists are >= 2 long: one mark per list
-        __syncwarp();
-        uint32_t seen = 0;  // marks before this round
-        for (uint32_t t0 = 0; t0 < total; t0 += 32 * kItemsA) {
-            uint32_t e[kItemsA], o[kItemsA];
-#pragma unroll
-            for (int u = 0; u < kItemsA; u++) {
-                const uint32_t w = ws.bits[(t0 >> 5) + u];
-                o[u] = (seen + __popc(w & le) - 1u) & 31u;
-                seen += __popc(w);
-            }
-            uint32_t special = 0;
-#pragma unroll
-            for (int u = 0; u < kItemsA; u++) {
-                const uint32_t tt = t0 + 32u * u + lane;
-                e[u] = kNone;
-                if (tt < total) {
-                    const uint2 fw = fbuf[b0 + o[u]];
-                    e[u] = a.post[fw.x + (tt - ws.pre[o[u]])];
-                    special |= fw.y | e[u];
-                }
-            }
-            if (special & kMulti) {
-#pragma unroll
-                for (int u = 0; u < kItemsA; u++) {
-                    const uint32_t tt = t0 + 32u * u + lane;
-                    if (tt < total) {
-                        const uint2 fw = fbuf[b0 + o[u]];
-                        if ((fw.y | e[u]) & kMulti) {
-                            const uint32_t n = (e[u] & kMulti) ? a.post_cnt[fw.x + (tt - ws.pre[o[u]])] : 1u;
-                            const uint32_t m = (fw.y & kMulti) ? a.fwd_cnt[f0 + b0 + o[u]] : 1u;
-                            add_general(t, e[u] & ~kMulti, n, m);
-                            e[u] = kNone;
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kItemsA; u += 2) {
-                if (t0 + 32u * u >= total) break;
-                items_add2(t, wq, e[u], e[u + 1]);
-            }
-        }
-        __syncwarp();
-    }
     // ---- long lists: one warp per list
     {
         uint32_t e[kItems];
@@ -492,18 +493,86 @@ __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t, con
             p0 = np0;
         }
     }
-    queue_flush(t, wq);
+    // ---- short lists: batches of 32, flattened
+    for (;;) {
+        uint32_t bi = 0;
+        if (lane == 0) bi = *t.over() ? 0x03FFFFFFu : atomicAdd(ctr, 1u);  // one lane polls the stop flag: uniform exit
+        bi = __shfl_sync(0xffffffffu, bi, 0);
+        const uint32_t b0 = bi * 32;
+        if (b0 >= ns) break;
+        const uint32_t j = b0 + lane;
+        const bool has = j < ns;
+        const uint32_t len = has ? (fbuf[j].y & ~kMulti) : 0u;
+        uint32_t incl = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (unsigned)d) incl += o;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t pre = incl - len;
+        ws.bits[lane] = 0;
+        ws.bits[lane + 32] = 0;
+        if (lane < kItemsA) ws.bits[64 + lane] = 0;
+        ws.pre[lane] = pre;
+        __syncwarp();
+        if (has) atomicOr(&ws.bits[pre >> 5], 1u << (pre & 31));  // lists are >= 2 long: one mark per list
+        __syncwarp();
+        uint32_t seen = 0;  // marks before this round
+        for (uint32_t t0 = 0; t0 < total; t0 += 32 * kItemsA) {
+            uint32_t e[kItemsA], o[kItemsA];
+#pragma unroll
+            for (int u = 0; u < kItemsA; u++) {
+                const uint32_t w = ws.bits[(t0 >> 5) + u];
+                o[u] = (seen + __popc(w & le) - 1u) & 31u;
+                seen += __popc(w);
+            }
+            uint32_t special = 0;
+#pragma unroll
+            for (int u = 0; u < kItemsA; u++) {
+                const uint32_t tt = t0 + 32u * u + lane;
+                e[u] = kNone;
+                if (tt < total) {
+                    const uint2 fw = fbuf[b0 + o[u]];
+                    e[u] = a.post[fw.x + (tt - ws.pre[o[u]])];
+                    special |= fw.y | e[u];
+                }
+            }
+            if (special & kMulti) {
+#pragma unroll
+                for (int u = 0; u < kItemsA; u++) {
+                    const uint32_t tt = t0 + 32u * u + lane;
+                    if (tt < total) {
+                        const uint2 fw = fbuf[b0 + o[u]];
+                        if ((fw.y | e[u]) & kMulti) {
+                            const uint32_t n = (e[u] & kMulti) ? a.post_cnt[fw.x + (tt - ws.pre[o[u]])] : 1u;
+                            const uint32_t m = (fw.y & kMulti) ? a.fwd_cnt[f0 + b0 + o[u]] : 1u;
+                            add_general(gen_args(a, t), e[u] & ~kMulti, n, m);
+                            e[u] = kNone;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kItemsA; u += 2) {
+                if (t0 + 32u * u >= total) break;
+                items_add2(a, t, wq, e[u], e[u + 1]);
+            }
+        }
+        __syncwarp();
+    }
+    queue_flush(a, t, wq);
 }
 
 // (inter, pc, tc) of a table slot
-__device__ __forceinline__ void slot_sums(const Tab& t, uint32_t c, uint32_t v, uint32_t* inter, uint32_t* pc, uint32_t* tc) {
+__device__ __forceinline__ void slot_sums(const XTab& x, uint32_t c, uint32_t v, uint32_t* inter, uint32_t* pc, uint32_t* tc) {
     uint32_t i = v & ~kFlag, p = i, q = i;
     if (v & kFlag) {
         uint32_t xs = __umulhi(c * 0x85EBCA6Bu, kXSlots);
-        while (*(volatile uint32_t*)(t.xkeys() + xs) != c) xs = (xs + 1 == kXSlots) ? 0 : xs + 1;
-        i += *(volatile uint32_t*)(t.xv(0) + xs);
-        p += *(volatile uint32_t*)(t.xv(1) + xs);
-        q += *(volatile uint32_t*)(t.xv(2) + xs);
+        while (*(volatile uint32_t*)(x.keys() + xs) != c) xs = (xs + 1 == kXSlots) ? 0 : xs + 1;
+        i += *(volatile uint32_t*)(x.v(0) + xs);
+        p += *(volatile uint32_t*)(x.v(1) + xs);
+        q += *(volatile uint32_t*)(x.v(2) + xs);
     }
     *inter = i;
     *pc = p;
@@ -536,12 +605,12 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(ScoreArgs a) {
     constexpr int WARPS = THREADS / 32;
     PD_DYNAMIC_SMEM(smem_raw);
-    const uint32_t H = 1u << a.hbits;
+    const uint32_t H = a.nslots;  // slots of both tiers
     uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);
     uint32_t* cnt = keys + H;
     uint2* fwdbuf = reinterpret_cast<uint2*>(cnt + H);                                  // 2 x fcap
     WarpScratch* ws = reinterpret_cast<WarpScratch*>(fwdbuf + 2 * (size_t)a.fcap);     // WARPS
-    uint16_t* cand = reinterpret_cast<uint16_t*>(ws + WARPS);                           // H
+    uint16_t* cand = reinterpret_cast<uint16_t*>(ws + WARPS);                           // one per slot, in warp slices
     __shared__ uint4 s_desc[2][2];  // two RowDesc buffers
     // per-row control words, double-buffered like s_desc: a row uses [buf]; thread 0 clears [buf ^ 1] while the row
     // runs (its last readers finished before the row's opening barrier)
@@ -555,11 +624,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
     Tab t;
     t.keys = keys;
     t.keys_sa = smem_addr(keys);
-    t.cnt_sa = smem_addr(cnt);
-    t.mask = H - 1;
-    t.hmul = a.hmul;
-    t.limit = H < kProbeLimit ? H : kProbeLimit;
-    t.xbase = xbase;
+    XTab xt;
+    xt.base = xbase;
 
     for (uint32_t i = tid; i < H; i += THREADS) {
         keys[i] = kEmpty;
@@ -673,10 +739,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
             }
             if (t.ctl->nx) {
                 for (uint32_t i = tid; i < kXSlots; i += THREADS) {
-                    t.xkeys()[i] = kEmpty;
-                    t.xv(0)[i] = 0;
-                    t.xv(1)[i] = 0;
-                    t.xv(2)[i] = 0;
+                    xt.keys()[i] = kEmpty;
+                    xt.v(0)[i] = 0;
+                    xt.v(1)[i] = 0;
+                    xt.v(2)[i] = 0;
                 }
                 __threadfence();
             }
@@ -706,7 +772,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
                         if (c != rc.r) {  // identity cell dropped (library.cpp:485-487)
                             pairs++;
                             uint32_t inter, pc, tc;
-                            slot_sums(t, c, cnt[s], &inter, &pc, &tc);
+                            slot_sums(xt, c, cnt[s], &inter, &pc, &tc);
                             valid = gate(a.k2, pc, tc, rc.kr, a.meta[c].x);
                         }
                         if (!valid) {
@@ -731,7 +797,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
                         keys[s] = kEmpty;
                         cnt[s] = 0;
                         uint32_t inter, pc, tc;
-                        slot_sums(t, c, v, &inter, &pc, &tc);
+                        slot_sums(xt, c, v, &inter, &pc, &tc);
                         const uint2 mc = a.meta[c];
                         emit_cell(a, rc, base + i, c, mc.y, mc.x, inter, pc, tc);
                     }
@@ -740,11 +806,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
             if (nx) {  // side-table slots are released only after every reader is done (linear probing)
                 __syncthreads();
                 for (uint32_t i = tid; i < nx; i += THREADS) {
-                    const uint32_t xs = t.xtouched()[i];
-                    t.xkeys()[xs] = kEmpty;
-                    t.xv(0)[xs] = 0;
-                    t.xv(1)[xs] = 0;
-                    t.xv(2)[xs] = 0;
+                    const uint32_t xs = xt.touched()[i];
+                    xt.keys()[xs] = kEmpty;
+                    xt.v(0)[xs] = 0;
+                    xt.v(1)[xs] = 0;
+                    xt.v(2)[xs] = 0;
                 }
                 __threadfence();
             }
@@ -758,9 +824,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
     if (lane == 0 && pairs) atomicAdd(a.n_pairs, pairs);
 }
 
-inline size_t score_smem_bytes(uint32_t hbits, uint32_t fcap, int threads) {
-    const size_t H = (size_t)1 << hbits;
-    return H * 8 + (size_t)fcap * 16 + (size_t)(threads / 32) * sizeof(WarpScratch) + H * 2 + 16;
+inline size_t score_smem_bytes(uint32_t t1, uint32_t hbits, uint32_t fcap, int threads) {
+    const size_t H = (size_t)t1 + ((size_t)1 << hbits);
+    return H * 8 + (size_t)fcap * 16 + (size_t)(threads / 32) * (sizeof(WarpScratch) + 64) + H * 2 + 16;
 }
 
 // Last resort for rows with more distinct columns than any shared-memory table holds: the reference's own scheme,
