@@ -63,7 +63,7 @@ def build_engine(force=False, verbose=False):
     deps = _sources(CSRC, INCLUDE)
     if force or _stale(ENGINE_LIB, deps):
         cmd = [NVCC] + ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-pthread", "-shared",
-                              "-I", INCLUDE, "-I", CSRC, "-o", ENGINE_LIB] + srcs + ["-lcudart"]
+                              "-I", INCLUDE, "-I", CSRC, "-o", ENGINE_LIB] + os.environ.get("PD_NVCC_FLAGS", "").split() + srcs + ["-lcudart"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         out = _run(cmd)

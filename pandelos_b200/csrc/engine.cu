@@ -464,7 +464,7 @@ inline uint32_t log2_floor(uint64_t v) {
 inline void levels_of(const Index& ix, Level lv[kLevels]) {
     lv[0] = {512, 9, 128, 256, 256};
     lv[1] = {2048, 11, 256, 512, 1536};
-    lv[2] = {4096, 12, 512, 1024, ~0ull};
+    lv[2] = {4096, 11, 512, 1024, ~0ull};
     lv[3] = {2048, 14, 512, 1024, 0};
     if (const char* e = getenv("PD_LEVELS")) {  // tuning: "t1:hbits:threads:fcap:maxcols,..." for the four levels
         unsigned t1, h, t, f;
@@ -576,7 +576,7 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
     sk::ScoreArgs a;
     memset(&a, 0, sizeof(a));
     a.post = ix.post.p; a.post_cnt = ix.post_cnt.p; a.fwd = ix.fwd.p; a.fwd_cnt = ix.fwd_cnt.p; a.meta = ix.meta.p;
-    a.G = ix.info.G; a.k2 = 2u * (uint32_t)ix.info.k;
+    a.G = ix.info.G; a.S = ix.info.S; a.k2 = 2u * (uint32_t)ix.info.k;
     a.o_score = c.d_score.p; a.o_perc = c.d_perc.p; a.o_trperc = c.d_trperc.p;
     a.o_row = c.d_row.p; a.o_col = c.d_col.p; a.o_g1 = c.d_g1.p; a.o_g2 = c.d_g2.p;
     a.cell_cap = c.cap;

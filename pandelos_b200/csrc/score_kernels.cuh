@@ -11,15 +11,16 @@
 //                inside a gene (U/N > 0.999: rare) and goes to a small per-CTA side table in global memory (L2).
 //   postings     4-byte entries (column gene, bit 31 = "this gene holds the k-mer more than once").  The row's
 //                forward entries are staged in shared memory (cp.async, double buffered across rows) and split by the
-//                index build into three classes:
+//                index build into three classes (long and huge lists are walked first: they carry the homologs):
 //                  short lists  (<= kShortList)  flattened in batches of 32 lists so every lane has a posting,
 //                  long lists                    one warp walks one list, 8 x 32 consecutive postings per round,
 //                                                the next round's loads issued while this round is accumulated,
 //                  huge lists   (> kHugeList)    all warps of the CTA stride over the same list.
-//   table        buckets of 4 slots: a posting's column is hashed to its home bucket, read with one 16-byte shared
-//                load, matched branch-free against the 4 keys and counted with one shared-memory atomic; postings
-//                that miss (first visit of a column in this row, bucket overflow) go to a per-warp queue that is
-//                probed / inserted 32 postings at a time, every lane busy.
+//   table        two tiers of (key, count) slots in shared memory.  Tier 1 is direct mapped by an ORDER-PRESERVING
+//                function of the column, slot = floor(c * T1 / S): one 4-byte shared load + one shared atomic per
+//                posting, and a row's frequent columns (its homologs, one per genome, far apart in gene order) each
+//                keep a slot for the whole row.  Postings whose tier-1 slot belongs to another column go to a
+//                per-warp queue and are probed / inserted into tier 2 (linear probing) 32 at a time, all lanes busy.
 //   finalize     warp-local: each warp compacts the occupied slots of its slice of the table, applies the exact
 //                integer validity gate, reserves output space with one atomic per warp and row, then computes the
 //                float32 Jaccard only for the cells that pass                             library.cpp:493-505
@@ -68,6 +69,7 @@ struct ScoreArgs {
     uint32_t* cursor;
     // parameters
     uint32_t G;
+    uint32_t S;       // genes (debug bounds checks)
     uint32_t k2;      // 2k: perc >= thr  <=>  2k * pc >= K  (exact for K < 2^20, see gate())
     uint32_t hbits;   // log2 of the tier-2 slots H
     uint32_t hmul;    // tier-2 home slot of column c = floor(c * H / S) = umulhi(c, hmul)
@@ -95,6 +97,20 @@ struct ScoreArgs {
     // side tables: per CTA kXSlots x (key, d_inter, d_pc, d_tc) + kXSlots touched indices, clean between rows
     uint32_t* xtab;
 };
+
+#if defined(PD_DEBUG_BOUNDS) && !defined(PD_EMU)
+#define PD_CHECK(cond, id, v)                                                                                        \
+    do {                                                                                                             \
+        if (!(cond)) {                                                                                               \
+            printf("PD_CHECK %d failed v=%u blk=%d thr=%d\n", id, (unsigned)(v), (int)blockIdx.x, (int)threadIdx.x); \
+            __trap();                                                                                                \
+        }                                                                                                            \
+    } while (0)
+#else
+#define PD_CHECK(cond, id, v) \
+    do {                      \
+    } while (0)
+#endif
 
 struct DenseArgs {
     uint32_t S;
@@ -231,6 +247,7 @@ __device__ __forceinline__ uint32_t x_find_or_insert(const XTab& x, uint32_t c) 
 __device__ __forceinline__ uint32_t t2_find_or_insert(const ScoreArgs& a, const Tab& t, uint32_t c) {
     uint32_t hh = t2_home(a, c), probes = 0;
     for (;;) {
+        PD_CHECK(a.t1 + hh < a.nslots, 2, hh);
         const saddr_t addr = t.keys_sa + (a.t1 + hh) * 4u;
         uint32_t kk = lds_u32(addr);
         if (kk == kEmpty) {
@@ -286,6 +303,7 @@ __device__ __noinline__ void add_general(const GenArgs g, uint32_t c, uint32_t n
         }
     }
     uint32_t* cnt = g.keys + g.nslots;
+    PD_CHECK(h < g.nslots, 7, h);
     atomicAdd(&cnt[h], 1u);
     if ((n | m) > 1u) {  // corrections for the repeated k-mer go to the side table
         atomicOr(&cnt[h], kFlag);
@@ -360,6 +378,9 @@ __device__ __forceinline__ void item_miss(const ScoreArgs& a, const Tab& t, Warp
 // two items at a time: both tier-1 loads are in flight before either is compared
 __device__ __forceinline__ void items_add2(const ScoreArgs& a, const Tab& t, WarpQueue& wq, uint32_t c0, uint32_t c1) {
     const uint32_t s0 = t1_slot(a, c0), s1 = t1_slot(a, c1);
+    PD_CHECK(s0 < a.t1 && s1 < a.t1, 1, s0);
+    PD_CHECK(c0 == kNone || c0 < a.S, 11, c0);
+    PD_CHECK(c1 == kNone || c1 < a.S, 12, c1);
     const uint32_t k0 = lds_u32(t.keys_sa + s0 * 4u);
     const uint32_t k1 = lds_u32(t.keys_sa + s1 * 4u);
     const bool hit0 = k0 == c0, hit1 = k1 == c1;  // kNone is never a key: no hit
@@ -594,6 +615,7 @@ __device__ __forceinline__ void emit_cell(const ScoreArgs& a, const RowCtx& rc, 
         a.o_g1[idx] = (int32_t)rc.gr;
         a.o_g2[idx] = (int32_t)gc;
     }
+    PD_CHECK(gc < a.G && c < a.S, 6, gc);
     // scores are positive floats: their bit patterns order like the values
     atomicMax(&a.bh[(size_t)rc.bh_row * a.G + gc], __float_as_uint(score));
     if (a.colmax) atomicMax(&a.colmax[c], __float_as_uint(score));
@@ -722,8 +744,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
         }
         const bool over = *t.over() != 0;
         const uint32_t nx = t.ctl->nx < kXCap ? t.ctl->nx : kXCap;
-        // each warp owns a slice of the table
-        const uint32_t spw = H >= 32u * WARPS ? H / WARPS : 32u;
+        // each warp owns a slice of the table (both tiers, slots [0, H)); H is a multiple of 32
+        const uint32_t spw = ((H / 32 + WARPS - 1) / WARPS) * 32;
         const uint32_t lo = warp * spw;
         if (over) {
             // does not fit: hand the row to the next level, wipe both tables
@@ -752,10 +774,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
                 uint16_t* cw = cand + lo;
                 // ---- occupied slots of the slice, compacted
                 uint32_t n = 0;
-                for (uint32_t s0 = 0; s0 < spw; s0 += 32) {
+                for (uint32_t s0 = 0; s0 < spw && lo + s0 < H; s0 += 32) {
                     const uint32_t s = lo + s0 + lane;
                     const bool occ = keys[s] != kEmpty;
                     const unsigned mb = __ballot_sync(0xffffffffu, occ);
+                    PD_CHECK(s < H && n + 32 <= spw + 32, 4, s);
                     if (occ) cw[n + __popc(mb & lt)] = (uint16_t)s;
                     n += __popc(mb);
                 }
@@ -769,6 +792,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
                     if (i < n) {
                         s = cw[i];
                         const uint32_t c = keys[s];
+                        PD_CHECK(s < H && c < a.S, 5, c);
                         if (c != rc.r) {  // identity cell dropped (library.cpp:485-487)
                             pairs++;
                             uint32_t inter, pc, tc;
