@@ -121,6 +121,23 @@ int pd_compute_scores(pd_index* ix, uint32_t genome, pd_scores* out);
 void pd_scores_release(pd_index* ix, pd_scores* s);
 int pd_last_score_stats(const pd_scores* s, pd_score_stats* out);
 
+/* The whole per-genome task of the reference's Java host on the device (Pangenes.java:60-183): computeScores(genome),
+ * the inter-genome bidirectional-best-hit test (:98-128), the per-row threshold (:146-155) and the intra-genome
+ * (paralog) test (:164-176).  Returns the arguments of the addConnection calls the Java code would make: one entry
+ * (src, dst, score) per inter-genome BBH cell (src = the row gene of `genome`; Java also adds the mirrored (dst, src),
+ * which the other genome's call returns too) and per intra-genome edge (src < dst).  The cells themselves stay in HBM.
+ * Arrays are pinned host memory owned by the library until pd_edges_release.  Thread-safe like pd_compute_scores. */
+typedef struct pd_edges {
+    uint64_t count;
+    const uint32_t* src;
+    const uint32_t* dst;
+    const float* score;
+    uint64_t cells;   /* non-zero cells the filter looked at (= scoresCount of computeScores) */
+    void* owner;      /* private */
+} pd_edges;
+int pd_genome_edges(pd_index* ix, uint32_t genome, pd_edges* out);
+void pd_edges_release(pd_index* ix, pd_edges* e);
+
 /* Device-resident scoring of the gene range [row_begin, row_end) (multi-GPU partitions, bench `value`):
  * cells stay in the context's HBM buffers; d_best_hit (device, (row_end-row_begin) x G floats, may be NULL)
  * receives BH[r][h] = best score of gene r against genome h.  Rows are processed in blocks of `rows_per_launch`

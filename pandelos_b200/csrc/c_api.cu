@@ -108,6 +108,21 @@ void pd_scores_release(pd_index* ix, pd_scores* s) {
     memset(s, 0, sizeof(*s));
 }
 
+int pd_genome_edges(pd_index* ix, uint32_t genome, pd_edges* out) {
+    if (!ix || !out) {
+        pd::set_last_error("null argument");
+        return PD_ERR_INVALID;
+    }
+    memset(out, 0, sizeof(*out));
+    return guarded([&] { ix->ix.genome_edges(genome, out); });
+}
+
+void pd_edges_release(pd_index* ix, pd_edges* e) {
+    if (!ix || !e || !e->owner) return;
+    ix->ix.release(static_cast<pd::ScoreContext*>(e->owner));
+    memset(e, 0, sizeof(*e));
+}
+
 int pd_last_score_stats(const pd_scores* s, pd_score_stats* out) {
     if (!s || !s->owner || !out) return PD_ERR_INVALID;
     pd::Index::context_stats(static_cast<pd::ScoreContext*>(s->owner), out);

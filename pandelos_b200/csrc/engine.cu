@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 
+#include "filter_kernels.cuh"
 #include "index_kernels.cuh"
 #include "prims.cuh"
 #include "score_kernels.cuh"
@@ -63,6 +64,14 @@ struct ScoreContext {
     rt::DevBuf<uint32_t> d_cursors;             // 16
     rt::DevBuf<sk::RowDesc> d_rows, d_ovf;
     rt::DevBuf<uint32_t> d_dense, d_xtab, d_sorttmp;
+    // per-genome network filter (genome_edges)
+    rt::DevBuf<uint32_t> d_imax, d_rowthr, d_esrc, d_edst;
+    rt::DevBuf<float> d_escore;
+    rt::DevBuf<uint8_t> d_flag;
+    rt::PinBuf<uint32_t> h_esrc, h_edst;
+    rt::PinBuf<float> h_escore;
+    uint64_t edge_cap = 0;
+    bool g1_bhrow = false;
     rt::DevBuf<uint64_t> d_rowkeys;
     uint32_t xtab_ctas = 0;
     rt::PinBuf<unsigned long long> h_counters;
@@ -416,9 +425,14 @@ void Index::genome_lists() {
         for (uint32_t s = 0; s < S; s++) genome_rows[cur[genome_of[s]]++] = s;
     }
     d_genome_rows.alloc(std::max<size_t>(S, 1));
+    d_local_of.alloc(std::max<size_t>(S, 1));
     if (S) {
+        std::vector<uint32_t> local_of(S);
+        for (uint32_t g = 0; g < G; g++)
+            for (uint32_t i = genome_ptr[g]; i < genome_ptr[g + 1]; i++) local_of[genome_rows[i]] = i - genome_ptr[g];
         rt::stream_t st = rt::stream_create();
         rt::h2d(d_genome_rows.p, genome_rows.data(), sizeof(uint32_t) * S, st);
+        rt::h2d(d_local_of.p, local_of.data(), sizeof(uint32_t) * S, st);
         rt::sync(st);
         rt::stream_destroy(st);
     }
@@ -431,6 +445,11 @@ namespace {
 
 static const int kMaxCtasPerSm = 16;
 static const int kLevels = 4;  // three first-try levels by row size + the retry level
+
+__global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t* p, uint32_t n, uint32_t v) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i < n) p[i] = v;
+}
 
 // side tables (score_kernels.cuh): keys empty, sums zero
 __global__ void __launch_bounds__(256) xtab_init_kernel(uint32_t* xtab, uint32_t ctas) {
@@ -580,6 +599,7 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
     a.o_score = c.d_score.p; a.o_perc = c.d_perc.p; a.o_trperc = c.d_trperc.p;
     a.o_row = c.d_row.p; a.o_col = c.d_col.p; a.o_g1 = c.d_g1.p; a.o_g2 = c.d_g2.p;
     a.cell_cap = c.cap;
+    a.g1_bhrow = c.g1_bhrow ? 1u : 0u;
     a.n_cells = c.d_counters.p + 0;
     a.n_pairs = c.d_counters.p + 1;
     a.bh = d_bh;
@@ -710,6 +730,96 @@ void Index::compute_scores(uint32_t genome, pd_scores* out) {
         out->scoresMaxMappings = c.h_map.p;
         out->owner = cp;
     } catch (...) {
+        release(cp);
+        throw;
+    }
+}
+
+void Index::genome_edges(uint32_t genome, pd_edges* out) {
+    if (genome >= info.G) throw Error(PD_ERR_INVALID, "unknown genome");
+    rt::set_device(device);
+    genome_lists();
+    ScoreContext* cp = acquire();
+    ScoreContext& c = *cp;
+    try {
+        memset(&c.stats, 0, sizeof(c.stats));
+        const uint32_t S = info.S, G = info.G;
+        const uint32_t r0 = genome_ptr[genome], rows = genome_ptr[genome + 1] - r0;
+        rt::event_record(c.ev_call0, c.st);
+        c.d_bh.ensure(std::max<size_t>((size_t)rows * G, 1));
+        c.d_colmax.ensure(std::max<size_t>(S, 1));
+        if (c.cap == 0) c.ensure_cells(opt.cell_capacity ? opt.cell_capacity : std::max<uint64_t>(1u << 16, (uint64_t)rows * 1024));
+        uint64_t cells = 0, pairs = 0, lookups = 0, fwd_entries = 0;
+        c.g1_bhrow = true;  // the filter wants the row's index inside the genome next to every cell
+        for (int attempt = 0; attempt < 3; attempt++) {
+            rt::zero(c.d_bh.p, sizeof(uint32_t) * (size_t)rows * G, c.st);
+            rt::zero(c.d_colmax.p, sizeof(uint32_t) * S, c.st);
+            cells = rows ? run_rows(c, rows, d_genome_rows.p + r0, 0, c.d_bh.p, c.d_colmax.p, &pairs, &lookups, &fwd_entries) : 0;
+            if (cells <= c.cap) break;
+            c.ensure_cells(cells + cells / 8);
+        }
+        c.g1_bhrow = false;
+        if (cells > c.cap) throw Error(PD_ERR_CUDA, "cell count unstable between passes");
+
+        // ---- the Java host's filter over the cells, on the device (Pangenes.java:98-176)
+        uint64_t edges = 0;
+        if (cells) {
+            c.d_flag.ensure(cells);
+            c.d_imax.ensure(std::max<size_t>(G, 1));
+            c.d_rowthr.ensure(std::max<size_t>(rows, 1));
+            if (c.edge_cap == 0) {
+                c.edge_cap = std::max<uint64_t>(1u << 14, (uint64_t)rows * 4);
+                c.d_esrc.alloc(c.edge_cap); c.d_edst.alloc(c.edge_cap); c.d_escore.alloc(c.edge_cap);
+            }
+            fk::FilterArgs fa;
+            memset(&fa, 0, sizeof(fa));
+            fa.cells = cells;
+            fa.score = c.d_score.p; fa.row = c.d_row.p; fa.col = c.d_col.p; fa.bhrow = c.d_g1.p; fa.g2 = c.d_g2.p;
+            fa.genome = genome; fa.G = G;
+            fa.bh = c.d_bh.p; fa.colmax = c.d_colmax.p; fa.local_of = d_local_of.p;
+            fa.imax = c.d_imax.p; fa.rowthr = c.d_rowthr.p; fa.flag = c.d_flag.p;
+            fa.n_edges = c.d_counters.p + 6;
+            rt::zero(c.d_imax.p, sizeof(uint32_t) * G, c.st);
+            rt::fill_byte(c.d_rowthr.p, 0, sizeof(uint32_t) * rows, c.st);
+            PD_LAUNCH(fill_u32_kernel, blocks_for(rows), 256, 0, c.st, c.d_rowthr.p, rows, 0x7F800000u);  // +inf
+            PD_LAUNCH(fk::inter_mark_kernel, blocks_for(cells), 256, 0, c.st, fa);
+            PD_LAUNCH(fk::row_threshold_kernel, blocks_for(cells), 256, 0, c.st, fa);
+            for (int attempt = 0; attempt < 2; attempt++) {
+                fa.e_src = c.d_esrc.p; fa.e_dst = c.d_edst.p; fa.e_score = c.d_escore.p;
+                fa.edge_cap = c.edge_cap;
+                rt::zero(c.d_counters.p + 6, sizeof(unsigned long long), c.st);
+                PD_LAUNCH(fk::edge_emit_kernel, blocks_for(cells), 256, 0, c.st, fa);
+                rt::d2h(c.h_counters.p + 6, c.d_counters.p + 6, sizeof(unsigned long long), c.st);
+                rt::sync(c.st);
+                edges = c.h_counters.p[6];
+                if (edges <= c.edge_cap) break;
+                c.edge_cap = edges + edges / 8;
+                c.d_esrc.alloc(c.edge_cap); c.d_edst.alloc(c.edge_cap); c.d_escore.alloc(c.edge_cap);
+            }
+            c.stats.launches += 5;
+        }
+        const size_t ne = std::max<uint64_t>(edges, 1);
+        c.h_esrc.ensure(ne); c.h_edst.ensure(ne); c.h_escore.ensure(ne);
+        rt::d2h(c.h_esrc.p, c.d_esrc.p, sizeof(uint32_t) * edges, c.st);
+        rt::d2h(c.h_edst.p, c.d_edst.p, sizeof(uint32_t) * edges, c.st);
+        rt::d2h(c.h_escore.p, c.d_escore.p, sizeof(float) * edges, c.st);
+        rt::event_record(c.ev_call1, c.st);
+        rt::sync(c.st);
+        rt::collect();
+        c.stats.total_ms = rt::event_ms(c.ev_call0, c.ev_call1);
+        c.stats.rows = rows;
+        c.stats.lookups = lookups;
+        c.stats.fwd_entries = fwd_entries;
+        c.stats.pairs = pairs;
+        c.stats.cells = cells;
+        out->count = edges;
+        out->src = c.h_esrc.p;
+        out->dst = c.h_edst.p;
+        out->score = c.h_escore.p;
+        out->cells = cells;
+        out->owner = cp;
+    } catch (...) {
+        c.g1_bhrow = false;
         release(cp);
         throw;
     }

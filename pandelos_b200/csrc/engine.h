@@ -35,6 +35,7 @@ struct Index {
     rt::DevBuf<uint32_t> grp_head;   // kept only with opt.keep_sorted
     rt::DevBuf<uint64_t> ent_rank;   // kept only with opt.keep_sorted
     rt::DevBuf<uint32_t> d_genome_rows;  // with genome_rows (below)
+    rt::DevBuf<uint32_t> d_local_of;     // gene -> index inside its genome (flat_map of every genome, library.cpp:428-432)
 
     // host mirrors (O(S)), fetched from the device on first use: host_mirrors() / genome_lists()
     std::mutex mirror_mu;
@@ -59,6 +60,7 @@ struct Index {
     ScoreContext* acquire();
     void release(ScoreContext* c);
     void compute_scores(uint32_t genome, pd_scores* out);
+    void genome_edges(uint32_t genome, pd_edges* out);
     void score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_per_launch, float* d_best_hit, pd_score_stats* st);
     void partition_rows(uint32_t parts, bool snap, uint32_t* bounds);
     static void context_stats(ScoreContext* c, pd_score_stats* out);

@@ -1,0 +1,202 @@
+// pangenes — native host of the B200 engine with the command line of the reference's Java host
+// (reference ig/infoasys/cli/pangenes/Cli.java:13-57: -i/--input, -k/--kvalue, -o/--output required; -j/--threads,
+// -c/--complexity, -h/--help), for boxes without a JVM:
+//
+//     pangenes -i in.faa -k K -o out.net          the line of pandelos.sh:73, one word changed
+//
+//   .faa reader      two lines per gene, blank lines skipped, header split on TAB, genome ids in first-seen order
+//                    (PangeneIData.java:30-75)
+//   per genome       pd_genome_edges: computeScores + the BBH / paralog filter of Pangenes.java:98-176 on the GPU
+//   network          PangeneNet.addConnection semantics (first score of a (src, dest) wins, PangeneNet.java:49-62);
+//                    .net written as saveToFile(file, false) (PangeneNet.java:159-179): one line "src\tdst\tscore"
+//                    per undirected edge with src <= dst, score = the float widened to double and printed the way
+//                    Java's Double.toString prints it.  Line ORDER: the reference iterates a HashMap; here lines are
+//                    sorted by (src, dst) — netclu_ng.py reads the file into a graph, the order carries no meaning.
+#include <charconv>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "pandelos_b200.h"
+
+namespace {
+
+std::string trim(const std::string& s) {  // String.trim(): code points <= U+0020 off both ends
+    size_t a = 0, b = s.size();
+    while (a < b && (unsigned char)s[a] <= 0x20) a++;
+    while (b > a && (unsigned char)s[b - 1] <= 0x20) b--;
+    return s.substr(a, b - a);
+}
+
+// Double.toString(d) for finite d > 0 (JDK 19+: shortest decimal that round-trips; decimal notation for
+// 1e-3 <= d < 1e7, otherwise computerized scientific notation)
+std::string java_double_to_string(double d) {
+    if (d == 0) return "0.0";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof(buf), d, std::chars_format::scientific);
+    std::string s(buf, r.ptr);  // d[.ddd]e[+-]xx, shortest round trip
+    const size_t e = s.find('e');
+    std::string mant = s.substr(0, e);
+    const int exp10 = atoi(s.c_str() + e + 1);
+    std::string digits;
+    for (char ch : mant)
+        if (ch != '.' && ch != '-') digits.push_back(ch);
+    std::string out = d < 0 ? "-" : "";
+    if (exp10 >= -3 && exp10 < 7) {
+        if (exp10 >= 0) {
+            std::string ip = digits.substr(0, std::min<size_t>(digits.size(), (size_t)exp10 + 1));
+            while ((int)ip.size() < exp10 + 1) ip.push_back('0');
+            std::string fp = digits.size() > (size_t)exp10 + 1 ? digits.substr((size_t)exp10 + 1) : "0";
+            out += ip + "." + fp;
+        } else {
+            out += "0." + std::string((size_t)(-exp10 - 1), '0') + digits;
+        }
+    } else {
+        out += digits.substr(0, 1) + "." + (digits.size() > 1 ? digits.substr(1) : "0") + "E" + std::to_string(exp10);
+    }
+    return out;
+}
+
+void usage() {
+    printf("usage: pangenes -i <arg> -k <arg> -o <arg> [-j <arg>] [-c] [-h]\n"
+           " -c,--complexity     Compute the required number of operations without computing the network (fast)\n"
+           " -h,--help           Print this help message\n"
+           " -i,--input <arg>    Input file (.faa) to process\n"
+           " -j,--threads <arg>  Number of threads to use for the computation (accepted; the GPU engine ignores it)\n"
+           " -k,--kvalue <arg>   Length of the kmers used by the algorithm\n"
+           " -o,--output <arg>   Output file for the network\n");
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    std::string in, out;
+    int k = 0;
+    bool complexity = false;
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto need = [&](const char* what) -> const char* {
+            if (i + 1 >= argc) {
+                fprintf(stderr, "Missing argument for option: %s\n", what);
+                exit(2);
+            }
+            return argv[++i];
+        };
+        if (a == "-i" || a == "--input") in = need("i");
+        else if (a == "-o" || a == "--output") out = need("o");
+        else if (a == "-k" || a == "--kvalue") k = atoi(need("k"));
+        else if (a == "-j" || a == "--threads") need("j");
+        else if (a == "-c" || a == "--complexity") complexity = true;
+        else if (a == "-h" || a == "--help") {
+            usage();
+            return 0;
+        } else {
+            fprintf(stderr, "Unrecognized option: %s\n", a.c_str());
+            usage();
+            return 2;
+        }
+    }
+    if (in.empty() || out.empty() || k == 0) {
+        fprintf(stderr, "Missing required options: i, k, o\n");
+        usage();
+        return 2;
+    }
+
+    // ---- PangeneIData.readFromFile
+    std::ifstream f(in);
+    if (!f) {
+        fprintf(stderr, "cannot read %s\n", in.c_str());
+        return 1;
+    }
+    std::vector<uint8_t> residues;
+    std::vector<uint64_t> offsets(1, 0);
+    std::vector<uint32_t> genome_of;
+    std::unordered_map<std::string, uint32_t> genome_id;
+    std::string line, genome_name;
+    bool name_line = true;
+    while (std::getline(f, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        const std::string t = trim(line);
+        if (t.empty()) continue;
+        if (name_line) {
+            const size_t tab = t.find('\t');
+            genome_name = t.substr(0, tab);
+            if (tab == std::string::npos || t.find('\t', tab + 1) == std::string::npos) {
+                // the reference indexes cc[1], cc[2]: a header with fewer than three fields is an error there too
+                fprintf(stderr, "malformed header line (need genome<TAB>gene<TAB>product): %s\n", t.c_str());
+                return 1;
+            }
+        } else {
+            residues.insert(residues.end(), t.begin(), t.end());
+            offsets.push_back(residues.size());
+            auto it = genome_id.find(genome_name);
+            if (it == genome_id.end()) it = genome_id.emplace(genome_name, (uint32_t)genome_id.size()).first;
+            genome_of.push_back(it->second);
+        }
+        name_line = !name_line;
+    }
+    const uint32_t S = (uint32_t)genome_of.size();
+
+    pd_options opt;
+    memset(&opt, 0, sizeof(opt));
+    opt.device = -1;
+    opt.verbose = 1;
+    pd_index* ix = nullptr;
+    if (pd_build(residues.data(), offsets.data(), genome_of.data(), S, k, &opt, &ix) != PD_OK) {
+        if (k <= 0) {  // library.cpp:90-93
+            printf("K value must be greater than 0.\n");
+            return 1;
+        }
+        fprintf(stderr, "pangenes: %s\n", pd_last_error());
+        return 1;
+    }
+    if (complexity) {  // Pangenes.java:33-36
+        pd_free(ix);
+        return 0;
+    }
+    pd_index_info info;
+    pd_info(ix, &info);
+
+    // ---- Pangenes.java:60-183, one task per genome; PangeneNet.addConnection
+    std::map<uint64_t, float> net;  // (src << 32 | dst) -> score, first score wins
+    auto add = [&](uint32_t src, uint32_t dst, float score) { net.emplace(((uint64_t)src << 32) | dst, score); };
+    for (uint32_t g = 0; g < info.G; g++) {
+        printf("Working on genome %u/%u\n", g, info.G);
+        pd_edges e;
+        if (pd_genome_edges(ix, g, &e) != PD_OK) {
+            fprintf(stderr, "pangenes: %s\n", pd_last_error());
+            return 1;
+        }
+        printf("Filtered count: %llu\n", (unsigned long long)e.cells);
+        for (uint64_t i = 0; i < e.count; i++) {
+            add(e.src[i], e.dst[i], e.score[i]);
+            if (genome_of[e.src[i]] != genome_of[e.dst[i]]) add(e.dst[i], e.src[i], e.score[i]);  // Pangenes.java:103-104
+        }
+        pd_edges_release(ix, &e);
+    }
+    pd_free(ix);
+
+    // ---- PangeneNet.saveToFile(file, false)
+    FILE* o = fopen(out.c_str(), "w");
+    if (!o) {
+        fprintf(stderr, "cannot write %s\n", out.c_str());
+        return 1;
+    }
+    uint64_t lines = 0;
+    for (const auto& kv : net) {
+        const uint32_t src = (uint32_t)(kv.first >> 32), dst = (uint32_t)kv.first;
+        if (src <= dst) {
+            fprintf(o, "%u\t%u\t%s\n", src, dst, java_double_to_string((double)kv.second).c_str());
+            lines++;
+        }
+    }
+    fclose(o);
+    printf("Network: %llu undirected edges written to %s\n", (unsigned long long)lines, out.c_str());
+    return 0;
+}

@@ -87,6 +87,7 @@ struct ScoreArgs {
     int32_t* o_col;
     int32_t* o_g1;
     int32_t* o_g2;
+    uint32_t g1_bhrow;               // non-zero: o_g1 receives the row's index inside the call instead of its genome
     unsigned long long cell_cap;
     unsigned long long* n_cells;     // running cell count (keeps counting past cell_cap)
     unsigned long long* n_pairs;     // candidate cells evaluated (col != row)
@@ -612,7 +613,7 @@ __device__ __forceinline__ void emit_cell(const ScoreArgs& a, const RowCtx& rc, 
         a.o_trperc[idx] = tr_perc;
         a.o_row[idx] = (int32_t)rc.r;
         a.o_col[idx] = (int32_t)c;
-        a.o_g1[idx] = (int32_t)rc.gr;
+        a.o_g1[idx] = (int32_t)(a.g1_bhrow ? rc.bh_row : rc.gr);
         a.o_g2[idx] = (int32_t)gc;
     }
     PD_CHECK(gc < a.G && c < a.S, 6, gc);

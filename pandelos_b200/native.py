@@ -53,6 +53,11 @@ class ScoreStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class EdgesStruct(C.Structure):
+    _fields_ = [("count", C.c_uint64), ("src", C.POINTER(C.c_uint32)), ("dst", C.POINTER(C.c_uint32)), ("score", C.POINTER(C.c_float)),
+                ("cells", C.c_uint64), ("owner", C.c_void_p)]
+
+
 _lib = None
 _lib_path = None
 
@@ -81,6 +86,8 @@ def load(path=None):
     L.pd_compute_scores.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(ScoresStruct)]
     L.pd_scores_release.argtypes = [C.c_void_p, C.POINTER(ScoresStruct)]
     L.pd_last_score_stats.argtypes = [C.POINTER(ScoresStruct), C.POINTER(ScoreStats)]
+    L.pd_genome_edges.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(EdgesStruct)]
+    L.pd_edges_release.argtypes = [C.c_void_p, C.POINTER(EdgesStruct)]
     L.pd_score_partition_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(ScoreStats)]
     L.pd_partition_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p]
     _lib, _lib_path = L, path
@@ -200,6 +207,22 @@ class PangeneNative:
         st = ScoresStruct()
         _check(self._L.pd_compute_scores(self._h, int(genome), C.byref(st)))
         return st, (lambda: self._L.pd_scores_release(self._h, C.byref(st)))
+
+    def genomeEdges(self, genome):
+        """The pool task of Pangenes.java:60-183 for one genome, filter included, on the device: returns
+        (src uint32[], dst uint32[], score float32[], cells) = the addConnection calls (inter-genome BBH edges once,
+        as (row gene, column gene); intra-genome edges with src < dst)."""
+        e = EdgesStruct()
+        _check(self._L.pd_genome_edges(self._h, int(genome), C.byref(e)))
+        try:
+            n = int(e.count)
+
+            def arr(p, dt):
+                return np.ctypeslib.as_array(p, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
+
+            return arr(e.src, np.uint32), arr(e.dst, np.uint32), arr(e.score, np.float32), int(e.cells)
+        finally:
+            self._L.pd_edges_release(self._h, C.byref(e))
 
     # ---- diagnostics / partitions
     def gene_stats(self):

@@ -190,6 +190,7 @@ inline float __uint2float_rn(unsigned v) { return static_cast<float>(v); }
 inline int __float_as_int(float f) { return cuemu::from_bits<int>(cuemu::to_bits(f)); }
 inline float __int_as_float(int i) { return cuemu::from_bits<float>(cuemu::to_bits(i)); }
 inline unsigned __float_as_uint(float f) { return cuemu::from_bits<unsigned>(cuemu::to_bits(f)); }
+inline float __uint_as_float(unsigned u) { return cuemu::from_bits<float>(cuemu::to_bits(u)); }
 template <class T>
 inline T __ldg(const T* p) { return *p; }
 
