@@ -136,38 +136,47 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t* __restrict__
 static const int kEntThreads = 512;
 static const int kEntItems = 8;
 static const int kEntTile = kEntThreads * kEntItems;  // 4096 keys per block
+static const int kEntWarps = kEntThreads / 32;
 
-// flags of the kEntItems consecutive keys of this thread: bit j of hm / gm = key j is an entry / group head
-__device__ __forceinline__ void entry_flags(const uint64_t* __restrict__ keys, uint64_t N, int seq_bits, uint64_t base,
-                                            uint64_t (&kv)[kEntItems], unsigned& hm, unsigned& gm) {
-    uint64_t prev = 0;
-    if (base > 0 && base <= N) prev = keys[base - 1];
-    hm = gm = 0;
-#pragma unroll
-    for (int j = 0; j < kEntItems; j++) {
-        const uint64_t idx = base + j;
-        kv[j] = idx < N ? keys[idx] : 0ull;
-        if (idx < N) {
-            const bool first = idx == 0;
-            if (first || kv[j] != prev) hm |= 1u << j;
-            if (first || (kv[j] >> seq_bits) != (prev >> seq_bits)) gm |= 1u << j;
-        }
-        prev = kv[j];
-    }
+// Layout: warp w of a block owns keys [tile + w * 256, + 256); in round j its lanes hold 32 consecutive keys, so
+// every load and store is coalesced and prefix counts inside a round are popcounts of ballots.
+// Flags of this lane's key in round j: hm / gm = ballots of "entry head" / "group head" over the warp.
+__device__ __forceinline__ void entry_round(const uint64_t* __restrict__ keys, uint64_t N, int seq_bits, uint64_t idx, uint64_t& kv,
+                                            unsigned& hm, unsigned& gm) {
+    const unsigned lane = threadIdx.x & 31;
+    const bool in = idx < N;
+    kv = in ? keys[idx] : 0ull;
+    uint64_t prev = __shfl_up_sync(0xffffffffu, kv, 1);
+    if (lane == 0) prev = (idx > 0 && in) ? keys[idx - 1] : 0ull;
+    const bool first = idx == 0;
+    hm = __ballot_sync(0xffffffffu, in && (first || kv != prev));
+    gm = __ballot_sync(0xffffffffu, in && (first || (kv >> seq_bits) != (prev >> seq_bits)));
 }
 
 __global__ void __launch_bounds__(kEntThreads) entry_count_kernel(const uint64_t* __restrict__ keys, uint64_t N, int seq_bits,
                                                                    uint32_t* __restrict__ tile_heads, uint32_t* __restrict__ tile_gheads) {
-    __shared__ uint32_t scratch[33];
-    const uint64_t base = (uint64_t)blockIdx.x * kEntTile + (uint64_t)threadIdx.x * kEntItems;
-    uint64_t kv[kEntItems];
-    unsigned hm, gm;
-    entry_flags(keys, N, seq_bits, base, kv, hm, gm);
-    uint32_t tot;
-    prims::block_excl_scan<kEntThreads>((uint32_t)__popc(hm) | ((uint32_t)__popc(gm) << 16), scratch, &tot);
+    __shared__ uint32_t s_h, s_g;
+    if (threadIdx.x == 0) s_h = s_g = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t base = (uint64_t)blockIdx.x * kEntTile + (uint64_t)warp * (32 * kEntItems);
+    uint32_t h = 0, g = 0;
+#pragma unroll
+    for (int j = 0; j < kEntItems; j++) {
+        uint64_t kv;
+        unsigned hm, gm;
+        entry_round(keys, N, seq_bits, base + j * 32 + lane, kv, hm, gm);
+        h += __popc(hm);
+        g += __popc(gm);
+    }
+    if (lane == 0) {
+        atomicAdd(&s_h, h);
+        atomicAdd(&s_g, g);
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        tile_heads[blockIdx.x] = tot & 0xFFFFu;
-        tile_gheads[blockIdx.x] = tot >> 16;
+        tile_heads[blockIdx.x] = s_h;
+        tile_gheads[blockIdx.x] = s_g;
     }
 }
 
@@ -177,38 +186,47 @@ __global__ void __launch_bounds__(kEntThreads) entry_apply_kernel(const uint64_t
                                                                    uint32_t* __restrict__ post, uint32_t* __restrict__ post_cnt,
                                                                    uint32_t* __restrict__ ent_gid, uint32_t* __restrict__ grp_head,
                                                                    uint64_t* __restrict__ ent_rank, uint32_t* __restrict__ spurious) {
-    __shared__ uint32_t scratch[33];
-    const uint64_t base = (uint64_t)blockIdx.x * kEntTile + (uint64_t)threadIdx.x * kEntItems;
+    __shared__ uint32_t w_h[kEntWarps], w_g[kEntWarps];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint64_t base = (uint64_t)blockIdx.x * kEntTile + (uint64_t)warp * (32 * kEntItems);
     uint64_t kv[kEntItems];
-    unsigned hm, gm;
-    entry_flags(keys, N, seq_bits, base, kv, hm, gm);
-    uint32_t tot;
-    const uint32_t ex = prims::block_excl_scan<kEntThreads>((uint32_t)__popc(hm) | ((uint32_t)__popc(gm) << 16), scratch, &tot);
-    uint32_t e = tile_head_off[blockIdx.x] + (ex & 0xFFFFu);       // entries before this thread's keys
-    uint32_t gcount = tile_ghead_off[blockIdx.x] + (ex >> 16);     // group heads before this thread's keys
+    unsigned hm[kEntItems], gm[kEntItems];
+    uint32_t h = 0, g = 0;
+#pragma unroll
+    for (int j = 0; j < kEntItems; j++) {
+        entry_round(keys, N, seq_bits, base + j * 32 + lane, kv[j], hm[j], gm[j]);
+        h += __popc(hm[j]);
+        g += __popc(gm[j]);
+    }
+    if (lane == 0) {
+        w_h[warp] = h;
+        w_g[warp] = g;
+    }
+    __syncthreads();
+    uint32_t e0 = tile_head_off[blockIdx.x], g0 = tile_ghead_off[blockIdx.x];  // entries / group heads before this warp's keys
+    for (unsigned w = 0; w < warp; w++) {
+        e0 += w_h[w];
+        g0 += w_g[w];
+    }
     const uint64_t seq_mask = (1ull << seq_bits) - 1ull;
 #pragma unroll
     for (int j = 0; j < kEntItems; j++) {
-        const uint64_t idx = base + j;
-        if (idx >= N) break;
-        bool gh = (gm >> j) & 1u;
-        if ((hm >> j) & 1u) {
-            if (gh && e == U - 1 && e != 0) {  // the tail merge
+        const uint64_t idx = base + j * 32 + lane;
+        // the key after mine (equal keys follow each other): lane + 1, or the next round's / warp's first key
+        uint64_t nxt = __shfl_down_sync(0xffffffffu, kv[j], 1);
+        if (lane == 31) nxt = idx + 1 < N ? keys[idx + 1] : ~kv[j];
+        if ((hm[j] >> lane) & 1u) {
+            const uint32_t e = e0 + __popc(hm[j] & lt);
+            bool gh = (gm[j] >> lane) & 1u;
+            uint32_t gid = g0 + __popc(gm[j] & lt) + (gh ? 1u : 0u) - 1u;
+            if (gh && e == U - 1 && e != 0) {  // the tail merge: the last entry joins the group before it
                 gh = false;
+                gid -= 1;
                 *spurious = 1;
-            } else if (gh) {
-                gcount++;
-            }
-            const uint32_t gid = gcount - 1;
-            // multiplicity: equal keys follow each other
-            uint64_t nxt = ~kv[j];
-            if (j + 1 < kEntItems) {
-                if (idx + 1 < N) nxt = kv[j + 1 < kEntItems ? j + 1 : j];
-            } else if (idx + 1 < N) {
-                nxt = keys[idx + 1];
             }
             uint32_t cnt = 1;
-            if (nxt == kv[j]) {
+            if (idx + 1 < N && nxt == kv[j]) {
                 cnt = 2;
                 while (idx + cnt < N && keys[idx + cnt] == kv[j]) cnt++;
             }
@@ -217,8 +235,9 @@ __global__ void __launch_bounds__(kEntThreads) entry_apply_kernel(const uint64_t
             ent_gid[e] = gid;
             if (gh) grp_head[gid] = e;
             if (ent_rank) ent_rank[e] = kv[j] >> seq_bits;
-            e++;
         }
+        e0 += __popc(hm[j]);
+        g0 += __popc(gm[j]);
     }
 }
 

@@ -21,6 +21,7 @@ static const int kSortItems = 16;
 static const int kSortTile = kSortThreads * kSortItems;  // 4096 keys per block
 static const int kSortWarps = kSortThreads / 32;
 static const int kRadix = 256;
+static const int kSortGroup = 8;  // keys ranked together
 
 // ---------------------------------------------------------------------------------------------- block helpers
 
@@ -171,23 +172,35 @@ __global__ void __launch_bounds__(kSortThreads, 4) radix_scatter_kernel(const ui
     uint16_t rnk[kSortItems];
     uint32_t* my_wc = wc + warp * kRadix;
     const unsigned lt_mask = (1u << lane) - 1u;
+    // Ranking in groups of kSortGroup keys: first the group's peer masks (independent match instructions, all in
+    // flight together), then the per-digit counter updates, which must stay in key order (stability)
 #pragma unroll
-    for (int j = 0; j < kSortItems; j++) {
-        const uint32_t local = warp * (32 * kSortItems) + j * 32 + lane;
-        const bool valid = local < tile_n;
-        key[j] = valid ? keys[tile_base + local] : 0ull;
-        // invalid lanes take a private pseudo-digit so they never join a valid lane's peer group
-        const unsigned d = valid ? ((unsigned)(key[j] >> shift) & 0xFFu) : (256u + lane);
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const unsigned leader = __ffs(peers) - 1;
-        uint32_t base_cnt = 0;
-        if (valid && lane == leader) {
-            base_cnt = my_wc[d];
-            my_wc[d] = base_cnt + __popc(peers);
+    for (int j0 = 0; j0 < kSortItems; j0 += kSortGroup) {
+        unsigned peers[kSortGroup];
+        unsigned dig[kSortGroup];
+#pragma unroll
+        for (int jj = 0; jj < kSortGroup; jj++) {
+            const int j = j0 + jj;
+            const uint32_t local = warp * (32 * kSortItems) + j * 32 + lane;
+            const bool valid = local < tile_n;
+            key[j] = valid ? keys[tile_base + local] : 0ull;
+            // invalid lanes take a private pseudo-digit so they never join a valid lane's peer group
+            dig[jj] = valid ? ((unsigned)(key[j] >> shift) & 0xFFu) : (256u + lane);
+            peers[jj] = __match_any_sync(0xffffffffu, dig[jj]);
         }
-        base_cnt = __shfl_sync(0xffffffffu, base_cnt, leader);
-        rnk[j] = (uint16_t)(base_cnt + __popc(peers & lt_mask));
-        __syncwarp();
+#pragma unroll
+        for (int jj = 0; jj < kSortGroup; jj++) {
+            const int j = j0 + jj;
+            const unsigned leader = __ffs(peers[jj]) - 1;
+            uint32_t base_cnt = 0;
+            if (dig[jj] < 256u && lane == leader) {
+                base_cnt = my_wc[dig[jj]];
+                my_wc[dig[jj]] = base_cnt + __popc(peers[jj]);
+            }
+            base_cnt = __shfl_sync(0xffffffffu, base_cnt, leader);
+            rnk[j] = (uint16_t)(base_cnt + __popc(peers[jj] & lt_mask));
+            __syncwarp();
+        }
     }
     __syncthreads();
 

@@ -143,7 +143,6 @@ __device__ __forceinline__ void cp_async_wait_all() {
 typedef uintptr_t saddr_t;
 __device__ __forceinline__ saddr_t smem_addr(const void* p) { return reinterpret_cast<uintptr_t>(p); }
 __device__ __forceinline__ uint32_t lds_u32(saddr_t a) { return *reinterpret_cast<volatile uint32_t*>(a); }
-__device__ __forceinline__ uint4 lds_v4(saddr_t a) { return *reinterpret_cast<uint4*>(a); }
 __device__ __forceinline__ uint32_t atoms_cas(saddr_t a, uint32_t cmp, uint32_t val) { return atomicCAS(reinterpret_cast<uint32_t*>(a), cmp, val); }
 __device__ __forceinline__ void reds_inc(saddr_t a) { atomicAdd(reinterpret_cast<uint32_t*>(a), 1u); }
 #else
@@ -152,11 +151,6 @@ __device__ __forceinline__ saddr_t smem_addr(const void* p) { return static_cast
 __device__ __forceinline__ uint32_t lds_u32(saddr_t a) {
     uint32_t v;
     asm volatile("ld.volatile.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint4 lds_v4(saddr_t a) {
-    uint4 v;
-    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
     return v;
 }
 __device__ __forceinline__ uint32_t atoms_cas(saddr_t a, uint32_t cmp, uint32_t val) {
