@@ -339,7 +339,34 @@ def main():
         else:
             e_ms, e_pairs = float(te[0].item()), float(te[1].item())
         e2e = {"value": e_pairs / (e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e_ms}
+               "ms_per_step": e_ms, "call": "pd_build + pd_compute_scores per genome (the JNI boundary), 2 host threads"}
+
+        # the same step through the native-CLI call path: pd_genome_edges runs the Java host's BBH filter on the device,
+        # so only network edges come back (reported next to e2e, not instead of it)
+        def one_genome_edges(pn, g):
+            e, rel = pn.genome_edges_raw(g)
+            n = int(e.count)
+            rel()
+            return 12 * n, n
+
+        barrier()
+        t0 = time.perf_counter()
+        pn = native.PangeneNative(k, data_pinned, device=local, contexts=2)
+        with ThreadPoolExecutor(max_workers=2) as pool:
+            res_e = list(pool.map(lambda g: one_genome_edges(pn, g), range(g0, g1)))
+        barrier()
+        n_ms = (time.perf_counter() - t0) * 1e3
+        pn.close()
+        n_pairs = float(pairs_e)
+        if world > 1:
+            tn = torch.tensor([n_ms, n_pairs], dtype=torch.float64, device=dev)
+            tn_max = tn.clone()
+            dist.all_reduce(tn_max, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tn, op=dist.ReduceOp.SUM)
+            n_ms, n_pairs = float(tn_max[0].item()), float(tn[1].item())
+        e2e["network_path"] = {"value": n_pairs / (n_ms * 1e-3), "unit": "pairs/s", "ms_per_step": n_ms,
+                               "d2h_bytes_per_step": int(sum(r[0] for r in res_e)), "edges": int(sum(r[1] for r in res_e)),
+                               "call": "pd_build + pd_genome_edges per genome (native pangenes CLI path), 2 host threads"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -224,6 +224,12 @@ class PangeneNative:
         finally:
             self._L.pd_edges_release(self._h, C.byref(e))
 
+    def genome_edges_raw(self, genome):
+        """Zero-copy variant of genomeEdges: returns (EdgesStruct, release callable)."""
+        e = EdgesStruct()
+        _check(self._L.pd_genome_edges(self._h, int(genome), C.byref(e)))
+        return e, (lambda: self._L.pd_edges_release(self._h, C.byref(e)))
+
     # ---- diagnostics / partitions
     def gene_stats(self):
         S = self.info.S
