@@ -183,11 +183,22 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library
+    # chatter) is sent to stderr, and the JSON line goes to the saved descriptor
+    global print
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*a, **kw):  # noqa: A001 — the result line
+        kw.setdefault("file", real_stdout)
+        kw.setdefault("flush", True)
+        _print(*a, **kw)
+
     if args.impl == "reference":
         return run_reference(args)
 
-    # stdout carries exactly one JSON line: NCCL's own banner / debug lines go to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from pandelos_b200 import native

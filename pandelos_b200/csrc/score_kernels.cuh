@@ -45,7 +45,10 @@ static const uint32_t kXSlots = 2048;           // side-table slots per CTA (glo
 static const uint32_t kXCap = kXSlots * 3 / 4;
 static const uint32_t kProbeLimit = 160;        // probes after which a row is declared too big for its table
 static const uint32_t kNone = 0x7FFFFFFFu;      // "no posting" in a lane's item (gene ids are < 2^31 - 1)
-static const int kItems = 8;                    // postings per lane per round of a long list
+#ifndef PD_KITEMS
+#define PD_KITEMS 4
+#endif
+static const int kItems = PD_KITEMS;            // postings per lane per round of a long list
 static const int kItemsA = 4;                   // ... of the flattened short lists
 static const uint32_t kQueue = 128;             // per-warp ring of postings that missed tier 1
 static const int kDenseThreads = 256;

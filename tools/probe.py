@@ -40,7 +40,7 @@ def main():
             t = time.time()
             st = pn.score_partition_device(0, min(rows, i.S))
             wall = time.time() - t
-            alg = 8.0 * st.lookups + 8.0 * st.fwd_entries + 28.0 * st.cells + 4.0 * st.rows * i.G + 8.0 * i.S
+            alg = 8.0 * st.lookups + 12.0 * st.fwd_entries + 20.0 * st.cells + 4.0 * st.rows * i.G + 8.0 * i.S
             print(json.dumps({"workload": spec, "rows": st.rows, "lookups": st.lookups, "pairs": st.pairs, "cells": st.cells,
                               "fallback_rows": st.fallback_rows, "retry_rows": st.retry_rows, "launches": st.launches, "kernel_ms": round(st.kernel_ms, 3),
                               "total_ms": round(st.total_ms, 3), "wall_ms": round(wall * 1e3, 3),
