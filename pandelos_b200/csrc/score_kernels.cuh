@@ -135,6 +135,14 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
 #endif
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+#ifdef PD_EMU
+    *reinterpret_cast<uint4*>(smem_dst) = *reinterpret_cast<const uint4*>(gsrc);
+#else
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+#endif
+}
 __device__ __forceinline__ void cp_async_wait_all() {
 #ifndef PD_EMU
     asm volatile("cp.async.wait_all;\n" ::: "memory");
@@ -686,49 +694,48 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
     for (;;) {
         cp_async_wait_all();
         __syncthreads();  // the row's descriptor and first forward segment are staged; the table is clean
-        const uint4 rw0 = s_desc[buf][0], rw1 = s_desc[buf][1];  // (gene, bh_row, fb, fe), (kr, gr, fm, fh)
-        if (rw0.x == kEmpty) break;
+        // Nothing of the row's descriptor or of the look-ahead is kept in registers across the accumulate phase (the hot
+        // loop runs at the register cap): the descriptor is re-read from shared memory afterwards, the next row's
+        // descriptor travels by cp.async straight into the other buffer.
+        if (s_desc[buf][0].x == kEmpty) break;
         t.ctl = &s_ctl[buf];
-        uint4 nd0 = make_uint4(kEmpty, 0u, 0u, 0u), nd1 = make_uint4(0u, 0u, 0u, 0u);
         uint32_t idx_after = 0;
-        if (tid == 0) {  // both are consumed after the accumulate phase
+        if (tid == 0) {
             if (idx_next < n_rows) {
-                nd0 = rows4[2 * (size_t)idx_next];
-                nd1 = rows4[2 * (size_t)idx_next + 1];
+                cp_async16(&s_desc[buf ^ 1][0], &rows4[2 * (size_t)idx_next]);
+                cp_async16(&s_desc[buf ^ 1][1], &rows4[2 * (size_t)idx_next + 1]);
+            } else {
+                s_desc[buf ^ 1][0] = make_uint4(kEmpty, 0u, 0u, 0u);
             }
-            idx_after = atomicAdd(a.cursor, 1u);
+            idx_after = atomicAdd(a.cursor, 1u);  // consumed after the accumulate phase
         }
-        RowCtx rc;
-        rc.r = rw0.x;
-        rc.bh_row = rw0.y;
-        rc.kr = rw1.x;
-        rc.gr = rw1.y;
-        const uint32_t fb = rw0.z, fe = rw0.w, fm = rw1.z, fh = rw1.w;
         uint2* fbuf = fwdbuf + (size_t)buf * fcap;
 
         // ---- accumulate, one staged segment of forward entries at a time
-        for (uint32_t f0 = fb;;) {
-            const uint32_t f1 = fe - f0 < fcap ? fe : f0 + fcap;
-            const uint32_t ns = fm > f0 ? (fm < f1 ? fm - f0 : f1 - f0) : 0u;
-            const uint32_t nl = fh > f0 ? (fh < f1 ? fh - f0 : f1 - f0) : 0u;
-            accumulate<THREADS>(a, t, fbuf, f0, ns, nl, f1 - f0, ws, s_ctl[buf].ctr);
-            if (f1 >= fe) break;
-            __syncthreads();
-            f0 = f1;
-            const uint32_t f2 = fe - f0 < fcap ? fe : f0 + fcap;
-            for (uint32_t f = f0 + tid; f < f2; f += THREADS) fbuf[f - f0] = a.fwd[f];
-            if (tid == 0) s_ctl[buf].ctr[0] = s_ctl[buf].ctr[1] = 0;
-            __syncthreads();
+        {
+            const uint32_t fb = s_desc[buf][0].z, fe = s_desc[buf][0].w, fm = s_desc[buf][1].z, fh = s_desc[buf][1].w;
+            for (uint32_t f0 = fb;;) {
+                const uint32_t f1 = fe - f0 < fcap ? fe : f0 + fcap;
+                const uint32_t ns = fm > f0 ? (fm < f1 ? fm - f0 : f1 - f0) : 0u;
+                const uint32_t nl = fh > f0 ? (fh < f1 ? fh - f0 : f1 - f0) : 0u;
+                accumulate<THREADS>(a, t, fbuf, f0, ns, nl, f1 - f0, ws, s_ctl[buf].ctr);
+                if (f1 >= fe) break;
+                __syncthreads();
+                f0 = f1;
+                const uint32_t f2 = fe - f0 < fcap ? fe : f0 + fcap;
+                for (uint32_t f = f0 + tid; f < f2; f += THREADS) fbuf[f - f0] = a.fwd[f];
+                if (tid == 0) s_ctl[buf].ctr[0] = s_ctl[buf].ctr[1] = 0;
+                __syncthreads();
+            }
         }
         if (tid == 0) {
-            s_desc[buf ^ 1][0] = nd0;
-            s_desc[buf ^ 1][1] = nd1;
             s_ctl[buf ^ 1].nx = 0;
             s_ctl[buf ^ 1].over = 0;
             s_ctl[buf ^ 1].ctr[0] = 0;
             s_ctl[buf ^ 1].ctr[1] = 0;
             idx_next = idx_after;
         }
+        cp_async_wait_all();  // thread 0: the next row's descriptor has landed
         __threadfence_block();
         __syncthreads();  // the table is complete
 
@@ -740,6 +747,12 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
                 for (uint32_t f = d0.z + tid; f < f1; f += THREADS) cp_async8(&nbuf[f - d0.z], &a.fwd[f]);
             }
         }
+        const uint4 rw0 = s_desc[buf][0], rw1 = s_desc[buf][1];  // (gene, bh_row, fb, fe), (kr, gr, fm, fh)
+        RowCtx rc;
+        rc.r = rw0.x;
+        rc.bh_row = rw0.y;
+        rc.kr = rw1.x;
+        rc.gr = rw1.y;
         const bool over = *t.over() != 0;
         const uint32_t nx = t.ctl->nx < kXCap ? t.ctl->nx : kXCap;
         // each warp owns a slice of the table (both tiers, slots [0, H)); H is a multiple of 32
