@@ -46,7 +46,7 @@ static const uint32_t kXCap = kXSlots * 3 / 4;
 static const uint32_t kProbeLimit = 160;        // probes after which a row is declared too big for its table
 static const uint32_t kNone = 0x7FFFFFFFu;      // "no posting" in a lane's item (gene ids are < 2^31 - 1)
 #ifndef PD_KITEMS
-#define PD_KITEMS 4
+#define PD_KITEMS 8
 #endif
 static const int kItems = PD_KITEMS;            // postings per lane per round of a long list
 static const int kItemsA = 4;                   // ... of the flattened short lists
@@ -647,13 +647,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t fcap = a.fcap;
-    uint32_t* xbase = a.xtab + (size_t)blockIdx.x * (5 * kXSlots);
 
     Tab t;
     t.keys = keys;
     t.keys_sa = smem_addr(keys);
-    XTab xt;
-    xt.base = xbase;
 
     for (uint32_t i = tid; i < H; i += THREADS) {
         keys[i] = kEmpty;
@@ -688,7 +685,6 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
             for (uint32_t f = d0.z + tid; f < f1; f += THREADS) cp_async8(&fwdbuf[f - d0.z], &a.fwd[f]);
         }
     }
-    unsigned long long pairs = 0;
     int buf = 0;
 
     for (;;) {
@@ -755,6 +751,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
         rc.gr = rw1.y;
         const bool over = *t.over() != 0;
         const uint32_t nx = t.ctl->nx < kXCap ? t.ctl->nx : kXCap;
+        uint32_t pairs = 0;  // candidate cells of this row seen by this lane
+        XTab xt;
+        xt.base = a.xtab + (size_t)blockIdx.x * (5 * kXSlots);
         // each warp owns a slice of the table (both tiers, slots [0, H)); H is a multiple of 32
         const uint32_t spw = ((H / 32 + WARPS - 1) / WARPS) * 32;
         const uint32_t lo = warp * spw;
@@ -850,13 +849,12 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
                 __threadfence();
             }
         }
+        // one atomic per warp and row for the pair statistic (kept out of the registers of the accumulate phase)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
+        if (lane == 0 && pairs) atomicAdd(a.n_pairs, (unsigned long long)pairs);
         buf ^= 1;
     }
-
-    // one atomic per warp for the pair statistic
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
-    if (lane == 0 && pairs) atomicAdd(a.n_pairs, pairs);
 }
 
 inline size_t score_smem_bytes(uint32_t t1, uint32_t hbits, uint32_t fcap, int threads) {
