@@ -701,12 +701,11 @@ void Index::compute_scores(uint32_t genome, pd_scores* out) {
         rt::d2h(c.h_trperc.p, c.d_trperc.p, sizeof(float) * cells, c.st);
         rt::d2h(c.h_row.p, c.d_row.p, sizeof(int32_t) * cells, c.st);
         rt::d2h(c.h_col.p, c.d_col.p, sizeof(int32_t) * cells, c.st);
+        rt::d2h(c.h_g1.p, c.d_g1.p, sizeof(int32_t) * cells, c.st);
         rt::d2h(c.h_g2.p, c.d_g2.p, sizeof(int32_t) * cells, c.st);
         rt::d2h(c.h_bh.p, c.d_bh.p, sizeof(float) * (size_t)rows * G, c.st);
         rt::d2h(c.h_colmax.p, c.d_colmax.p, sizeof(float) * S, c.st);
         rt::event_record(c.ev_call1, c.st);
-        // first_seq_genome is the call's genome for every cell (library.cpp:569): written here, not copied
-        std::fill(c.h_g1.p, c.h_g1.p + cells, (int32_t)genome);
         // this genome's rows in flat_map while the copies run; release() puts INT32_MAX back
         for (uint32_t i = 0; i < rows; i++) c.h_map.p[genome_rows[r0 + i]] = (int32_t)i;
         c.map_r0 = r0;
