@@ -222,7 +222,10 @@ def main():
     q = min(q, w.G)
     if world * q > w.G:
         q = max(1, w.G // world)
-    data = native.PangeneIData(w.residues, w.offsets, w.genome_of)
+    # the O(S) gene table (offsets, genome ids) in pinned host memory: it is re-sent with every index build
+    off_pin = torch.from_numpy(w.offsets.astype(np.int64)).pin_memory()
+    gid_pin = torch.from_numpy(w.genome_of.astype(np.int32)).pin_memory()
+    data = native.PangeneIData(w.residues, off_pin.numpy().view(np.uint64), gid_pin.numpy().view(np.uint32))
     # the job's query genes = the first world x q genomes, split by posting-list volume at genome boundaries
     if world > 1:
         pn0 = native.PangeneNative(k, data, device=local)

@@ -353,14 +353,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     info.groups = n_groups;
     info.R = R;
     info.lookups = lookups;
-    {   // longest gene in k-mers: only reported
-        uint32_t mk = 0;
-        for (uint32_t s = 0; s < S; s++) {
-            const uint64_t len = offsets[s + 1] - offsets[s];
-            if (len >= (uint64_t)k) mk = std::max<uint32_t>(mk, (uint32_t)(len - k + 1));
-        }
-        info.max_kseq = mk;
-    }
+    info.max_kseq = h_flags[2];
     info.build_ms[0] = total ? t_hist.ms() : 0;
     if (N) {
         info.build_ms[1] = t_enc.ms();

@@ -35,15 +35,15 @@ static const int kClsBits = 21;  // a gene holds < 2^20 k-mers
 static const unsigned long long kClsMask = (1ull << kClsBits) - 1ull;
 
 // ---- per gene: kseq_lengths, meta, checks.  flags[0]: bit 0 = offsets descend, bit 1 = a gene of 2^20 or more
-// residues; flags[1] = largest genome id.  kseq has S + 1 entries (the last one 0) so its exclusive scan ends in N.
+// residues; flags[1] = largest genome id; flags[2] = longest gene in k-mers.  kseq has S + 1 entries (the last one 0) so
+// its exclusive scan ends in N.
 __global__ void __launch_bounds__(256) gene_meta_kernel(const uint64_t* __restrict__ off, const uint32_t* __restrict__ genome_ids,
                                                          uint32_t S, int k, uint32_t* __restrict__ kseq, uint2* __restrict__ meta,
                                                          uint32_t* __restrict__ flags) {
     const uint32_t s = blockIdx.x * 256u + threadIdx.x;
-    uint32_t err = 0, gid = 0;
+    uint32_t err = 0, gid = 0, kl = 0;
     if (s < S) {
         const uint64_t o0 = off[s], o1 = off[s + 1];
-        uint32_t kl = 0;
         if (o1 < o0) {
             err = 1;
         } else {
@@ -62,10 +62,13 @@ __global__ void __launch_bounds__(256) gene_meta_kernel(const uint64_t* __restri
         err |= __shfl_xor_sync(0xffffffffu, err, d);
         const uint32_t o = __shfl_xor_sync(0xffffffffu, gid, d);
         gid = o > gid ? o : gid;
+        const uint32_t ok = __shfl_xor_sync(0xffffffffu, kl, d);
+        kl = ok > kl ? ok : kl;
     }
     if ((threadIdx.x & 31) == 0) {
         if (err) atomicOr(&flags[0], err);
         atomicMax(&flags[1], gid);
+        atomicMax(&flags[2], kl);
     }
 }
 
