@@ -39,7 +39,7 @@ typedef struct pd_index pd_index; /* the device-resident index: replaces `pair_i
 typedef struct pd_options {
     int32_t device;          /* CUDA ordinal; -1 = the calling thread's current device */
     int32_t verbose;         /* 1 = print the reference's cost report (library.cpp:347-370) to stdout */
-    int32_t contexts;        /* concurrent pd_compute_scores calls served without blocking (0 = default 2) */
+    int32_t contexts;        /* concurrent pd_compute_scores calls served without blocking (0 = default 4) */
     int32_t hash_log2;       /* log2 slots of the per-row shared-memory accumulator (0 = default 12) */
     uint64_t cell_capacity;  /* initial per-call cell buffer, in cells (0 = automatic) */
     int32_t keep_sorted;     /* 1 = keep the sorted k-mer keys so pd_entries can return ranks (tests) */

@@ -5,8 +5,12 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <map>
+#include <thread>
 
 #include "filter_kernels.cuh"
 #include "index_kernels.cuh"
@@ -80,6 +84,8 @@ struct ScoreContext {
     rt::PinBuf<int32_t> h_row, h_col, h_g1, h_g2, h_map;
     pd_score_stats stats;
     uint32_t map_r0 = 0, map_rows = 0;  // rows currently set in h_map
+    bool host_cells = false;            // the pinned cell arrays follow `cap`
+    unsigned long long seq = 0;         // last completion number asked of the stream (publish / wait)
 
     explicit ScoreContext(Index* i) : ix(i) {
         st = rt::stream_create();
@@ -89,7 +95,8 @@ struct ScoreContext {
         ev_k1 = rt::event_create();
         d_counters.alloc(8);
         d_cursors.alloc(16);
-        h_counters.ensure(8);
+        h_counters.ensure(16);
+        memset(h_counters.p, 0, 16 * sizeof(unsigned long long));
         memset(&stats, 0, sizeof(stats));
     }
     ~ScoreContext() {
@@ -104,16 +111,60 @@ struct ScoreContext {
         d_score.alloc(n); d_perc.alloc(n); d_trperc.alloc(n);
         d_row.alloc(n); d_col.alloc(n); d_g1.alloc(n); d_g2.alloc(n);
         cap = n;
+        if (host_cells) ensure_host_cells();
+    }
+    // pinned images of the cell arrays, sized with the device arrays so that they are reallocated as rarely
+    void ensure_host_cells() {
+        host_cells = true;
+        const size_t n = std::max<uint64_t>(cap, 1);
+        h_score.ensure(n); h_perc.ensure(n); h_trperc.ensure(n);
+        h_row.ensure(n); h_col.ensure(n); h_g1.ensure(n); h_g2.ensure(n);
     }
 };
 
+// PD_TRACE=1: host wall-clock per phase of the per-genome calls, summed over calls and printed when the index dies
+// takes a stage token unless the stage is switched off
+struct StageLock {
+    std::unique_lock<std::mutex> lk;
+    StageLock(std::mutex& m, bool on) : lk(m, std::defer_lock) { if (on) lk.lock(); }
+    void unlock() { if (lk.owns_lock()) lk.unlock(); }
+};
+
+namespace trace {
+enum { kAcquire, kPre, kZ, kGrow, kKeys, kRadix, kSortLaunch, kLaunch, kLevelsWait, kRetryWait, kTokenWait, kCopyEnqueue, kCopyWait, kTail, kCalls, kN };
+static std::atomic<uint64_t> ns[kN];
+static const char* const names[kN] = {"acquire", "pre", "zero", "grow", "keys", "radix", "sort_launch", "launch", "levels_wait", "retry_wait", "token_wait", "copy_enqueue", "copy_wait", "tail", "calls"};
+static bool on() {
+    static const bool v = getenv("PD_TRACE") != nullptr;
+    return v;
+}
+struct Clock {
+    std::chrono::steady_clock::time_point t;
+    Clock() : t(std::chrono::steady_clock::now()) {}
+    void lap(int what) {
+        if (!on()) return;
+        const auto n = std::chrono::steady_clock::now();
+        ns[what] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(n - t).count();
+        t = n;
+    }
+};
+static void report() {
+    if (!on() || ns[kCalls] == 0) return;
+    fprintf(stderr, "[pd trace] %llu calls;", (unsigned long long)ns[kCalls].load());
+    for (int i = 0; i < kCalls; i++) fprintf(stderr, " %s %.1f ms;", names[i], (double)ns[i].exchange(0) * 1e-6);
+    fprintf(stderr, "\n");
+    ns[kCalls] = 0;
+}
+}  // namespace trace
+
 Index::~Index() {
+    trace::report();
     for (ScoreContext* c : all_ctx) delete c;
 }
 
 ScoreContext* Index::acquire() {
     std::unique_lock<std::mutex> lk(mu);
-    const size_t limit = opt.contexts > 0 ? (size_t)opt.contexts : 2;
+    const size_t limit = opt.contexts > 0 ? (size_t)opt.contexts : 4;
     for (;;) {
         if (!free_ctx.empty()) {
             ScoreContext* c = free_ctx.back();
@@ -153,6 +204,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     if (rt::device_count() <= 0) throw Error(PD_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU path");
     if (opt.device >= 0) rt::set_device(opt.device);
     device = rt::current_device();
+    if (const char* e = getenv("PD_STAGE_TOKENS")) stage_tokens = atoi(e);
     sms = rt::sm_count();
     smem_optin = rt::max_optin_smem();
 
@@ -444,6 +496,70 @@ __global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t* p, uint32_t n, 
     if (i < n) p[i] = v;
 }
 
+// Zero fill of per-call buffers by a kernel.  cudaMemsetAsync of a large range may be carried out by a copy engine, where
+// it queues behind the result arrays another context is sending to the host; a kernel only needs SMs.
+__global__ void __launch_bounds__(256) zero_words_kernel(uint32_t* p, uint64_t words) {
+    const uint64_t stride = (uint64_t)gridDim.x * 256u;
+    uint64_t i = (uint64_t)blockIdx.x * 256u + threadIdx.x;
+    const uint64_t quads = (reinterpret_cast<uintptr_t>(p) & 15u) == 0 ? words / 4 : 0;
+    uint4* q = reinterpret_cast<uint4*>(p);
+    for (uint64_t j = i; j < quads; j += stride) q[j] = make_uint4(0, 0, 0, 0);
+    for (uint64_t j = quads * 4 + i; j < words; j += stride) p[j] = 0;
+}
+static void zero_words(void* p, uint64_t bytes, rt::stream_t st) {
+    if (!bytes) return;
+    const uint64_t words = bytes / 4;  // every buffer here holds 4- or 8-byte elements
+    const unsigned grid = (unsigned)std::min<uint64_t>((words / 4 + 255) / 256 + 1, 148 * 8);
+    PD_LAUNCH(zero_words_kernel, grid, 256, 0, st, static_cast<uint32_t*>(p), words);
+}
+
+// Job counters and completion flags go to the host by stores into pinned (device-visible) host memory, and the host
+// waits by polling that memory (ScoreContext::wait).  Two things measured on the per-genome path with several calling
+// threads made this necessary: a cudaMemcpyAsync of the counters queues on the device-to-host copy engine behind the
+// result arrays another call is sending, and a thread blocked in cudaStreamSynchronize slows down the kernel launches
+// of the other threads by an order of magnitude (driver lock).  Polling memory involves no driver call.
+static const uint32_t kSeqSlot = 15;
+__global__ void publish_counters_kernel(unsigned long long* host, const unsigned long long* dev, uint32_t first, uint32_t count,
+                                        unsigned long long seq) {
+    if (threadIdx.x < count) host[first + threadIdx.x] = dev[first + threadIdx.x];
+    __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<volatile unsigned long long*>(host + kSeqSlot) = seq;
+        __threadfence_system();
+    }
+}
+
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#elif defined(__aarch64__)
+    asm volatile("yield");
+#endif
+}
+// queues the counters [first, first + count) and a completion number behind the work already on the context's stream
+static void publish(ScoreContext& c, uint32_t first, uint32_t count) {
+    c.seq++;
+    PD_LAUNCH(publish_counters_kernel, 1, 32, 0, c.st, c.h_counters.p, c.d_counters.p, first, count, c.seq);
+}
+// waits for the last publish() by polling the completion number.  The stream itself is only asked (for failures) every
+// 20 ms: cudaStreamQuery takes the driver lock that the launches of the other calling threads need.
+static void wait(ScoreContext& c) {
+    volatile unsigned long long* f = c.h_counters.p + kSeqSlot;
+    auto last = std::chrono::steady_clock::now();
+    for (uint32_t spins = 1; *f != c.seq; spins++) {
+        for (int i = 0; i < 16; i++) cpu_relax();
+        if ((spins & 255u) == 0) {
+            const auto now = std::chrono::steady_clock::now();
+            if (now - last > std::chrono::milliseconds(20)) {
+                last = now;
+                if (rt::stream_idle(c.st) && *f != c.seq) throw Error(PD_ERR_CUDA, "completion number never arrived");
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+}
+
 // side tables (score_kernels.cuh): keys empty, sums zero
 __global__ void __launch_bounds__(256) xtab_init_kernel(uint32_t* xtab, uint32_t ctas) {
     const uint64_t n = (uint64_t)ctas * 5 * sk::kXSlots;
@@ -514,8 +630,20 @@ inline void levels_of(const Index& ix, Level lv[kLevels]) {
 template <int THREADS>
 void launch_rows_t(ScoreContext& c, sk::ScoreArgs& a, size_t smem) {
     Index& ix = *c.ix;
-    rt::allow_smem(sk::score_rows_kernel<THREADS>, smem);
-    int occ = std::min(kMaxCtasPerSm, std::max(1, rt::occupancy(sk::score_rows_kernel<THREADS>, THREADS, smem)));
+    // the shared-memory opt-in and the occupancy of a (kernel, shared memory, device) combination never change: ask once
+    static std::mutex cache_mu;
+    static std::map<std::pair<int, size_t>, int> cache;
+    int occ;
+    {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        auto it = cache.find(std::make_pair(ix.device, smem));
+        if (it == cache.end()) {
+            rt::allow_smem(sk::score_rows_kernel<THREADS>, smem);
+            const int o = std::min(kMaxCtasPerSm, std::max(1, rt::occupancy(sk::score_rows_kernel<THREADS>, THREADS, smem)));
+            it = cache.emplace(std::make_pair(ix.device, smem), o).first;
+        }
+        occ = it->second;
+    }
     unsigned grid = (unsigned)std::min<uint64_t>(a.n_rows, (uint64_t)ix.sms * occ);
     PD_LAUNCH(sk::score_rows_kernel<THREADS>, grid, THREADS, smem, c.st, a);
 }
@@ -549,6 +677,7 @@ void launch_rows(ScoreContext& c, sk::ScoreArgs a, const Level& lv, int cursor_i
 static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, uint32_t gene_base, uint32_t* d_bh, uint32_t* d_colmax,
                          uint64_t* pairs, uint64_t* lookups, uint64_t* fwd_entries) {
     Index& ix = *c.ix;
+    trace::Clock tc;
     Level lv[kLevels];
     levels_of(ix, lv);
     const uint32_t want_ctas = (uint32_t)ix.sms * kMaxCtasPerSm;
@@ -557,10 +686,12 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
         PD_LAUNCH(xtab_init_kernel, (unsigned)ix.sms * 4, 256, 0, c.st, c.d_xtab.p, want_ctas);
         c.xtab_ctas = want_ctas;
     }
-    rt::zero(c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
-    rt::zero(c.d_cursors.p, 16 * sizeof(uint32_t), c.st);
-    c.d_rows.ensure(n);
-    c.d_ovf.ensure((size_t)2 * n);
+    tc.lap(trace::kPre);
+    zero_words(c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
+    zero_words(c.d_cursors.p, 16 * sizeof(uint32_t), c.st);
+    tc.lap(trace::kZ);
+    c.d_rows.grow(n);
+    c.d_ovf.grow((size_t)2 * n);
 
     // ---- row descriptors on the device: sorted by (first-try level, family key)
     sk::ClassifyArgs ca;
@@ -578,13 +709,17 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
     for (int l = 0; l < 3; l++) ca.max_cols[l] = lv[l].max_cols;
     ca.counts = c.d_cursors.p + 8;  // [8..10]
     ca.stats = c.d_counters.p + 4;  // [4], [5]
-    c.d_rowkeys.ensure((size_t)2 * n);
-    c.d_sorttmp.ensure(prims::radix_tmp_words(n) + 16);
+    c.d_rowkeys.grow((size_t)2 * n);
+    c.d_sorttmp.grow(prims::radix_tmp_words(n) + 16);
+    tc.lap(trace::kGrow);
     PD_LAUNCH(sk::row_keys_kernel, blocks_for(n), 256, 0, c.st, ca, c.d_rowkeys.p);
+    tc.lap(trace::kKeys);
     uint64_t nl = 0;
     const uint64_t* sorted_keys = prims::radix_sort_u64(c.d_rowkeys.p, c.d_rowkeys.p + n, n, 31, 64, c.d_sorttmp.p, c.st, &nl);
+    tc.lap(trace::kRadix);
     PD_LAUNCH(sk::row_desc_kernel, blocks_for(n), 256, 0, c.st, ca, sorted_keys, c.d_rows.p);
     c.stats.launches += 2 + nl;
+    tc.lap(trace::kSortLaunch);
 
     sk::ScoreArgs a;
     memset(&a, 0, sizeof(a));
@@ -611,44 +746,49 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
         b.n_overflow = c.d_counters.p + 2;
         launch_rows(c, b, lv[level], level);
     }
-    rt::d2h(c.h_counters.p, c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
-    rt::sync(c.st);
-    // retry level: rows that overflowed their first table
-    if (c.h_counters.p[2]) {
-        c.stats.retry_rows += c.h_counters.p[2];
+    // retry level: rows that overflowed their first table.  Their count stays on the device (no host round trip in
+    // the middle of the job: a counter read-back would queue behind the result arrays another call is sending)
+    {
         sk::ScoreArgs b = a;
         b.rows = c.d_ovf.p;
-        b.n_rows = (uint32_t)c.h_counters.p[2];
+        b.n_rows = n;  // upper bound: sizes the grid
+        b.n_rows_ovf = c.d_counters.p + 2;
         b.overflow_rows = c.d_ovf.p + n;
         b.n_overflow = c.d_counters.p + 3;
         launch_rows(c, b, lv[kLevels - 1], kLevels - 1);
-        rt::d2h(c.h_counters.p, c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
-        rt::sync(c.st);
-        // last resort: dense global accumulators
-        const uint32_t nr = (uint32_t)c.h_counters.p[3];
-        if (nr) {
-            const unsigned grid = std::min<unsigned>(nr, 32);
-            const size_t words = (size_t)grid * 4 * ix.info.S;
-            if (c.d_dense.n < words) {
-                c.d_dense.alloc(words);
-                rt::zero(c.d_dense.p, words * sizeof(uint32_t), c.st);
-            }
-            sk::ScoreArgs b2 = a;
-            b2.rows = c.d_ovf.p + n;
-            b2.n_rows = nr;
-            b2.cursor = c.d_cursors.p + kLevels;
-            sk::DenseArgs d;
-            d.S = ix.info.S;
-            d.acc = c.d_dense.p;
-            PD_LAUNCH(sk::score_rows_dense_kernel, grid, sk::kDenseThreads, 0, c.st, b2, d);
-            c.stats.launches++;
-            c.stats.fallback_rows += nr;
-            rt::d2h(c.h_counters.p, c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
-        }
     }
+    publish(c, 0, 8);
     rt::event_record(c.ev_k1, c.st);
-    rt::sync(c.st);
+    tc.lap(trace::kLaunch);
+    wait(c);
+    tc.lap(trace::kLevelsWait);
     c.stats.kernel_ms += rt::event_ms(c.ev_k0, c.ev_k1);
+    c.stats.retry_rows += c.h_counters.p[2];
+    // last resort: dense global accumulators
+    if (const uint32_t nr = (uint32_t)c.h_counters.p[3]) {
+        const unsigned grid = std::min<unsigned>(nr, 32);
+        const size_t words = (size_t)grid * 4 * ix.info.S;
+        if (c.d_dense.n < words) {
+            c.d_dense.alloc(words);
+            zero_words(c.d_dense.p, words * sizeof(uint32_t), c.st);
+        }
+        sk::ScoreArgs b2 = a;
+        b2.rows = c.d_ovf.p + n;
+        b2.n_rows = nr;
+        b2.cursor = c.d_cursors.p + kLevels;
+        sk::DenseArgs d;
+        d.S = ix.info.S;
+        d.acc = c.d_dense.p;
+        rt::event_record(c.ev_k0, c.st);
+        PD_LAUNCH(sk::score_rows_dense_kernel, grid, sk::kDenseThreads, 0, c.st, b2, d);
+        c.stats.launches++;
+        c.stats.fallback_rows += nr;
+        publish(c, 0, 8);
+        rt::event_record(c.ev_k1, c.st);
+        wait(c);
+        tc.lap(trace::kRetryWait);
+        c.stats.kernel_ms += rt::event_ms(c.ev_k0, c.ev_k1);
+    }
     *pairs = c.h_counters.p[1];
     *lookups = c.h_counters.p[4];
     *fwd_entries = c.h_counters.p[5];
@@ -659,6 +799,7 @@ void Index::compute_scores(uint32_t genome, pd_scores* out) {
     if (genome >= info.G) throw Error(PD_ERR_INVALID, "unknown genome");
     rt::set_device(device);
     genome_lists();
+    trace::Clock tc;
     ScoreContext* cp = acquire();
     ScoreContext& c = *cp;
     try {
@@ -666,24 +807,28 @@ void Index::compute_scores(uint32_t genome, pd_scores* out) {
         const uint32_t S = info.S, G = info.G;
         const uint32_t r0 = genome_ptr[genome], rows = genome_ptr[genome + 1] - r0;
         rt::event_record(c.ev_call0, c.st);
-        c.d_bh.ensure(std::max<size_t>((size_t)rows * G, 1));
+        c.d_bh.grow(std::max<size_t>((size_t)rows * G, 1));
         c.d_colmax.ensure(std::max<size_t>(S, 1));
-        if (c.cap == 0) c.ensure_cells(opt.cell_capacity ? opt.cell_capacity : std::max<uint64_t>(1u << 16, (uint64_t)rows * 1024));
+        if (c.cap == 0) c.ensure_cells(opt.cell_capacity ? opt.cell_capacity : std::max<uint64_t>(1u << 16, (uint64_t)rows * 1536));
         uint64_t cells = 0, pairs = 0, lookups = 0, fwd_entries = 0;
+        StageLock compute(compute_token, stage_tokens & 1);
+        tc.lap(trace::kAcquire);
         for (int attempt = 0; attempt < 3; attempt++) {
-            rt::zero(c.d_bh.p, sizeof(uint32_t) * (size_t)rows * G, c.st);
-            rt::zero(c.d_colmax.p, sizeof(uint32_t) * S, c.st);
+            zero_words(c.d_bh.p, sizeof(uint32_t) * (size_t)rows * G, c.st);
+            zero_words(c.d_colmax.p, sizeof(uint32_t) * S, c.st);
             cells = rows ? run_rows(c, rows, d_genome_rows.p + r0, 0, c.d_bh.p, c.d_colmax.p, &pairs, &lookups, &fwd_entries) : 0;
             if (cells <= c.cap) break;
-            c.ensure_cells(cells + cells / 8);
+            c.ensure_cells(cells + cells / 2);
         }
         if (cells > c.cap) throw Error(PD_ERR_CUDA, "cell count unstable between passes");
         if (cells > 0x7fffffffull) throw Error(PD_ERR_UNSUPPORTED, "more than 2^31 cells in one computeScores call");
 
-        const size_t nc = std::max<uint64_t>(cells, 1);
-        c.h_score.ensure(nc); c.h_perc.ensure(nc); c.h_trperc.ensure(nc);
-        c.h_row.ensure(nc); c.h_col.ensure(nc); c.h_g1.ensure(nc); c.h_g2.ensure(nc);
-        c.h_bh.ensure(std::max<size_t>((size_t)rows * G, 1));
+        compute.unlock();
+        tc = trace::Clock();
+        StageLock copy(copy_token, stage_tokens & 2);
+        tc.lap(trace::kTokenWait);
+        c.ensure_host_cells();
+        c.h_bh.grow(std::max<size_t>((size_t)rows * G, 1));
         c.h_colmax.ensure(std::max<size_t>(S, 1));
         if (c.h_map.n < std::max<size_t>(S, 1)) {  // flat_map (library.cpp:428-432): all INT32_MAX between calls
             c.h_map.ensure(std::max<size_t>(S, 1));
@@ -703,8 +848,14 @@ void Index::compute_scores(uint32_t genome, pd_scores* out) {
         for (uint32_t i = 0; i < rows; i++) c.h_map.p[genome_rows[r0 + i]] = (int32_t)i;
         c.map_r0 = r0;
         c.map_rows = rows;
-        rt::sync(c.st);
+        publish(c, 0, 0);
+        tc.lap(trace::kCopyEnqueue);
+        wait(c);
+        copy.unlock();
+        tc.lap(trace::kCopyWait);
         rt::collect();
+        tc.lap(trace::kTail);
+        if (trace::on()) trace::ns[trace::kCalls]++;
         c.stats.total_ms = rt::event_ms(c.ev_call0, c.ev_call1);
         c.stats.rows = rows;
         c.stats.lookups = lookups;
@@ -740,17 +891,18 @@ void Index::genome_edges(uint32_t genome, pd_edges* out) {
         const uint32_t S = info.S, G = info.G;
         const uint32_t r0 = genome_ptr[genome], rows = genome_ptr[genome + 1] - r0;
         rt::event_record(c.ev_call0, c.st);
-        c.d_bh.ensure(std::max<size_t>((size_t)rows * G, 1));
+        c.d_bh.grow(std::max<size_t>((size_t)rows * G, 1));
         c.d_colmax.ensure(std::max<size_t>(S, 1));
-        if (c.cap == 0) c.ensure_cells(opt.cell_capacity ? opt.cell_capacity : std::max<uint64_t>(1u << 16, (uint64_t)rows * 1024));
+        if (c.cap == 0) c.ensure_cells(opt.cell_capacity ? opt.cell_capacity : std::max<uint64_t>(1u << 16, (uint64_t)rows * 1536));
         uint64_t cells = 0, pairs = 0, lookups = 0, fwd_entries = 0;
+        StageLock compute(compute_token, stage_tokens & 1);
         c.g1_bhrow = true;  // the filter wants the row's index inside the genome next to every cell
         for (int attempt = 0; attempt < 3; attempt++) {
-            rt::zero(c.d_bh.p, sizeof(uint32_t) * (size_t)rows * G, c.st);
-            rt::zero(c.d_colmax.p, sizeof(uint32_t) * S, c.st);
+            zero_words(c.d_bh.p, sizeof(uint32_t) * (size_t)rows * G, c.st);
+            zero_words(c.d_colmax.p, sizeof(uint32_t) * S, c.st);
             cells = rows ? run_rows(c, rows, d_genome_rows.p + r0, 0, c.d_bh.p, c.d_colmax.p, &pairs, &lookups, &fwd_entries) : 0;
             if (cells <= c.cap) break;
-            c.ensure_cells(cells + cells / 8);
+            c.ensure_cells(cells + cells / 2);
         }
         c.g1_bhrow = false;
         if (cells > c.cap) throw Error(PD_ERR_CUDA, "cell count unstable between passes");
@@ -758,11 +910,11 @@ void Index::genome_edges(uint32_t genome, pd_edges* out) {
         // ---- the Java host's filter over the cells, on the device (Pangenes.java:98-176)
         uint64_t edges = 0;
         if (cells) {
-            c.d_flag.ensure(cells);
+            c.d_flag.ensure(c.cap);
             c.d_imax.ensure(std::max<size_t>(G, 1));
-            c.d_rowthr.ensure(std::max<size_t>(rows, 1));
-            if (c.edge_cap == 0) {
-                c.edge_cap = std::max<uint64_t>(1u << 14, (uint64_t)rows * 4);
+            c.d_rowthr.grow(std::max<size_t>(rows, 1));
+            if (c.edge_cap < c.cap) {  // edges <= cells <= cap: sized with the cell arrays, the retry below never runs
+                c.edge_cap = c.cap;
                 c.d_esrc.alloc(c.edge_cap); c.d_edst.alloc(c.edge_cap); c.d_escore.alloc(c.edge_cap);
             }
             fk::FilterArgs fa;
@@ -773,18 +925,17 @@ void Index::genome_edges(uint32_t genome, pd_edges* out) {
             fa.bh = c.d_bh.p; fa.colmax = c.d_colmax.p; fa.local_of = d_local_of.p;
             fa.imax = c.d_imax.p; fa.rowthr = c.d_rowthr.p; fa.flag = c.d_flag.p;
             fa.n_edges = c.d_counters.p + 6;
-            rt::zero(c.d_imax.p, sizeof(uint32_t) * G, c.st);
-            rt::fill_byte(c.d_rowthr.p, 0, sizeof(uint32_t) * rows, c.st);
+            zero_words(c.d_imax.p, sizeof(uint32_t) * G, c.st);
             PD_LAUNCH(fill_u32_kernel, blocks_for(rows), 256, 0, c.st, c.d_rowthr.p, rows, 0x7F800000u);  // +inf
             PD_LAUNCH(fk::inter_mark_kernel, blocks_for(cells), 256, 0, c.st, fa);
             PD_LAUNCH(fk::row_threshold_kernel, blocks_for(cells), 256, 0, c.st, fa);
             for (int attempt = 0; attempt < 2; attempt++) {
                 fa.e_src = c.d_esrc.p; fa.e_dst = c.d_edst.p; fa.e_score = c.d_escore.p;
                 fa.edge_cap = c.edge_cap;
-                rt::zero(c.d_counters.p + 6, sizeof(unsigned long long), c.st);
+                zero_words(c.d_counters.p + 6, sizeof(unsigned long long), c.st);
                 PD_LAUNCH(fk::edge_emit_kernel, blocks_for(cells), 256, 0, c.st, fa);
-                rt::d2h(c.h_counters.p + 6, c.d_counters.p + 6, sizeof(unsigned long long), c.st);
-                rt::sync(c.st);
+                publish(c, 6, 1);
+                wait(c);
                 edges = c.h_counters.p[6];
                 if (edges <= c.edge_cap) break;
                 c.edge_cap = edges + edges / 8;
@@ -792,13 +943,17 @@ void Index::genome_edges(uint32_t genome, pd_edges* out) {
             }
             c.stats.launches += 5;
         }
+        compute.unlock();
+        StageLock copy(copy_token, stage_tokens & 2);
         const size_t ne = std::max<uint64_t>(edges, 1);
-        c.h_esrc.ensure(ne); c.h_edst.ensure(ne); c.h_escore.ensure(ne);
+        c.h_esrc.grow(ne); c.h_edst.grow(ne); c.h_escore.grow(ne);
         rt::d2h(c.h_esrc.p, c.d_esrc.p, sizeof(uint32_t) * edges, c.st);
         rt::d2h(c.h_edst.p, c.d_edst.p, sizeof(uint32_t) * edges, c.st);
         rt::d2h(c.h_escore.p, c.d_escore.p, sizeof(float) * edges, c.st);
         rt::event_record(c.ev_call1, c.st);
-        rt::sync(c.st);
+        publish(c, 0, 0);
+        wait(c);
+        copy.unlock();
         rt::collect();
         c.stats.total_ms = rt::event_ms(c.ev_call0, c.ev_call1);
         c.stats.rows = rows;
@@ -836,7 +991,7 @@ void Index::score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_
         }
         if (c.cap == 0) c.ensure_cells(opt.cell_capacity ? opt.cell_capacity : std::max<uint64_t>(1u << 20, (uint64_t)rows_per_launch * 1024));
         rt::event_record(c.ev_call0, c.st);
-        rt::zero(bh, sizeof(uint32_t) * (size_t)total_rows * G, c.st);
+        zero_words(bh, sizeof(uint32_t) * (size_t)total_rows * G, c.st);
         for (uint32_t b0 = row_begin; b0 < row_end; b0 += rows_per_launch) {
             const uint32_t n = std::min(rows_per_launch, row_end - b0);
             uint64_t lookups = 0, pairs = 0, cells = 0, fwd_entries = 0;

@@ -51,6 +51,13 @@ struct Index {
     // contexts
     std::mutex mu;
     std::condition_variable cv;
+    // Stage tokens of the per-genome calls.  Concurrent calls share the device-to-host copy engine by time slicing, so
+    // calls that start copying together also finish together and the host gets every result late; the copy token makes
+    // the copy stage first-come-first-served, and while one call sends its arrays the others compute.  The compute
+    // token (off by default) does the same for the kernels; measured slower, because kernels of different calls fill
+    // each other's tails.
+    std::mutex compute_token, copy_token;
+    int stage_tokens = 2;  // bit 0: compute stage, bit 1: copy stage (PD_STAGE_TOKENS)
     std::vector<ScoreContext*> free_ctx;
     std::vector<ScoreContext*> all_ctx;
 

@@ -209,6 +209,13 @@ inline void hfree(void* p) {
 inline stream_t stream_create() { stream_t s; PD_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return s; }
 inline void stream_destroy(stream_t s) { cudaStreamDestroy(s); }
 inline void sync(stream_t s) { PD_CUDA(cudaStreamSynchronize(s)); }
+// non-blocking: true when everything queued on the stream has finished; throws on a failed stream
+inline bool stream_idle(stream_t s) {
+    const cudaError_t e = cudaStreamQuery(s);
+    if (e == cudaErrorNotReady) return false;
+    PD_CUDA(e);
+    return true;
+}
 inline void h2d(void* d, const void* h, size_t n, stream_t s) { if (n) PD_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
 inline void d2h(void* h, const void* d, size_t n, stream_t s) { if (n) PD_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
 inline void d2d(void* dst, const void* src, size_t n, stream_t s) { if (n) PD_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s)); }
@@ -224,7 +231,16 @@ inline void check_launch(const char* what) {
 }
 template <class K>
 inline void allow_smem(K kern, size_t bytes) {
-    if (bytes > 48 * 1024) PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    if (bytes <= 48 * 1024) return;
+    // once per (kernel, device): cudaFuncSetAttribute stalls for milliseconds when other host threads have work in flight
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> done;
+    const std::pair<const void*, int> key(reinterpret_cast<const void*>(kern), current_device());
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& have = done[key];
+    if (have >= bytes) return;
+    PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    have = bytes;
 }
 template <class K>
 inline int occupancy(K kern, int threads, size_t smem) {
@@ -264,6 +280,7 @@ inline void hfree(void* p) { free(p); }
 inline stream_t stream_create() { return 0; }
 inline void stream_destroy(stream_t) {}
 inline void sync(stream_t) {}
+inline bool stream_idle(stream_t) { return true; }
 inline void h2d(void* d, const void* h, size_t n, stream_t) { if (n) memcpy(d, h, n); }
 inline void d2h(void* h, const void* d, size_t n, stream_t) { if (n) memcpy(h, d, n); }
 inline void d2d(void* dst, const void* src, size_t n, stream_t) { if (n) memmove(dst, src, n); }
@@ -310,6 +327,9 @@ struct DevBuf {
     ~DevBuf() { release(); }
     void alloc(size_t count) { release(); p = static_cast<T*>(dmalloc(count * sizeof(T))); n = count; }
     void ensure(size_t count) { if (count > n) alloc(count); }
+    // per-call buffers whose size follows the input: grow with headroom so that a run of slightly larger calls does
+    // not reallocate (a reallocation costs a cudaMalloc and, through collect(), a device-wide synchronisation)
+    void grow(size_t count) { if (count > n) alloc(count + count / 4); }
     void release() { if (p) dfree(p); p = nullptr; n = 0; }
     size_t bytes() const { return n * sizeof(T); }
 };
@@ -325,6 +345,7 @@ struct PinBuf {
     void ensure(size_t count) {
         if (count > n) { release(); p = static_cast<T*>(hmalloc(count * sizeof(T))); n = count; }
     }
+    void grow(size_t count) { if (count > n) ensure(count + count / 4); }
     void release() { if (p) hfree(p); p = nullptr; n = 0; }
 };
 

@@ -69,6 +69,7 @@ struct ScoreArgs {
     uint32_t n_rows;
     const uint32_t* n_rows_dev;  // non-null: rows per level live on the device (row_keys_kernel); this launch takes
     uint32_t level;              // the rows of level `level`: [sum of the counts before it, + n_rows_dev[level])
+    const unsigned long long* n_rows_ovf;  // non-null (retry launch): the row count is the overflow counter of the launches before
     uint32_t* cursor;
     // parameters
     uint32_t G;
@@ -661,6 +662,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
         n_rows = a.n_rows_dev[a.level];
         for (uint32_t l = 0; l < a.level; l++) row0 += a.n_rows_dev[l];
     }
+    if (a.n_rows_ovf) n_rows = (uint32_t)*a.n_rows_ovf;
     const uint4* rows4 = reinterpret_cast<const uint4*>(a.rows + row0);
     uint32_t idx_next = 0;  // thread 0: row claimed for the iteration after this one
     if (tid == 0) {

@@ -113,6 +113,7 @@ inline void __syncthreads() { cuemu::barrier_wait(cuemu::st().block_bar); }
 inline void __syncwarp(unsigned = 0xffffffffu) { cuemu::barrier_wait(cuemu::cur_warp().bar); }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
+inline void __threadfence_system() {}
 
 // Only full-mask, convergent use is supported (what the kernels are written to).
 template <class T>
