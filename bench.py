@@ -328,7 +328,7 @@ def main():
 
         def one_genome(pn, g):
             stt, rel = pn.compute_scores_raw(g)
-            nbytes = 28 * stt.scoresCount + 4 * stt.rows * stt.G + 4 * stt.S  # seven cell arrays, best-hit table, colmax
+            nbytes = 24 * stt.scoresCount + 4 * stt.rows * stt.G + 4 * stt.S  # six cell arrays (first_seq_genome is host-filled), best-hit table, colmax
             ss = native.ScoreStats()
             pn._L.pd_last_score_stats(stt, ss)
             rel()

@@ -11,6 +11,9 @@
 #include <cstdio>
 #include <map>
 #include <thread>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "filter_kernels.cuh"
 #include "index_kernels.cuh"
@@ -78,6 +81,7 @@ struct ScoreContext {
     bool g1_bhrow = false;
     rt::DevBuf<uint64_t> d_rowkeys;
     uint32_t xtab_ctas = 0;
+    uint32_t dense_S = 0;  // gene count the dense accumulators are laid out (and clean) for
     rt::PinBuf<unsigned long long> h_counters;
     rt::PinBuf<sk::RowDesc> h_rows;
     rt::PinBuf<float> h_score, h_perc, h_trperc, h_bh, h_colmax;
@@ -123,6 +127,25 @@ struct ScoreContext {
 };
 
 // PD_TRACE=1: host wall-clock per phase of the per-genome calls, summed over calls and printed when the index dies
+// fills a pinned result array from the host with streaming stores (no read-for-ownership of lines that are only written)
+static void fill_i32_stream(int32_t* p, uint64_t n, int32_t v) {
+#if defined(__SSE2__) && !defined(PD_EMU)
+    uint64_t i = 0;
+    while (i < n && (reinterpret_cast<uintptr_t>(p + i) & 15u)) p[i++] = v;
+    const __m128i vv = _mm_set1_epi32(v);
+    for (; i + 16 <= n; i += 16) {
+        _mm_stream_si128(reinterpret_cast<__m128i*>(p + i), vv);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(p + i + 4), vv);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(p + i + 8), vv);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(p + i + 12), vv);
+    }
+    _mm_sfence();
+    for (; i < n; i++) p[i] = v;
+#else
+    std::fill(p, p + n, v);
+#endif
+}
+
 // takes a stage token unless the stage is switched off
 struct StageLock {
     std::unique_lock<std::mutex> lk;
@@ -157,9 +180,37 @@ static void report() {
 }
 }  // namespace trace
 
+// Score contexts (stream, events, per-call device and pinned result buffers) hold nothing of the index they serve, so
+// they outlive it: a dying index parks its contexts here and the next index on that device takes them over with their
+// buffers already grown.  Without this every new index pays the cudaMalloc / cudaMallocHost warm-up of its first calls
+// again (measured: hundreds of milliseconds over the first few hundred calls).  Parked contexts are never destroyed at
+// process exit: the CUDA runtime may be gone by then.
+namespace {
+struct ContextPool {
+    std::mutex mu;
+    std::vector<ScoreContext*> parked[16];
+};
+ContextPool& context_pool() {
+    static ContextPool* p = new ContextPool;
+    return *p;
+}
+const size_t kParkedPerDevice = 8;
+}  // namespace
+
 Index::~Index() {
     trace::report();
-    for (ScoreContext* c : all_ctx) delete c;
+    ContextPool& pool = context_pool();
+    for (ScoreContext* c : all_ctx) {
+        c->ix = nullptr;
+        std::unique_lock<std::mutex> lk(pool.mu);
+        std::vector<ScoreContext*>& v = pool.parked[device & 15];
+        if (v.size() < kParkedPerDevice) {
+            v.push_back(c);
+        } else {
+            lk.unlock();
+            delete c;
+        }
+    }
 }
 
 ScoreContext* Index::acquire() {
@@ -172,7 +223,18 @@ ScoreContext* Index::acquire() {
             return c;
         }
         if (all_ctx.size() < limit) {
-            ScoreContext* c = new ScoreContext(this);
+            ScoreContext* c = nullptr;
+            {
+                ContextPool& pool = context_pool();
+                std::lock_guard<std::mutex> pk(pool.mu);
+                std::vector<ScoreContext*>& v = pool.parked[device & 15];
+                if (!v.empty()) {
+                    c = v.back();
+                    v.pop_back();
+                }
+            }
+            if (c) c->ix = this;
+            else c = new ScoreContext(this);
             all_ctx.push_back(c);
             return c;
         }
@@ -768,9 +830,10 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
     if (const uint32_t nr = (uint32_t)c.h_counters.p[3]) {
         const unsigned grid = std::min<unsigned>(nr, 32);
         const size_t words = (size_t)grid * 4 * ix.info.S;
-        if (c.d_dense.n < words) {
-            c.d_dense.alloc(words);
-            zero_words(c.d_dense.p, words * sizeof(uint32_t), c.st);
+        if (c.d_dense.n < words || c.dense_S != ix.info.S) {  // the per-CTA layout follows S: a context taken over from an
+            if (c.d_dense.n < words) c.d_dense.alloc(words);  // index of another size holds stale `touched` lists in it
+            zero_words(c.d_dense.p, c.d_dense.n * sizeof(uint32_t), c.st);
+            c.dense_S = ix.info.S;
         }
         sk::ScoreArgs b2 = a;
         b2.rows = c.d_ovf.p + n;
@@ -839,16 +902,20 @@ void Index::compute_scores(uint32_t genome, pd_scores* out) {
         rt::d2h(c.h_trperc.p, c.d_trperc.p, sizeof(float) * cells, c.st);
         rt::d2h(c.h_row.p, c.d_row.p, sizeof(int32_t) * cells, c.st);
         rt::d2h(c.h_col.p, c.d_col.p, sizeof(int32_t) * cells, c.st);
-        rt::d2h(c.h_g1.p, c.d_g1.p, sizeof(int32_t) * cells, c.st);
+        static const bool host_g1 = getenv("PD_HOST_G1") ? atoi(getenv("PD_HOST_G1")) != 0 : true;
+        if (!host_g1) rt::d2h(c.h_g1.p, c.d_g1.p, sizeof(int32_t) * cells, c.st);
         rt::d2h(c.h_g2.p, c.d_g2.p, sizeof(int32_t) * cells, c.st);
         rt::d2h(c.h_bh.p, c.d_bh.p, sizeof(float) * (size_t)rows * G, c.st);
         rt::d2h(c.h_colmax.p, c.d_colmax.p, sizeof(float) * S, c.st);
         rt::event_record(c.ev_call1, c.st);
-        // this genome's rows in flat_map while the copies run; release() puts INT32_MAX back
+        publish(c, 0, 0);
+        // while the copies run: first_seq_genome is the genome of the cell's row (library.cpp:571-572), i.e. the call's
+        // genome in every cell: written here instead of crossing PCIe (one seventh of the cell bytes); and this
+        // genome's rows go into flat_map (release() puts INT32_MAX back)
+        if (host_g1) fill_i32_stream(c.h_g1.p, cells, (int32_t)genome);
         for (uint32_t i = 0; i < rows; i++) c.h_map.p[genome_rows[r0 + i]] = (int32_t)i;
         c.map_r0 = r0;
         c.map_rows = rows;
-        publish(c, 0, 0);
         tc.lap(trace::kCopyEnqueue);
         wait(c);
         copy.unlock();

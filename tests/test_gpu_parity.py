@@ -87,6 +87,16 @@ def test_overflow_levels_and_dense_path(monkeypatch):
     assert st["fallback_rows"] > 0
 
 
+def test_contexts_taken_over_by_indices_of_other_sizes(monkeypatch):
+    """Score contexts (result buffers, dense accumulators, side tables) are parked when an index dies and taken over by
+    the next one: a larger index, then a smaller one, then a larger one again, each through the dense fallback."""
+    monkeypatch.setenv("PD_SMEM_TOP", "2048")
+    for genes, seed in ((300, 71), (90, 72), (400, 73), (90, 74)):
+        w = synth.generate(5, genes, 150.0, 0.1, seed, low_complexity=0.3)
+        st = check_workload(w, 4, hash_log2=6, index=False)
+        assert st["fallback_rows"] > 0
+
+
 def test_cell_buffer_regrow_and_concurrent_calls():
     import threading
     w = synth.generate(6, 200, 150.0, 0.1, 64)
