@@ -6,6 +6,7 @@
 * libnative.so          drop-in for the reference's JNI library (loads under System.loadLibrary("native")); needs
                         JNI headers: $JAVA_HOME/include, else the reference's vendored copy by include path
 * pangenes              native CLI with the reference's Pangenes flags
+* calculate_k           native drop-in for the reference's calculate_k.py (CPU only)
 * libpdsynth.so         synthetic workload generator
 """
 import os
@@ -25,6 +26,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 ENGINE_LIB = os.path.join(HERE, "libpandelos_b200.so")
 JNI_LIB = os.path.join(HERE, "libnative.so")
 CLI_BIN = os.path.join(HERE, "pangenes")
+CALCK_BIN = os.path.join(HERE, "calculate_k")
 SYNTH_LIB = os.path.join(HERE, "libpdsynth.so")
 
 
@@ -99,15 +101,19 @@ def build_jni(force=False):
 
 
 def build_host(force=False):
+    """The native hosts: `pangenes` (links the engine) and `calculate_k` (CPU only, no engine)."""
     build_engine(force=False)
     hdir = os.path.join(CSRC, "host")
     if not os.path.isdir(hdir):
         return None
-    srcs = [os.path.join(hdir, f) for f in sorted(os.listdir(hdir)) if f.endswith(".cpp")]
-    if force or _stale(CLI_BIN, srcs + _sources(hdir, INCLUDE) + [ENGINE_LIB]):
-        cmd = [CXX, "-std=c++17", "-O2", "-Wall", "-I", INCLUDE, "-I", hdir, "-o", CLI_BIN] + srcs + \
-              ["-L", HERE, "-lpandelos_b200", "-Wl,-rpath,$ORIGIN", "-pthread"]
-        _run(cmd)
+    headers = _sources(hdir, INCLUDE, exts=(".h", ".hpp"))
+    src = os.path.join(hdir, "pangenes_main.cpp")
+    if force or _stale(CLI_BIN, [src] + headers + [ENGINE_LIB]):
+        _run([CXX, "-std=c++17", "-O2", "-Wall", "-I", INCLUDE, "-I", hdir, "-o", CLI_BIN, src,
+              "-L", HERE, "-lpandelos_b200", "-Wl,-rpath,$ORIGIN", "-pthread"])
+    src = os.path.join(hdir, "calculate_k_main.cpp")
+    if force or _stale(CALCK_BIN, [src] + headers):
+        _run([CXX, "-std=c++17", "-O2", "-Wall", "-I", hdir, "-o", CALCK_BIN, src])
     return CLI_BIN
 
 

@@ -17,22 +17,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <fstream>
 #include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
 
+#include "faa.h"
 #include "pandelos_b200.h"
 
 namespace {
-
-std::string trim(const std::string& s) {  // String.trim(): code points <= U+0020 off both ends
-    size_t a = 0, b = s.size();
-    while (a < b && (unsigned char)s[a] <= 0x20) a++;
-    while (b > a && (unsigned char)s[b - 1] <= 0x20) b--;
-    return s.substr(a, b - a);
-}
 
 // Double.toString(d) for finite d > 0 (JDK 19+: shortest decimal that round-trips; decimal notation for
 // 1e-3 <= d < 1e7, otherwise computerized scientific notation)
@@ -108,38 +101,43 @@ int main(int argc, char** argv) {
         return 2;
     }
 
-    // ---- PangeneIData.readFromFile
-    std::ifstream f(in);
-    if (!f) {
+    // ---- PangeneIData.readFromFile (PangeneIData.java:30-75) over the mapped file: no per-line strings for the sequences
+    pd_host::MappedFile f(in);
+    if (!f.ok()) {
         fprintf(stderr, "cannot read %s\n", in.c_str());
         return 1;
     }
     std::vector<uint8_t> residues;
+    residues.reserve(f.size());
     std::vector<uint64_t> offsets(1, 0);
     std::vector<uint32_t> genome_of;
     std::unordered_map<std::string, uint32_t> genome_id;
-    std::string line, genome_name;
+    std::string genome_name, bad_header;
     bool name_line = true;
-    while (std::getline(f, line)) {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        const std::string t = trim(line);
-        if (t.empty()) continue;
+    pd_host::for_each_line(f.data(), f.size(), [&](size_t, const char* b, const char* e) {
+        while (b < e && (unsigned char)*b <= 0x20) b++;  // String.trim(): code points <= U+0020 off both ends
+        while (e > b && (unsigned char)e[-1] <= 0x20) e--;
+        if (b == e || !bad_header.empty()) return;  // blank lines are skipped
         if (name_line) {
-            const size_t tab = t.find('\t');
-            genome_name = t.substr(0, tab);
-            if (tab == std::string::npos || t.find('\t', tab + 1) == std::string::npos) {
-                // the reference indexes cc[1], cc[2]: a header with fewer than three fields is an error there too
-                fprintf(stderr, "malformed header line (need genome<TAB>gene<TAB>product): %s\n", t.c_str());
-                return 1;
+            const char* tab = static_cast<const char*>(memchr(b, '\t', (size_t)(e - b)));
+            // the reference indexes cc[1], cc[2]: a header with fewer than three fields is an error there too
+            if (!tab || !memchr(tab + 1, '\t', (size_t)(e - tab - 1))) {
+                bad_header.assign(b, e);
+                return;
             }
+            genome_name.assign(b, tab);
         } else {
-            residues.insert(residues.end(), t.begin(), t.end());
+            residues.insert(residues.end(), reinterpret_cast<const uint8_t*>(b), reinterpret_cast<const uint8_t*>(e));
             offsets.push_back(residues.size());
             auto it = genome_id.find(genome_name);
             if (it == genome_id.end()) it = genome_id.emplace(genome_name, (uint32_t)genome_id.size()).first;
             genome_of.push_back(it->second);
         }
         name_line = !name_line;
+    });
+    if (!bad_header.empty()) {
+        fprintf(stderr, "malformed header line (need genome<TAB>gene<TAB>product): %s\n", bad_header.c_str());
+        return 1;
     }
     const uint32_t S = (uint32_t)genome_of.size();
 
