@@ -655,7 +655,7 @@ inline void levels_of(const Index& ix, Level lv[kLevels]) {
     lv[0] = {512, 9, 128, 256, 256};
     lv[1] = {2048, 11, 256, 512, 1536};
     lv[2] = {4096, 11, 512, 1024, ~0ull};
-    lv[3] = {2048, 14, 512, 1024, 0};
+    lv[3] = {2048, 14, 1024, 1024, 0};  // few, heavy rows, one CTA per SM: twice the warps per row shortens the tail
     if (const char* e = getenv("PD_LEVELS")) {  // tuning: "t1:hbits:threads:fcap:maxcols,..." for the four levels
         unsigned t1, h, t, f;
         unsigned long long m;
@@ -674,7 +674,7 @@ inline void levels_of(const Index& ix, Level lv[kLevels]) {
         lv[0] = {t1, hb, 128, 256, 0};   // unused
         lv[1] = {t1, hb, 128, 256, 0};   // unused
         lv[2] = {t1, hb, hb >= 12 ? 256 : 128, 256, ~0ull};
-        lv[3] = {2048, std::max<uint32_t>(hb, 14), 512, 1024, 0};
+        lv[3] = {2048, std::max<uint32_t>(hb, 14), 1024, 1024, 0};
     }
     if (const char* e = getenv("PD_SMEM_TOP")) {  // tests: shrink the retry table to force the dense path
         const size_t v = (size_t)atoll(e);
@@ -736,8 +736,11 @@ void launch_rows(ScoreContext& c, sk::ScoreArgs a, const Level& lv, int cursor_i
 
 // Scores the `n` rows gene(i) = genes[i] (device array) or gene_base + i; row i writes best hits to row i of d_bh.
 // Returns the number of non-zero cells; cells beyond c.cap are counted but not stored (caller grows and re-runs).
+// by_cost: order the rows of a level by descending posting-list volume instead of by family.  Family order makes
+// neighbouring rows share posting lists in L2 and is what a block of many genomes wants; the rows of ONE genome belong
+// to different families, so there a per-genome call starts its heaviest rows first and shortens the tail of the launch.
 static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, uint32_t gene_base, uint32_t* d_bh, uint32_t* d_colmax,
-                         uint64_t* pairs, uint64_t* lookups, uint64_t* fwd_entries) {
+                         uint64_t* pairs, uint64_t* lookups, uint64_t* fwd_entries, bool by_cost) {
     Index& ix = *c.ix;
     trace::Clock tc;
     Level lv[kLevels];
@@ -771,6 +774,10 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
     for (int l = 0; l < 3; l++) ca.max_cols[l] = lv[l].max_cols;
     ca.counts = c.d_cursors.p + 8;  // [8..10]
     ca.stats = c.d_counters.p + 4;  // [4], [5]
+    {
+        static const char* const order = getenv("PD_ROW_ORDER");  // tuning: "family" | "cost"
+        ca.by_cost = order ? (strcmp(order, "cost") == 0) : by_cost;
+    }
     c.d_rowkeys.grow((size_t)2 * n);
     c.d_sorttmp.grow(prims::radix_tmp_words(n) + 16);
     tc.lap(trace::kGrow);
@@ -879,7 +886,7 @@ void Index::compute_scores(uint32_t genome, pd_scores* out) {
         for (int attempt = 0; attempt < 3; attempt++) {
             zero_words(c.d_bh.p, sizeof(uint32_t) * (size_t)rows * G, c.st);
             zero_words(c.d_colmax.p, sizeof(uint32_t) * S, c.st);
-            cells = rows ? run_rows(c, rows, d_genome_rows.p + r0, 0, c.d_bh.p, c.d_colmax.p, &pairs, &lookups, &fwd_entries) : 0;
+            cells = rows ? run_rows(c, rows, d_genome_rows.p + r0, 0, c.d_bh.p, c.d_colmax.p, &pairs, &lookups, &fwd_entries, true) : 0;
             if (cells <= c.cap) break;
             c.ensure_cells(cells + cells / 2);
         }
@@ -967,7 +974,7 @@ void Index::genome_edges(uint32_t genome, pd_edges* out) {
         for (int attempt = 0; attempt < 3; attempt++) {
             zero_words(c.d_bh.p, sizeof(uint32_t) * (size_t)rows * G, c.st);
             zero_words(c.d_colmax.p, sizeof(uint32_t) * S, c.st);
-            cells = rows ? run_rows(c, rows, d_genome_rows.p + r0, 0, c.d_bh.p, c.d_colmax.p, &pairs, &lookups, &fwd_entries) : 0;
+            cells = rows ? run_rows(c, rows, d_genome_rows.p + r0, 0, c.d_bh.p, c.d_colmax.p, &pairs, &lookups, &fwd_entries, true) : 0;
             if (cells <= c.cap) break;
             c.ensure_cells(cells + cells / 2);
         }
@@ -1064,7 +1071,7 @@ void Index::score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_
             uint64_t lookups = 0, pairs = 0, cells = 0, fwd_entries = 0;
             uint32_t* bh_blk = bh + (size_t)(b0 - row_begin) * G;
             for (int attempt = 0; attempt < 3; attempt++) {
-                cells = run_rows(c, n, nullptr, b0, bh_blk, nullptr, &pairs, &lookups, &fwd_entries);
+                cells = run_rows(c, n, nullptr, b0, bh_blk, nullptr, &pairs, &lookups, &fwd_entries, false);
                 if (cells <= c.cap) break;
                 c.ensure_cells(cells + cells / 8);
             }

@@ -965,6 +965,7 @@ struct ClassifyArgs {
     uint32_t cls_bits;
     const uint2* meta;
     unsigned long long max_cols[3];
+    uint32_t by_cost;                // non-zero: inside a level, heaviest rows first instead of family order (see run_rows)
     uint32_t* counts;                // [3] rows per level
     unsigned long long* stats;       // [0] += postings the rows visit, [1] += their forward entries
 };
@@ -977,7 +978,9 @@ __global__ void __launch_bounds__(256) row_keys_kernel(ClassifyArgs a, uint64_t*
         const unsigned long long v = a.visited[g];
         const unsigned long long cols = v < a.S ? v : a.S;
         const unsigned long long level = cols <= a.max_cols[0] ? 0 : (cols <= a.max_cols[1] ? 1 : 2);
-        keys[i] = (level << 62) | ((unsigned long long)(a.fam_key[g] & 0x7FFFFFFFu) << 31) | i;
+        const unsigned long long mid = a.by_cost ? 0x7FFFFFFFull - (v < 0x7FFFFFFFull ? v : 0x7FFFFFFFull)
+                                                 : (unsigned long long)(a.fam_key[g] & 0x7FFFFFFFu);
+        keys[i] = (level << 62) | (mid << 31) | i;
         atomicAdd(&a.counts[level], 1u);
         lk = v;
         fe = a.fwd_ptr[g + 1] - a.fwd_ptr[g];
