@@ -154,9 +154,9 @@ struct StageLock {
 };
 
 namespace trace {
-enum { kAcquire, kPre, kZ, kGrow, kKeys, kRadix, kSortLaunch, kLaunch, kLevelsWait, kRetryWait, kTokenWait, kCopyEnqueue, kCopyWait, kTail, kCalls, kN };
+enum { kAcquire, kSortLaunch, kLaunch, kLevelsWait, kRetryWait, kTokenWait, kCopyEnqueue, kCopyWait, kTail, kCalls, kN };
 static std::atomic<uint64_t> ns[kN];
-static const char* const names[kN] = {"acquire", "pre", "zero", "grow", "keys", "radix", "sort_launch", "launch", "levels_wait", "retry_wait", "token_wait", "copy_enqueue", "copy_wait", "tail", "calls"};
+static const char* const names[kN] = {"acquire", "sort_launch", "launch", "levels_wait", "retry_wait", "token_wait", "copy_enqueue", "copy_wait", "tail", "calls"};
 static bool on() {
     static const bool v = getenv("PD_TRACE") != nullptr;
     return v;
@@ -751,10 +751,8 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
         PD_LAUNCH(xtab_init_kernel, (unsigned)ix.sms * 4, 256, 0, c.st, c.d_xtab.p, want_ctas);
         c.xtab_ctas = want_ctas;
     }
-    tc.lap(trace::kPre);
     zero_words(c.d_counters.p, 8 * sizeof(unsigned long long), c.st);
     zero_words(c.d_cursors.p, 16 * sizeof(uint32_t), c.st);
-    tc.lap(trace::kZ);
     c.d_rows.grow(n);
     c.d_ovf.grow((size_t)2 * n);
 
@@ -780,12 +778,9 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
     }
     c.d_rowkeys.grow((size_t)2 * n);
     c.d_sorttmp.grow(prims::radix_tmp_words(n) + 16);
-    tc.lap(trace::kGrow);
     PD_LAUNCH(sk::row_keys_kernel, blocks_for(n), 256, 0, c.st, ca, c.d_rowkeys.p);
-    tc.lap(trace::kKeys);
     uint64_t nl = 0;
     const uint64_t* sorted_keys = prims::radix_sort_u64(c.d_rowkeys.p, c.d_rowkeys.p + n, n, 31, 64, c.d_sorttmp.p, c.st, &nl);
-    tc.lap(trace::kRadix);
     PD_LAUNCH(sk::row_desc_kernel, blocks_for(n), 256, 0, c.st, ca, sorted_keys, c.d_rows.p);
     c.stats.launches += 2 + nl;
     tc.lap(trace::kSortLaunch);

@@ -12,12 +12,12 @@
 //                    per undirected edge with src <= dst, score = the float widened to double and printed the way
 //                    Java's Double.toString prints it.  Line ORDER: the reference iterates a HashMap; here lines are
 //                    sorted by (src, dst) — netclu_ng.py reads the file into a graph, the order carries no meaning.
+#include <algorithm>
 #include <charconv>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -161,9 +161,17 @@ int main(int argc, char** argv) {
     pd_index_info info;
     pd_info(ix, &info);
 
-    // ---- Pangenes.java:60-183, one task per genome; PangeneNet.addConnection
-    std::map<uint64_t, float> net;  // (src << 32 | dst) -> score, first score wins
-    auto add = [&](uint32_t src, uint32_t dst, float score) { net.emplace(((uint64_t)src << 32) | dst, score); };
+    // ---- Pangenes.java:60-183, one task per genome; PangeneNet.addConnection keeps the FIRST score of a directed
+    // (src, dest) pair (PangeneNet.java:49-62) and saveToFile(file, false) prints the pairs with src <= dest.  An
+    // inter-genome edge is added in both directions at once (Pangenes.java:103-104), so the printed pair (min, max) gets
+    // its score from the first task that reports the edge in either direction: edges are collected once, as
+    // (min << 32 | max, score) in task order, then stable-sorted and the first of every key kept.  (The reference's
+    // HashMap of boxed pairs does not survive 10^8 edges; 16 bytes per reported edge do.)
+    struct Edge {
+        uint64_t key;
+        float score;
+    };
+    std::vector<Edge> net;
     for (uint32_t g = 0; g < info.G; g++) {
         printf("Working on genome %u/%u\n", g, info.G);
         pd_edges e;
@@ -172,13 +180,16 @@ int main(int argc, char** argv) {
             return 1;
         }
         printf("Filtered count: %llu\n", (unsigned long long)e.cells);
+        net.reserve(net.size() + e.count);
         for (uint64_t i = 0; i < e.count; i++) {
-            add(e.src[i], e.dst[i], e.score[i]);
-            if (genome_of[e.src[i]] != genome_of[e.dst[i]]) add(e.dst[i], e.src[i], e.score[i]);  // Pangenes.java:103-104
+            const uint32_t a = e.src[i], b = e.dst[i];
+            // an intra-genome edge is added as (src, dest) only (Pangenes.java:171); it is reported with src < dest
+            net.push_back(Edge{a <= b ? ((uint64_t)a << 32) | b : ((uint64_t)b << 32) | a, e.score[i]});
         }
         pd_edges_release(ix, &e);
     }
     pd_free(ix);
+    std::stable_sort(net.begin(), net.end(), [](const Edge& x, const Edge& y) { return x.key < y.key; });
 
     // ---- PangeneNet.saveToFile(file, false)
     FILE* o = fopen(out.c_str(), "w");
@@ -186,13 +197,14 @@ int main(int argc, char** argv) {
         fprintf(stderr, "cannot write %s\n", out.c_str());
         return 1;
     }
+    std::vector<char> obuf(1 << 22);
+    setvbuf(o, obuf.data(), _IOFBF, obuf.size());
     uint64_t lines = 0;
-    for (const auto& kv : net) {
-        const uint32_t src = (uint32_t)(kv.first >> 32), dst = (uint32_t)kv.first;
-        if (src <= dst) {
-            fprintf(o, "%u\t%u\t%s\n", src, dst, java_double_to_string((double)kv.second).c_str());
-            lines++;
-        }
+    for (size_t i = 0; i < net.size(); i++) {
+        if (i && net[i].key == net[i - 1].key) continue;  // a later report of the same pair
+        const uint32_t src = (uint32_t)(net[i].key >> 32), dst = (uint32_t)net[i].key;
+        fprintf(o, "%u\t%u\t%s\n", src, dst, java_double_to_string((double)net[i].score).c_str());
+        lines++;
     }
     fclose(o);
     printf("Network: %llu undirected edges written to %s\n", (unsigned long long)lines, out.c_str());
