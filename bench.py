@@ -311,7 +311,17 @@ def main():
     alg_bytes = 8.0 * stats["lookups"] + 12.0 * stats["fwd_entries"] + 20.0 * stats["cells"] + 4.0 * rows_n * G + 8.0 * info.S
     peak, peak_kind = peaks()
     achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # DRAM traffic of the dominant kernel: one `ncu --set full` capture of its largest launch, committed under profiles/
+    traffic, traffic_launch = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_score_traffic.json")
+    if args.workload == "scaleout1000" and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes"]
+        traffic_launch = {"launch": tj["launch"], "algorithmic_bytes": tj["block_algorithmic_bytes"],
+                          "traffic_over_algorithmic": tj["traffic_over_algorithmic"], "source": tj["source"]}
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_launch": traffic_launch,
                 "bytes_per_lookup_model": 8, "bytes_per_lookup_read": 4,
                 "kernel": "score_rows_kernel", "kernel_ms_per_step": kms, "peak_kind": peak_kind,
                 "lookups_per_s": stats["lookups"] / (kms * 1e-3) if kms > 0 else 0.0}
