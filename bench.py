@@ -38,7 +38,8 @@ QUERY_GENOMES = {"scaleout1000": 125}
 # genomes of the workload the CPU reference is timed on (bounded sample: ~10-30 s of host work)
 CPU_SAMPLE_GENOMES = {"scaleout1000": 48, "mycoplasma64": 64}
 # host threads calling pd_compute_scores in the e2e arm (the Java host uses a thread pool, Pangenes.java:54-66)
-E2E_THREADS = int(os.environ.get("PD_E2E_THREADS", "4"))
+E2E_THREADS = int(os.environ.get("PD_E2E_THREADS", "0")) or max(
+    1, min(4, (os.cpu_count() or 4) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
 
 
 def log(*a):

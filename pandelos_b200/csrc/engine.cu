@@ -612,6 +612,7 @@ static void wait(ScoreContext& c) {
     for (uint32_t spins = 1; *f != c.seq; spins++) {
         for (int i = 0; i < 16; i++) cpu_relax();
         if ((spins & 255u) == 0) {
+            std::this_thread::yield();  // a box with fewer cores than waiting threads must still make progress
             const auto now = std::chrono::steady_clock::now();
             if (now - last > std::chrono::milliseconds(20)) {
                 last = now;
