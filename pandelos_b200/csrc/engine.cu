@@ -516,30 +516,53 @@ void Index::host_mirrors() {
     have_mirrors = true;
 }
 
-// genes of each genome in input order (genome_sequences, library.cpp:245), host and device
+// genes of each genome in input order (genome_sequences, library.cpp:245), host and device.  Made on the device — a
+// stable sort of (genome << 32 | gene) on the genome bits — because the host version (three passes over S genes with
+// scattered writes, after copying the gene table back) cost tens of milliseconds in front of the first computeScores.
+namespace {
+__global__ void __launch_bounds__(256) genome_key_kernel(const uint2* __restrict__ meta, uint32_t S, uint64_t* __restrict__ keys,
+                                                          uint32_t* __restrict__ counts) {
+    const uint32_t s = blockIdx.x * 256u + threadIdx.x;
+    const bool valid = s < S;
+    const uint32_t g = valid ? meta[s].y : 0xFFFFFFFFu;
+    if (valid) keys[s] = ((uint64_t)g << 32) | s;
+    const unsigned peers = __match_any_sync(0xffffffffu, g);  // genes of a genome sit together: one add per run
+    if (valid && (threadIdx.x & 31u) == (unsigned)(__ffs((int)peers) - 1)) atomicAdd(&counts[g], (uint32_t)__popc(peers));
+}
+__global__ void __launch_bounds__(256) genome_rows_kernel(const uint64_t* __restrict__ sorted, uint32_t S, const uint32_t* __restrict__ gptr,
+                                                           uint32_t* __restrict__ rows, uint32_t* __restrict__ local_of) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= S) return;
+    const uint64_t key = sorted[i];
+    const uint32_t s = (uint32_t)key, g = (uint32_t)(key >> 32);
+    rows[i] = s;
+    local_of[s] = i - gptr[g];
+}
+}  // namespace
+
 void Index::genome_lists() {
-    host_mirrors();
     std::lock_guard<std::mutex> lk(mirror_mu);
     if (have_genome_lists) return;
     rt::set_device(device);
     const uint32_t S = info.S, G = info.G;
     genome_ptr.assign((size_t)G + 1, 0);
-    for (uint32_t s = 0; s < S; s++) genome_ptr[genome_of[s] + 1]++;
-    for (uint32_t g = 0; g < G; g++) genome_ptr[g + 1] += genome_ptr[g];
-    genome_rows.assign(S, 0);
-    {
-        std::vector<uint32_t> cur(genome_ptr.begin(), genome_ptr.end() - (G ? 1 : 0));
-        for (uint32_t s = 0; s < S; s++) genome_rows[cur[genome_of[s]]++] = s;
-    }
     d_genome_rows.alloc(std::max<size_t>(S, 1));
     d_local_of.alloc(std::max<size_t>(S, 1));
+    h_genome_rows.ensure(std::max<size_t>(S, 1));
+    genome_rows = h_genome_rows.p;
     if (S) {
-        std::vector<uint32_t> local_of(S);
-        for (uint32_t g = 0; g < G; g++)
-            for (uint32_t i = genome_ptr[g]; i < genome_ptr[g + 1]; i++) local_of[genome_rows[i]] = i - genome_ptr[g];
         rt::stream_t st = rt::stream_create();
-        rt::h2d(d_genome_rows.p, genome_rows.data(), sizeof(uint32_t) * S, st);
-        rt::h2d(d_local_of.p, local_of.data(), sizeof(uint32_t) * S, st);
+        rt::DevBuf<uint64_t> keys((size_t)2 * S);
+        rt::DevBuf<uint32_t> gptr((size_t)G + 1), tmp(prims::radix_tmp_words(S) + prims::scan_tmp_words((uint64_t)G + 1) + 32);
+        rt::zero(gptr.p, sizeof(uint32_t) * ((size_t)G + 1), st);
+        PD_LAUNCH(genome_key_kernel, (S + 255) / 256, 256, 0, st, (const uint2*)meta.p, S, keys.p, gptr.p);
+        prims::exclusive_scan_u32(gptr.p, gptr.p, (uint64_t)G + 1, tmp.p, nullptr, st);
+        int gbits = 1;
+        while (gbits < 32 && (1ull << gbits) < (uint64_t)G) gbits++;
+        const uint64_t* sorted = prims::radix_sort_u64(keys.p, keys.p + S, S, 32, 32 + gbits, tmp.p + prims::scan_tmp_words((uint64_t)G + 1) + 16, st);
+        PD_LAUNCH(genome_rows_kernel, (S + 255) / 256, 256, 0, st, sorted, S, (const uint32_t*)gptr.p, d_genome_rows.p, d_local_of.p);
+        rt::d2h(h_genome_rows.p, d_genome_rows.p, sizeof(uint32_t) * S, st);
+        rt::d2h(genome_ptr.data(), gptr.p, sizeof(uint32_t) * ((size_t)G + 1), st);
         rt::sync(st);
         rt::stream_destroy(st);
     }

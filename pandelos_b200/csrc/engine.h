@@ -44,7 +44,8 @@ struct Index {
     std::vector<uint32_t> genome_of;
     std::vector<uint64_t> visited;
     std::vector<uint32_t> genome_ptr;   // G+1
-    std::vector<uint32_t> genome_rows;  // genes grouped by genome, input order inside (genome_sequences, library.cpp:245)
+    rt::PinBuf<uint32_t> h_genome_rows;
+    const uint32_t* genome_rows = nullptr;  // genes grouped by genome, input order inside (genome_sequences, library.cpp:245)
     void host_mirrors();
     void genome_lists();
 
