@@ -57,22 +57,59 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled during the timed region (B200_PROFILING.md recipe): an `nvidia-smi -lms 100`
+    loop beside the bench (default), or the same counters read through NVML in this process (PD_CLOCKS=nvml, also the
+    fallback's other direction: if nvidia-smi cannot start nothing is sampled); PD_CLOCKS=off disables."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
+        self.mode = os.environ.get("PD_CLOCKS", "smi")
         self.proc = None
-        self.lines = []
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.lines = []      # nvidia-smi csv lines
+        self.samples = []    # (sm_mhz, reasons bitmask) from NVML
+        self.max_mhz = None
+        self.source = None
+
+    def _nvml_loop(self, nv, handle):
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(handle))))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.05)
 
     def start(self):
+        if self.mode == "off":
+            return
+        if self.mode == "nvml":
+            try:
+                import pynvml as nv
+                nv.nvmlInit()
+                # NVML enumerates physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it is a list of indices
+                vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
+                phys = int(vis[self.index]) if self.index < len(vis) else self.index
+                handle = nv.nvmlDeviceGetHandleByIndex(phys)
+                self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+                self._nv = nv
+                self.source = "nvml"
+                self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.source = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
@@ -81,15 +118,24 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.source == "nvml":
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            nv = self._nv
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            reasons = sorted(n for n, b in bits.items() if any(r & b for _, r in self.samples))
+            sm = [m for m, _ in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable" if self.mode != "off" else "clock sampling off"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
@@ -99,10 +145,11 @@ class ClockSampler:
                 mx = float(f[1])
             except ValueError:
                 continue
-            for n, v in zip(names, f[2:6]):
+            for n, v in zip(self.NAMES, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi"}
 
 
 def make_workload(name):
@@ -249,9 +296,14 @@ def main():
     rows_of_rank = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
     bh_local = torch.zeros((max(rows_of_rank), G), dtype=torch.float32, device=dev)  # padded to the largest slice
 
+    host_ms = [0.0, 0.0]  # wall clock of the last step's two calls (log only)
+
     def step():
+        t0 = time.perf_counter()
         pn = native.PangeneNative(k, data, device=local, residues_device_ptr=res_dev.data_ptr())
+        t1 = time.perf_counter()
         st = pn.score_partition_device(row0, row1, best_hit_ptr=bh_local.data_ptr())
+        host_ms[0], host_ms[1] = (t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3
         if world > 1:
             multigpu.allgather_best_hits(dist, bh_local, rows_of_rank, G, dev)
         return pn, st
@@ -287,8 +339,9 @@ def main():
         launches += int(st.launches + pn.info.build_ms[7])
         info = pn.info
         stats = st.as_dict()
-        log("[bench] step %.1f ms (wall %.1f): build %.1f [%s], scoring kernels %.1f, scoring call %.1f" % (
-            ms_steps[-1], wall, pn.info.build_ms[5], " ".join("%.1f" % v for v in pn.info.build_ms[:5]), st.kernel_ms, st.total_ms))
+        log("[bench] step %.1f ms (wall %.1f): build %.1f [%s], scoring kernels %.1f, scoring call %.1f; host wall: build call %.1f, scoring call %.1f" % (
+            ms_steps[-1], wall, pn.info.build_ms[5], " ".join("%.1f" % v for v in pn.info.build_ms[:5]), st.kernel_ms, st.total_ms,
+            host_ms[0], host_ms[1]))
         pn.close()
     clocks = sampler.stop() if rank == 0 else None
     ms = float(np.mean(ms_steps))

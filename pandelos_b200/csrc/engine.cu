@@ -172,7 +172,7 @@ struct Clock {
     }
 };
 static void report() {
-    if (!on() || ns[kCalls] == 0) return;
+    if (!on()) return;
     fprintf(stderr, "[pd trace] %llu calls;", (unsigned long long)ns[kCalls].load());
     for (int i = 0; i < kCalls; i++) fprintf(stderr, " %s %.1f ms;", names[i], (double)ns[i].exchange(0) * 1e-6);
     fprintf(stderr, "\n");
@@ -1070,8 +1070,10 @@ void Index::genome_edges(uint32_t genome, pd_edges* out) {
 void Index::score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_per_launch, float* d_best_hit, pd_score_stats* st_out) {
     if (row_begin > row_end || row_end > info.S) throw Error(PD_ERR_INVALID, "bad row range");
     rt::set_device(device);
+    trace::Clock ta;
     ScoreContext* cp = acquire();
     ScoreContext& c = *cp;
+    ta.lap(trace::kAcquire);
     try {
         memset(&c.stats, 0, sizeof(c.stats));
         const uint32_t G = info.G;
@@ -1102,8 +1104,11 @@ void Index::score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_
             c.stats.cells += cells;
         }
         rt::event_record(c.ev_call1, c.st);
+        trace::Clock tp;
         rt::sync(c.st);
+        tp.lap(trace::kCopyWait);
         rt::collect();
+        tp.lap(trace::kTail);
         c.stats.total_ms = rt::event_ms(c.ev_call0, c.ev_call1);
         if (st_out) *st_out = c.stats;
     } catch (...) {

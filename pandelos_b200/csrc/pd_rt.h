@@ -76,6 +76,7 @@ struct BlockCache {
     std::unordered_map<void*, std::pair<size_t, int>> live;        // block -> (size, device), handed out or queued
     std::vector<void*> pending;                                    // freed, possibly still in use by queued kernels
     size_t cached = 0;
+    size_t keep_limit = 0;                                         // idle bytes kept before trimming (0 = not asked yet)
 };
 inline BlockCache& block_cache(int dev) {
     static BlockCache caches[16];
@@ -111,8 +112,14 @@ inline void collect() {
         c.cached += sz;
     }
     c.pending.clear();
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) trim_cache(c, total_b / 2);
+    // Give memory back only when the idle blocks exceed three quarters of the device (asked once: cudaMemGetInfo and
+    // cudaFree cost milliseconds to tens of milliseconds, and a trimmed block is the next build's cudaMalloc);
+    // an allocation that fails empties the cache anyway (dmalloc).
+    if (c.keep_limit == 0) {
+        size_t free_b = 0, total_b = 0;
+        c.keep_limit = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? total_b / 4 * 3 : ~size_t(0);
+    }
+    if (c.cached > c.keep_limit) trim_cache(c, c.keep_limit);
 }
 inline void* dmalloc(size_t n) {
     n = round_block(n);
