@@ -58,8 +58,8 @@ def peaks():
 
 class ClockSampler:
     """SM clock and throttle reasons sampled during the timed region (B200_PROFILING.md recipe): an `nvidia-smi -lms 100`
-    loop beside the bench (default), or the same counters read through NVML in this process (PD_CLOCKS=nvml, also the
-    fallback's other direction: if nvidia-smi cannot start nothing is sampled); PD_CLOCKS=off disables."""
+    loop beside the bench (default).  PD_CLOCKS=nvml reads the same counters through NVML in this process (falls back to
+    nvidia-smi when the binding is missing); PD_CLOCKS=off disables sampling."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
