@@ -294,18 +294,32 @@ def main():
 
     G = w.G
     rows_of_rank = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
-    bh_local = torch.zeros((max(rows_of_rank), G), dtype=torch.float32, device=dev)  # padded to the largest slice
+    gather = None
+    if world > 1:
+        # best-hit slices are all-gathered chunk by chunk behind the scoring of the next chunk (multigpu.py)
+        gather = multigpu.ChunkedBestHitGather(dist, rows_of_rank, G, dev, chunks=max(1, -(-max(rows_of_rank) // 65536)))
+        bh_local = gather.local
+    else:
+        bh_local = torch.zeros((max(rows_of_rank), G), dtype=torch.float32, device=dev)
 
     host_ms = [0.0, 0.0]  # wall clock of the last step's two calls (log only)
+
+    class Stats:
+        def __init__(self, d):
+            self.__dict__.update(d)
+
+        def as_dict(self):
+            return dict(self.__dict__)
 
     def step():
         t0 = time.perf_counter()
         pn = native.PangeneNative(k, data, device=local, residues_device_ptr=res_dev.data_ptr())
         t1 = time.perf_counter()
-        st = pn.score_partition_device(row0, row1, best_hit_ptr=bh_local.data_ptr())
+        if gather is not None:
+            st = Stats(multigpu.score_and_gather(pn, gather, rank, row0))
+        else:
+            st = pn.score_partition_device(row0, row1, best_hit_ptr=bh_local.data_ptr())
         host_ms[0], host_ms[1] = (t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3
-        if world > 1:
-            multigpu.allgather_best_hits(dist, bh_local, rows_of_rank, G, dev)
         return pn, st
 
     def barrier():
@@ -479,7 +493,7 @@ def main():
                           "query_genomes_per_rank": int(q), "query_rows_per_rank": int(rows_n), "query_genomes_this_rank": [g0, g1],
                           "parallelism": "index replicated, query genomes split by posting-list volume" if world > 1 else "single GPU",
                           "l2": "flushed between timed steps (256 MiB fill)",
-                          "step": "index build from HBM-resident residues + scoring of the rank's query rows" + (" + NCCL allgather of best-hit slices" if world > 1 else "")},
+                          "step": "index build from HBM-resident residues + scoring of the rank's query rows" + (", NCCL allgather of the best-hit slices chunk by chunk behind the scoring" if world > 1 else "")},
                "lookups_per_s": lookups_all / (ms * 1e-3), "cells_per_step": cells_all, "pairs_per_step": pairs_all,
                "build_ms_per_step": build_ms / args.steps, "score_kernel_ms_per_step": kms,
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}

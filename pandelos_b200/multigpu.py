@@ -53,3 +53,74 @@ def allgather_best_hits(dist, bh_local, rows_of_rank, G, device):
         return padded, padded
     parts = [padded[r * max_rows:r * max_rows + int(rows_of_rank[r])] for r in range(world)]
     return torch.cat(parts, 0), padded
+
+
+class ChunkedBestHitGather:
+    """Scoring and the all-gather of the best-hit slices, overlapped chunk by chunk.
+
+    Every rank's slice (padded to the same number of rows) is cut into `chunks` row chunks of `chunk_rows` rows; as soon
+    as the engine has scored a chunk its rows are all-gathered asynchronously (NCCL on its own stream, NVLink) while the
+    next chunk is being scored, so only the last chunk's exchange is exposed.  One all-gather after all scoring — the
+    simple `allgather_best_hits` above — cost 27 ms on top of a 205 ms step on 8 B200s (8 x 1.9 GB slices).
+
+    The gathered table is chunk-major: `table[c, r, i]` is local row `c * chunk_rows + i` of rank `r`; `offset_of(rank,
+    local_row)` gives the row index into `table.view(-1, G)`, `assemble()` the plain rank-major (sum(rows) x G) table.
+    """
+
+    def __init__(self, dist, rows_of_rank, G, device, chunks):
+        import torch
+        self.dist, self.G, self.device = dist, int(G), device
+        self.rows_of_rank = [int(r) for r in rows_of_rank]
+        self.world = len(self.rows_of_rank)
+        max_rows = max(self.rows_of_rank) if self.world else 0
+        self.chunks = max(1, min(int(chunks), max(1, max_rows)))
+        self.chunk_rows = max(1, -(-max_rows // self.chunks))
+        self.table = torch.zeros((self.chunks, self.world, self.chunk_rows, self.G), dtype=torch.float32, device=device)
+        # this rank's slice, padded to chunks x chunk_rows rows: the engine writes best hits straight into it
+        self.local = torch.zeros((self.chunks * self.chunk_rows, self.G), dtype=torch.float32, device=device)
+        self.works = []
+
+    def local_range(self, rank, c):
+        """Local rows [lo, hi) of `rank` inside chunk c (hi <= that rank's row count; may be empty)."""
+        lo = min(c * self.chunk_rows, self.rows_of_rank[rank])
+        hi = min((c + 1) * self.chunk_rows, self.rows_of_rank[rank])
+        return lo, hi
+
+    def gather_chunk(self, c):
+        """Queues the all-gather of chunk c of every rank (asynchronous; call after the chunk's rows are final)."""
+        src = self.local[c * self.chunk_rows:(c + 1) * self.chunk_rows]
+        dst = self.table[c].view(self.world * self.chunk_rows, self.G)
+        self.works.append(self.dist.all_gather_into_tensor(dst, src, async_op=True))
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+    def offset_of(self, rank, local_row):
+        c, i = divmod(int(local_row), self.chunk_rows)
+        return (c * self.world + int(rank)) * self.chunk_rows + i
+
+    def assemble(self):
+        import torch
+        parts = []
+        for r in range(self.world):
+            rows = self.table[:, r].reshape(self.chunks * self.chunk_rows, self.G)
+            parts.append(rows[:self.rows_of_rank[r]])
+        return torch.cat(parts, 0)
+
+
+def score_and_gather(pn, gather, rank, row_begin):
+    """Scores this rank's genes [row_begin, row_begin + rows) chunk by chunk with `pn.score_partition_device`, queueing
+    each chunk's all-gather behind it; returns the summed pd_score_stats fields as a dict.  `gather.local` must be zero
+    where rows are padding (it is after construction; the engine zeroes the rows it scores)."""
+    total = None
+    for c in range(gather.chunks):
+        lo, hi = gather.local_range(rank, c)
+        if hi > lo:
+            st = pn.score_partition_device(row_begin + lo, row_begin + hi, best_hit_ptr=gather.local[lo].data_ptr())
+            d = st.as_dict()
+            total = d if total is None else {k: total[k] + v for k, v in d.items()}
+        gather.gather_chunk(c)
+    gather.wait()
+    return total

@@ -34,6 +34,16 @@ def _worker(rank, world, port, emu_path, out_dir):
     bh_all, _ = multigpu.allgather_best_hits(dist, bh_local, rows, G, "cpu")
     pairs = torch.tensor([float(st.pairs)], dtype=torch.float64)
     dist.all_reduce(pairs)
+    # the overlapped variant: scoring and gathering chunk by chunk (3 chunks, the last one ragged) must give the same table
+    gather = multigpu.ChunkedBestHitGather(dist, rows, G, "cpu", chunks=3)
+    tot = multigpu.score_and_gather(pn, gather, rank, int(bounds[rank]))
+    chunked = gather.assemble()
+    same = torch.equal(chunked.view(torch.int32), bh_all.view(torch.int32)) and tot["pairs"] == st.pairs and tot["rows"] == rows[rank]
+    probe_rank, probe_row = world - 1, rows[world - 1] - 1
+    same = same and torch.equal(gather.table.view(-1, G)[gather.offset_of(probe_rank, probe_row)],
+                                bh_all[sum(rows[:probe_rank]) + probe_row])
+    flag = torch.tensor([1.0 if same else 0.0], dtype=torch.float64)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         want = np.zeros((S, G), np.float32)
         total = 0
@@ -43,7 +53,7 @@ def _worker(rank, world, port, emu_path, out_dir):
             total += pn.last_stats.pairs
         got = bh_all.numpy()
         ok = got.shape == want.shape and (got.view(np.uint32) == want.view(np.uint32)).all() and int(pairs.item()) == total \
-            and set(bounds.tolist()) <= set(gb.tolist()) and (want > 0).any()
+            and set(bounds.tolist()) <= set(gb.tolist()) and (want > 0).any() and flag.item() == 1.0
         open(os.path.join(out_dir, "result"), "w").write("ok" if ok else "mismatch")
     pn.close()
     dist.barrier()
