@@ -353,9 +353,10 @@ def main():
         launches += int(st.launches + pn.info.build_ms[7])
         info = pn.info
         stats = st.as_dict()
-        log("[bench] step %.1f ms (wall %.1f): build %.1f [%s], scoring kernels %.1f, scoring call %.1f; host wall: build call %.1f, scoring call %.1f" % (
-            ms_steps[-1], wall, pn.info.build_ms[5], " ".join("%.1f" % v for v in pn.info.build_ms[:5]), st.kernel_ms, st.total_ms,
-            host_ms[0], host_ms[1]))
+        if rank == 0:
+            log("[bench] step %.1f ms (wall %.1f): build %.1f [%s], scoring kernels %.1f, scoring call %.1f; host wall: build call %.1f, scoring call %.1f" % (
+                ms_steps[-1], wall, pn.info.build_ms[5], " ".join("%.1f" % v for v in pn.info.build_ms[:5]), st.kernel_ms, st.total_ms,
+                host_ms[0], host_ms[1]))
         pn.close()
     clocks = sampler.stop() if rank == 0 else None
     ms = float(np.mean(ms_steps))
