@@ -675,11 +675,19 @@ inline uint32_t log2_floor(uint64_t v) {
 
 // Defaults: three first-try table sizes by row size and a large retry table.  pd_options.hash_log2 replaces the
 // first-try ladder by one small table of that many tier-2 slots; PD_SMEM_TOP (tests) caps the bytes of the retry table.
+inline bool small_index(const Index& ix) { return ix.info.S <= (1u << 18); }
+
 inline void levels_of(const Index& ix, Level lv[kLevels]) {
     lv[0] = {512, 9, 128, 256, 256};
     lv[1] = {2048, 11, 256, 512, 1536};
     lv[2] = {4096, 11, 512, 1024, ~0ull};
     lv[3] = {2048, 14, 1024, 1024, 0};  // few, heavy rows, one CTA per SM: twice the warps per row shortens the tail
+    // Small indices (tens of genomes, k = 4..5): a row shares random k-mers with thousands of the few ten thousand
+    // genes, so its columns are many relative to S and the tier-1 slots (S / T1 genes each) collide.  A larger table
+    // for the top level cuts the rows that have to be scored twice from 1/3 to 1/20 (xanthomonas14: 63 -> 44 ms,
+    // ecoli10: 15.5 -> 10 ms); at S in the millions the columns of a row are a vanishing part of S and the two smaller
+    // CTAs per SM are faster.
+    if (small_index(ix)) lv[2] = {8192, 12, 1024, 1024, ~0ull};
     if (const char* e = getenv("PD_LEVELS")) {  // tuning: "t1:hbits:threads:fcap:maxcols,..." for the four levels
         unsigned t1, h, t, f;
         unsigned long long m;
@@ -823,6 +831,7 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
     a.colmax = d_colmax;
     a.xtab = c.d_xtab.p;
 
+    const bool skip_retry = small_index(ix) && ix.opt.hash_log2 == 0 && !getenv("PD_LEVELS");
     rt::event_record(c.ev_k0, c.st);
     for (int level = 0; level < kLevels - 1; level++) {
         sk::ScoreArgs b = a;
@@ -830,13 +839,16 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
         b.n_rows = n;  // upper bound: sizes the grid
         b.n_rows_dev = c.d_cursors.p + 8;
         b.level = (uint32_t)level;
-        b.overflow_rows = c.d_ovf.p;
-        b.n_overflow = c.d_counters.p + 2;
+        // small indices: a row that overflows the (already large) top table has a fifth of all genes as columns and never
+        // fits the retry table either (measured: every retried row of ecoli10 / xanthomonas14 fell through) — straight
+        // to the dense kernel's list then
+        b.overflow_rows = c.d_ovf.p + (skip_retry ? n : 0);
+        b.n_overflow = c.d_counters.p + (skip_retry ? 3 : 2);
         launch_rows(c, b, lv[level], level);
     }
     // retry level: rows that overflowed their first table.  Their count stays on the device (no host round trip in
     // the middle of the job: a counter read-back would queue behind the result arrays another call is sending)
-    {
+    if (!skip_retry) {
         sk::ScoreArgs b = a;
         b.rows = c.d_ovf.p;
         b.n_rows = n;  // upper bound: sizes the grid
@@ -854,8 +866,12 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
     c.stats.retry_rows += c.h_counters.p[2];
     // last resort: dense global accumulators
     if (const uint32_t nr = (uint32_t)c.h_counters.p[3]) {
-        const unsigned grid = std::min<unsigned>(nr, 32);
-        const size_t words = (size_t)grid * 4 * ix.info.S;
+        // one CTA per row at a time, each with 20 S bytes of accumulators: as many CTAs as 2 GB of them allow, at most
+        // four per SM (small indices, where wide rows are common, get the whole device; at S = 4 M it is 32 CTAs)
+        const uint64_t per_cta = (uint64_t)4 * sk::kDenseWordsPerGene * std::max<uint32_t>(ix.info.S, 1);
+        const unsigned fit = (unsigned)std::max<uint64_t>(32, std::min<uint64_t>((uint64_t)ix.sms * 4, (2ull << 30) / per_cta));
+        const unsigned grid = std::min<unsigned>(nr, fit);
+        const size_t words = (size_t)grid * sk::kDenseWordsPerGene * ix.info.S;
         if (c.d_dense.n < words || c.dense_S != ix.info.S) {  // the per-CTA layout follows S: a context taken over from an
             if (c.d_dense.n < words) c.d_dense.alloc(words);  // index of another size holds stale `touched` lists in it
             zero_words(c.d_dense.p, c.d_dense.n * sizeof(uint32_t), c.st);

@@ -117,9 +117,10 @@ struct ScoreArgs {
     } while (0)
 #endif
 
+static const uint32_t kDenseWordsPerGene = 5;
 struct DenseArgs {
     uint32_t S;
-    uint32_t* acc;  // per CTA: inter[S], pc[S], tc[S], touched[S]; inter/pc/tc all zero between rows
+    uint32_t* acc;  // per CTA: hits[S], three correction arrays [S], touched[S]; the first four all zero between rows
 };
 
 struct RowCtx {
@@ -870,10 +871,13 @@ __global__ void __launch_bounds__(kDenseThreads) score_rows_dense_kernel(ScoreAr
     __shared__ uint32_t s_row;
     __shared__ uint32_t s_touched;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t* inter = d.acc + (size_t)blockIdx.x * 4 * d.S;
-    uint32_t* pcv = inter + d.S;
-    uint32_t* tcv = pcv + d.S;
-    uint32_t* touched = tcv + d.S;
+    // per CTA: hits[S] (postings seen per column) and three correction arrays for postings with a multiplicity above one
+    // on either side (rare: U/N > 0.999) — one atomic per posting instead of three — and the touched list
+    uint32_t* hits = d.acc + (size_t)blockIdx.x * kDenseWordsPerGene * d.S;
+    uint32_t* xin = hits + d.S;   // sum of min(n, m) - 1
+    uint32_t* xpc = xin + d.S;    // sum of m - 1
+    uint32_t* xtc = xpc + d.S;    // sum of n - 1
+    uint32_t* touched = xtc + d.S;
     unsigned long long pairs = 0;
     const uint32_t n_rows = a.n_rows_dev ? *a.n_rows_dev : a.n_rows;
 
@@ -899,10 +903,13 @@ __global__ void __launch_bounds__(kDenseThreads) score_rows_dense_kernel(ScoreAr
                 const uint32_t e = a.post[fw.x + p];
                 const uint32_t c = e & ~kMulti;
                 const uint32_t n = (e & kMulti) ? a.post_cnt[fw.x + p] : 1u;
-                const uint32_t old = atomicAdd(&tcv[c], n);  // counts are >= 1: old == 0 <=> first touch
+                const uint32_t old = atomicAdd(&hits[c], 1u);  // old == 0 <=> first touch
                 if (old == 0) touched[atomicAdd(&s_touched, 1u)] = c;
-                atomicAdd(&inter[c], n < m ? n : m);
-                atomicAdd(&pcv[c], m);
+                if ((n | m) > 1u) {
+                    atomicAdd(&xin[c], (n < m ? n : m) - 1u);
+                    atomicAdd(&xpc[c], m - 1u);
+                    atomicAdd(&xtc[c], n - 1u);
+                }
             }
         }
         __threadfence();
@@ -915,12 +922,14 @@ __global__ void __launch_bounds__(kDenseThreads) score_rows_dense_kernel(ScoreAr
             uint2 mc = make_uint2(0u, 0u);
             if (i < nt) {
                 c = *(volatile uint32_t*)&touched[i];
-                in = *(volatile uint32_t*)&inter[c];
-                pc = *(volatile uint32_t*)&pcv[c];
-                tc = *(volatile uint32_t*)&tcv[c];
-                inter[c] = 0;
-                pcv[c] = 0;
-                tcv[c] = 0;
+                const uint32_t h = *(volatile uint32_t*)&hits[c];
+                in = h + *(volatile uint32_t*)&xin[c];
+                pc = h + *(volatile uint32_t*)&xpc[c];
+                tc = h + *(volatile uint32_t*)&xtc[c];
+                hits[c] = 0;
+                xin[c] = 0;
+                xpc[c] = 0;
+                xtc[c] = 0;
                 if (c != rc.r) {
                     pairs++;
                     mc = a.meta[c];

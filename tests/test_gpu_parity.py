@@ -51,6 +51,15 @@ def test_config_shapes_scaled(shape, scale, k):
     assert st["cells"] > 0 and st["fallback_rows"] == 0
 
 
+def test_large_index_level_config_on_a_small_workload(monkeypatch):
+    """Indices below 2^18 genes take a larger top-level table; the configuration of the large ones (two 512-thread CTAs per
+    SM, 4096 + 2048 slots) is forced here so that parity covers it at oracle sizes too."""
+    monkeypatch.setenv("PD_LEVELS", "512:9:128:256:256,2048:11:256:512:1536,4096:11:512:1024:0,2048:14:1024:1024:0")
+    w = synth.shape("ecoli10", scale=0.08)
+    st = check_workload(w, 5, index=False)
+    assert st["cells"] > 0
+
+
 def test_low_complexity_multiplicities():
     """poly-A / poly-Q runs: counts > 1 everywhere, long posting lists, MULTI rows."""
     w = synth.generate(8, 300, 200.0, 0.1, 61, low_complexity=0.5)
