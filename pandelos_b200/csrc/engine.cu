@@ -82,6 +82,7 @@ struct ScoreContext {
     rt::DevBuf<uint64_t> d_rowkeys;
     uint32_t xtab_ctas = 0;
     uint32_t dense_S = 0;  // gene count the dense accumulators are laid out (and clean) for
+    uint32_t dense_layout = 0;  // 1: global-memory kernel, 2: shared-memory kernel (corrections only)
     rt::PinBuf<unsigned long long> h_counters;
     rt::PinBuf<sk::RowDesc> h_rows;
     rt::PinBuf<float> h_score, h_perc, h_trperc, h_bh, h_colmax;
@@ -864,28 +865,49 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
     tc.lap(trace::kLevelsWait);
     c.stats.kernel_ms += rt::event_ms(c.ev_k0, c.ev_k1);
     c.stats.retry_rows += c.h_counters.p[2];
-    // last resort: dense global accumulators
+    // last resort: one counter per gene — in shared memory where the index is small enough, else in global memory
     if (const uint32_t nr = (uint32_t)c.h_counters.p[3]) {
-        // one CTA per row at a time, each with 20 S bytes of accumulators: as many CTAs as 2 GB of them allow, at most
-        // four per SM (small indices, where wide rows are common, get the whole device; at S = 4 M it is 32 CTAs)
-        const uint64_t per_cta = (uint64_t)4 * sk::kDenseWordsPerGene * std::max<uint32_t>(ix.info.S, 1);
-        const unsigned fit = (unsigned)std::max<uint64_t>(32, std::min<uint64_t>((uint64_t)ix.sms * 4, (2ull << 30) / per_cta));
-        const unsigned grid = std::min<unsigned>(nr, fit);
-        const size_t words = (size_t)grid * sk::kDenseWordsPerGene * ix.info.S;
-        if (c.d_dense.n < words || c.dense_S != ix.info.S) {  // the per-CTA layout follows S: a context taken over from an
-            if (c.d_dense.n < words) c.d_dense.alloc(words);  // index of another size holds stale `touched` lists in it
+        const uint32_t S = ix.info.S;
+        const size_t smem_bytes = (size_t)((S + 1) / 2) * 4;
+        const char* const dense_env = getenv("PD_DENSE");  // tests: "global" keeps the global-memory kernel covered
+        const bool in_smem = S <= sk::kDenseSmemGenes && ix.info.max_kseq < sk::kDenseSmemMaxK && smem_bytes + 1024 <= ix.smem_optin &&
+                             !(dense_env && strcmp(dense_env, "global") == 0);
+        unsigned grid;
+        size_t words;
+        if (in_smem) {
+            grid = std::min<unsigned>(nr, (unsigned)ix.sms);
+            words = (size_t)grid * 3 * S;
+        } else {
+            // one CTA per row at a time, each with 20 S bytes of accumulators: as many CTAs as 2 GB of them allow, at most
+            // four per SM (at S = 4 M it is 32 CTAs)
+            const uint64_t per_cta = (uint64_t)4 * sk::kDenseWordsPerGene * std::max<uint32_t>(S, 1);
+            const unsigned fit = (unsigned)std::max<uint64_t>(32, std::min<uint64_t>((uint64_t)ix.sms * 4, (2ull << 30) / per_cta));
+            grid = std::min<unsigned>(nr, fit);
+            words = (size_t)grid * sk::kDenseWordsPerGene * S;
+        }
+        // the per-CTA layout follows S and the kernel: a context taken over from an index of another size (or used by the
+        // other kernel) holds stale `touched` lists where this layout wants zeros
+        const uint32_t layout = in_smem ? 2u : 1u;
+        if (c.d_dense.n < words || c.dense_S != S || c.dense_layout != layout) {
+            if (c.d_dense.n < words) c.d_dense.alloc(words);
             zero_words(c.d_dense.p, c.d_dense.n * sizeof(uint32_t), c.st);
-            c.dense_S = ix.info.S;
+            c.dense_S = S;
+            c.dense_layout = layout;
         }
         sk::ScoreArgs b2 = a;
         b2.rows = c.d_ovf.p + n;
         b2.n_rows = nr;
         b2.cursor = c.d_cursors.p + kLevels;
         sk::DenseArgs d;
-        d.S = ix.info.S;
+        d.S = S;
         d.acc = c.d_dense.p;
         rt::event_record(c.ev_k0, c.st);
-        PD_LAUNCH(sk::score_rows_dense_kernel, grid, sk::kDenseThreads, 0, c.st, b2, d);
+        if (in_smem) {
+            rt::allow_smem(sk::score_rows_dense_smem_kernel, smem_bytes);
+            PD_LAUNCH(sk::score_rows_dense_smem_kernel, grid, sk::kDenseSmemThreads, smem_bytes, c.st, b2, d);
+        } else {
+            PD_LAUNCH(sk::score_rows_dense_kernel, grid, sk::kDenseThreads, 0, c.st, b2, d);
+        }
         c.stats.launches++;
         c.stats.fallback_rows += nr;
         publish(c, 0, 8);

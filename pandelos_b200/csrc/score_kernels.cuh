@@ -954,6 +954,132 @@ __global__ void __launch_bounds__(kDenseThreads) score_rows_dense_kernel(ScoreAr
     if (lane == 0 && pairs) atomicAdd(a.n_pairs, pairs);
 }
 
+// The same for indices small enough that one counter per gene fits in shared memory (S <= kDenseSmemGenes, 16-bit
+// counters, two genes per word): the wide rows of small indices — a row sharing random k-mers with a third of all
+// genes — are the rule there, and global atomics make them cost 60 % of the scoring time.  A posting is one
+// fire-and-forget shared-memory add; no touched list, the finalize pass walks all S counters (a few thousand words per
+// thread block pass).  Postings with a multiplicity above one on either side add their corrections to global arrays
+// (3 x S words per CTA, all zero between rows), read only for rows that made any.  A column is hit at most once per
+// distinct k-mer of the row (twice in the tail-merged group), so 16 bits hold any row with fewer than 65,534 k-mers;
+// longer rows are left to the global-memory kernel (the host sends them there).
+static const int kDenseSmemThreads = 1024;
+static const uint32_t kDenseSmemGenes = 112 * 1024;  // 2 B each: 224 KB
+static const uint32_t kDenseSmemMaxK = 65534;
+
+__global__ void __launch_bounds__(kDenseSmemThreads, 1) score_rows_dense_smem_kernel(ScoreArgs a, DenseArgs d) {
+    PD_DYNAMIC_SMEM(smem_raw);
+    uint32_t* h = reinterpret_cast<uint32_t*>(smem_raw);  // (S + 1) / 2 words
+    __shared__ uint32_t s_row;
+    __shared__ uint32_t s_corrected;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t words = (d.S + 1) / 2;
+    uint32_t* xin = d.acc + (size_t)blockIdx.x * 3 * d.S;  // sum of min(n, m) - 1
+    uint32_t* xpc = xin + d.S;                             // sum of m - 1
+    uint32_t* xtc = xpc + d.S;                             // sum of n - 1
+    unsigned long long pairs = 0;
+    const uint32_t n_rows = a.n_rows_dev ? *a.n_rows_dev : a.n_rows;
+    for (uint32_t w = tid; w < words; w += kDenseSmemThreads) h[w] = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            s_row = atomicAdd(a.cursor, 1u);
+            s_corrected = 0;
+        }
+        __syncthreads();
+        const uint32_t ri = s_row;
+        if (ri >= n_rows) break;
+        const RowDesc rw = a.rows[ri];
+        RowCtx rc;
+        rc.r = rw.gene;
+        rc.bh_row = rw.bh_row;
+        rc.kr = rw.kr;
+        rc.gr = rw.gr;
+        // short posting lists: one thread per list; long and huge lists: one warp per list, lanes striding the postings
+        for (uint32_t f = rw.fb + tid; f < rw.fm; f += kDenseSmemThreads) {
+            const uint2 fw = a.fwd[f];
+            const uint32_t gl = fw.y & ~kMulti;
+            const uint32_t m = (fw.y & kMulti) ? a.fwd_cnt[f] : 1u;
+            for (uint32_t p = 0; p < gl; p++) {
+                const uint32_t e = a.post[fw.x + p];
+                const uint32_t c = e & ~kMulti;
+                atomicAdd(&h[c >> 1], 1u << ((c & 1u) * 16u));
+                if ((e & kMulti) || m > 1u) {
+                    const uint32_t n = (e & kMulti) ? a.post_cnt[fw.x + p] : 1u;
+                    atomicAdd(&xin[c], (n < m ? n : m) - 1u);
+                    atomicAdd(&xpc[c], m - 1u);
+                    atomicAdd(&xtc[c], n - 1u);
+                    s_corrected = 1u;
+                }
+            }
+        }
+        for (uint32_t f = rw.fm + warp; f < rw.fe; f += kDenseSmemThreads / 32) {
+            const uint2 fw = a.fwd[f];
+            const uint32_t m = (fw.y & kMulti) ? a.fwd_cnt[f] : 1u;
+            const uint32_t gl = fw.y & ~kMulti;
+            for (uint32_t p = lane; p < gl; p += 32) {
+                const uint32_t e = a.post[fw.x + p];
+                const uint32_t c = e & ~kMulti;
+                atomicAdd(&h[c >> 1], 1u << ((c & 1u) * 16u));
+                if ((e & kMulti) || m > 1u) {
+                    const uint32_t n = (e & kMulti) ? a.post_cnt[fw.x + p] : 1u;
+                    atomicAdd(&xin[c], (n < m ? n : m) - 1u);
+                    atomicAdd(&xpc[c], m - 1u);
+                    atomicAdd(&xtc[c], n - 1u);
+                    s_corrected = 1u;
+                }
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        const bool corrected = s_corrected != 0;
+        // finalize: every thread walks its words; both genes of a word, then the word is cleared
+        for (uint32_t w0 = 0; w0 < words; w0 += kDenseSmemThreads) {
+            const uint32_t w = w0 + tid;
+            const uint32_t v = w < words ? h[w] : 0u;
+            if (v) h[w] = 0;
+#pragma unroll
+            for (uint32_t half = 0; half < 2; half++) {
+                const uint32_t hits = half ? (v >> 16) : (v & 0xFFFFu);
+                const uint32_t c = 2 * w + half;
+                bool want = false;
+                uint32_t in = hits, pc = hits, tc = hits;
+                uint2 mc = make_uint2(0u, 0u);
+                if (hits) {
+                    if (corrected) {
+                        const uint32_t xi = *(volatile uint32_t*)&xin[c], xp = *(volatile uint32_t*)&xpc[c], xt = *(volatile uint32_t*)&xtc[c];
+                        if (xi | xp | xt) {
+                            in += xi;
+                            pc += xp;
+                            tc += xt;
+                            xin[c] = 0;
+                            xpc[c] = 0;
+                            xtc[c] = 0;
+                        }
+                    }
+                    if (c != rc.r) {  // identity cell dropped (library.cpp:485-487)
+                        pairs++;
+                        mc = a.meta[c];
+                        want = gate(a.k2, pc, tc, rc.kr, mc.x);
+                    }
+                }
+                const unsigned mb = __ballot_sync(0xffffffffu, want);
+                if (mb) {  // warp-aggregated append
+                    const unsigned leader = __ffs((int)mb) - 1;
+                    unsigned long long base = 0;
+                    if (lane == leader) base = atomicAdd(a.n_cells, (unsigned long long)__popc(mb));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (want) emit_cell(a, rc, base + __popc(mb & ((1u << lane) - 1u)), c, mc.y, mc.x, in, pc, tc);
+                }
+            }
+        }
+        if (corrected) __threadfence();
+    }
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, dd);
+    if (lane == 0 && pairs) atomicAdd(a.n_pairs, pairs);
+}
+
 // ------------------------------------------------------------------------------------------------ row lists
 
 // The rows of one scoring call are sorted on the device by (table level, family key) and turned into descriptors.

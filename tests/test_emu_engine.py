@@ -60,6 +60,11 @@ def test_overflow_levels_and_dense_path(monkeypatch):
     w = synth.generate(3, 60, 80.0, 0.1, 52, low_complexity=0.6)
     st = check_workload(w, 3, hash_log2=5)
     assert st["fallback_rows"] > 0
+    # the same rows through the global-memory fallback kernel (what indices above 112 K genes use)
+    monkeypatch.setenv("PD_DENSE", "global")
+    st = check_workload(w, 3, hash_log2=5)
+    assert st["fallback_rows"] > 0
+    monkeypatch.delenv("PD_DENSE")
     # a smaller index takes over the parked score context of the larger one (dense accumulators laid out for another S)
     w, k = fixtures.random_workload(51, genes=70, genomes=4, max_len=45)
     st = check_workload(w, k, hash_log2=4)

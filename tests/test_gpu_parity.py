@@ -96,6 +96,18 @@ def test_overflow_levels_and_dense_path(monkeypatch):
     assert st["fallback_rows"] > 0
 
 
+def test_dense_fallback_kernels_shared_and_global(monkeypatch):
+    """Rows wider than every hash table: small indices count them in shared memory (16-bit counter per gene), large ones
+    in global memory; both kernels on the same rows, with repeated k-mers (the correction arrays) and without."""
+    monkeypatch.setenv("PD_SMEM_TOP", "2048")
+    for low in (0.0, 0.4):
+        w = synth.generate(6, 220, 150.0, 0.1, 65, low_complexity=low)
+        for kind in ("smem", "global"):
+            monkeypatch.setenv("PD_DENSE", kind)
+            st = check_workload(w, 4, hash_log2=6, index=False)
+            assert st["fallback_rows"] > 0
+
+
 def test_contexts_taken_over_by_indices_of_other_sizes(monkeypatch):
     """Score contexts (result buffers, dense accumulators, side tables) are parked when an index dies and taken over by
     the next one: a larger index, then a smaller one, then a larger one again, each through the dense fallback."""
