@@ -118,6 +118,49 @@ def test_contexts_taken_over_by_indices_of_other_sizes(monkeypatch):
         assert st["fallback_rows"] > 0
 
 
+def _scores_digest(s):
+    """Order-independent digest of every field of a Scores object (cell order is free)."""
+    n = s.scoresCount
+    f32 = lambda a: np.ascontiguousarray(a[:n], dtype=np.float32).view(np.uint32).astype(np.uint64)
+    i32 = lambda a: np.ascontiguousarray(a[:n]).astype(np.int64).astype(np.uint64)
+    h = (i32(s.row) * np.uint64(0x9E3779B97F4A7C15)) ^ (i32(s.column) * np.uint64(0xC2B2AE3D27D4EB4F))
+    h = h * np.uint64(0x165667B19E3779F9) + f32(s.scores) + (f32(s.percs) << np.uint64(7)) + (f32(s.tr_percs) << np.uint64(13))
+    h = h ^ (i32(s.first_seq_genome) << np.uint64(40)) ^ (i32(s.second_seq_genome) << np.uint64(52))
+    return (int(n), int(h.sum(dtype=np.uint64)), np.ascontiguousarray(s.max_genome_score).tobytes(),
+            np.ascontiguousarray(s.max_genome_score_col).tobytes(), np.ascontiguousarray(s.scoresMaxMappings).tobytes())
+
+
+def test_concurrent_calls_stress():
+    """Four host threads, every genome several times each, results landing in pinned memory that the host learns about by
+    polling a completion number (no stream synchronisation): every call must return exactly what a lone call returns."""
+    import threading
+    w = synth.shape("salmonella7", scale=0.5)
+    pn = native.PangeneNative(5, native.PangeneIData(w.residues, w.offsets, w.genome_of), contexts=4)
+    try:
+        G = pn.info.G
+        want = [_scores_digest(pn.generateScoresPart(g)) for g in range(G)]
+        assert sum(d[0] for d in want) > 0
+        bad, errs = [], []
+
+        def work(t):
+            try:
+                for rep in range(6):
+                    for g in range(G):
+                        gg = (g + t) % G
+                        if _scores_digest(pn.generateScoresPart(gg)) != want[gg]:
+                            bad.append((t, rep, gg))
+            except Exception as e:  # pragma: no cover
+                errs.append(e)
+
+        th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errs, errs
+        assert not bad, bad[:5]
+    finally:
+        pn.close()
+
+
 def test_cell_buffer_regrow_and_concurrent_calls():
     import threading
     w = synth.generate(6, 200, 150.0, 0.1, 64)
