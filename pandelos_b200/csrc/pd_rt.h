@@ -6,6 +6,7 @@
 // emulator in tests/emu/cuemu.h — test infrastructure for a GPU-less container, never shipped.
 #pragma once
 
+#include <algorithm>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -118,6 +119,7 @@ inline void collect() {
     if (c.keep_limit == 0) {
         size_t free_b = 0, total_b = 0;
         c.keep_limit = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? total_b / 4 * 3 : ~size_t(0);
+        if (const char* e = getenv("PD_CACHE_KEEP_MB")) c.keep_limit = std::max<size_t>(1, (size_t)atoll(e)) << 20;  // hosts that share the GPU
     }
     if (c.cached > c.keep_limit) trim_cache(c, c.keep_limit);
 }
