@@ -13,12 +13,16 @@
 //                    Java's Double.toString prints it.  Line ORDER: the reference iterates a HashMap; here lines are
 //                    sorted by (src, dst) — netclu_ng.py reads the file into a graph, the order carries no meaning.
 #include <algorithm>
+#include <atomic>
 #include <charconv>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -56,12 +60,41 @@ std::string java_double_to_string(double d) {
     return out;
 }
 
+// PANGENES_TIMING=1: wall clock of the phases on stderr
+struct PhaseTimer {
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    const bool on = getenv("PANGENES_TIMING") != nullptr;
+    void lap(const char* what) {
+        const auto n = std::chrono::steady_clock::now();
+        if (on) fprintf(stderr, "[pangenes] %-14s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
+// appends Double.toString(d) at p (at most 32 characters).  Scores lie in (0, 1]: between 1e-3 and 1e7 Java prints the
+// shortest round-trip digits in plain decimal notation, which is to_chars' fixed format plus ".0" for whole numbers.
+char* append_java_double(char* p, double d) {
+    if (d >= 1e-3 && d < 1e7) {
+        char* e = std::to_chars(p, p + 32, d, std::chars_format::fixed).ptr;
+        bool dot = false;
+        for (char* q = p; q < e; q++) dot |= *q == '.';
+        if (!dot) {
+            *e++ = '.';
+            *e++ = '0';
+        }
+        return e;
+    }
+    const std::string s = java_double_to_string(d);
+    memcpy(p, s.data(), s.size());
+    return p + s.size();
+}
+
 void usage() {
     printf("usage: pangenes -i <arg> -k <arg> -o <arg> [-j <arg>] [-c] [-h]\n"
            " -c,--complexity     Compute the required number of operations without computing the network (fast)\n"
            " -h,--help           Print this help message\n"
            " -i,--input <arg>    Input file (.faa) to process\n"
-           " -j,--threads <arg>  Number of threads to use for the computation (accepted; the GPU engine ignores it)\n"
+           " -j,--threads <arg>  Upper bound on the host threads issuing per-genome calls (1 to 4 are used, by genome count)\n"
            " -k,--kvalue <arg>   Length of the kmers used by the algorithm\n"
            " -o,--output <arg>   Output file for the network\n");
 }
@@ -70,7 +103,7 @@ void usage() {
 
 int main(int argc, char** argv) {
     std::string in, out;
-    int k = 0;
+    int k = 0, threads = 0;
     bool complexity = false;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
@@ -84,9 +117,29 @@ int main(int argc, char** argv) {
         if (a == "-i" || a == "--input") in = need("i");
         else if (a == "-o" || a == "--output") out = need("o");
         else if (a == "-k" || a == "--kvalue") k = atoi(need("k"));
-        else if (a == "-j" || a == "--threads") need("j");
+        else if (a == "-j" || a == "--threads") threads = atoi(need("j"));
         else if (a == "-c" || a == "--complexity") complexity = true;
-        else if (a == "-h" || a == "--help") {
+        else if (a == "--selftest-format") {
+            // the fast writer against the reference formatter on float32 patterns in (0, 1] and around the notation
+            // switches (tests/test_network_filter.py; no GPU involved)
+            const long n = atol(need("selftest-format"));
+            uint32_t x = 0x9E3779B9u;
+            long bad = 0;
+            for (long i = 0; i < n; i++) {
+                x = x * 1664525u + 1013904223u;
+                uint32_t bits = 0x30000000u + (x % (0x3F800000u - 0x30000000u + 1u));  // 4.6e-10 .. 1.0
+                if (i % 7 == 0) bits = 0x3A83126Fu + (uint32_t)(i % 5) - 2u;            // around 1e-3
+                float f;
+                memcpy(&f, &bits, 4);
+                char buf[64];
+                const std::string fast(buf, append_java_double(buf, (double)f));
+                if (fast != java_double_to_string((double)f)) {
+                    if (bad++ < 5) fprintf(stderr, "mismatch at %a: %s vs %s\n", (double)f, fast.c_str(), java_double_to_string((double)f).c_str());
+                }
+            }
+            printf("selftest-format: %ld values, %ld mismatches\n", n, bad);
+            return bad ? 1 : 0;
+        } else if (a == "-h" || a == "--help") {
             usage();
             return 0;
         } else {
@@ -101,6 +154,7 @@ int main(int argc, char** argv) {
         return 2;
     }
 
+    PhaseTimer timer;
     // ---- PangeneIData.readFromFile (PangeneIData.java:30-75) over the mapped file: no per-line strings for the sequences
     pd_host::MappedFile f(in);
     if (!f.ok()) {
@@ -140,6 +194,7 @@ int main(int argc, char** argv) {
         return 1;
     }
     const uint32_t S = (uint32_t)genome_of.size();
+    timer.lap("read .faa");
 
     pd_options opt;
     memset(&opt, 0, sizeof(opt));
@@ -160,6 +215,7 @@ int main(int argc, char** argv) {
     }
     pd_index_info info;
     pd_info(ix, &info);
+    timer.lap("index build");
 
     // ---- Pangenes.java:60-183, one task per genome; PangeneNet.addConnection keeps the FIRST score of a directed
     // (src, dest) pair (PangeneNet.java:49-62) and saveToFile(file, false) prints the pairs with src <= dest.  An
@@ -171,25 +227,66 @@ int main(int argc, char** argv) {
         uint64_t key;
         float score;
     };
+    // one task per genome from a small pool of host threads, as Pangenes.java:54-66 (-j threads there; here at most as
+    // many as the engine has score contexts: while one call's edges cross PCIe the others' kernels run).  Each task keeps
+    // its own edge list; lists are joined in genome order, which is the order the sequential host would report them in.
+    std::vector<std::vector<Edge>> per_genome(info.G);
+    std::vector<unsigned long long> filtered(info.G, 0);
+    std::atomic<uint32_t> next(0);
+    std::atomic<bool> failed(false);
+    std::string failure;
+    std::mutex failure_mu;
+    auto worker = [&]() {
+        for (;;) {
+            const uint32_t g = next.fetch_add(1);
+            if (g >= info.G || failed.load()) return;
+            pd_edges e;
+            if (pd_genome_edges(ix, g, &e) != PD_OK) {
+                std::lock_guard<std::mutex> lk(failure_mu);
+                if (!failed.exchange(true)) failure = pd_last_error();
+                return;
+            }
+            filtered[g] = e.cells;
+            std::vector<Edge>& out_edges = per_genome[g];
+            out_edges.reserve(e.count);
+            for (uint64_t i = 0; i < e.count; i++) {
+                const uint32_t a = e.src[i], b = e.dst[i];
+                // an intra-genome edge is added as (src, dest) only (Pangenes.java:171); it is reported with src < dest
+                out_edges.push_back(Edge{a <= b ? ((uint64_t)a << 32) | b : ((uint64_t)b << 32) | a, e.score[i]});
+            }
+            pd_edges_release(ix, &e);
+        }
+    };
+    {
+        // every extra worker is an extra score context to warm up (pinned and device result buffers, ~0.1 s): worth it
+        // only on inputs with hundreds of genomes
+        const int wanted = info.G >= 400 ? 4 : (info.G >= 100 ? 2 : 1);
+        const unsigned n_workers = (unsigned)std::max(1, std::min(threads > 0 ? std::min(threads, wanted) : wanted, 4));
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < n_workers; t++) pool.emplace_back(worker);
+        worker();
+        for (std::thread& t : pool) t.join();
+    }
+    if (failed.load()) {
+        fprintf(stderr, "pangenes: %s\n", failure.c_str());
+        return 1;
+    }
     std::vector<Edge> net;
+    {
+        size_t total = 0;
+        for (const auto& v : per_genome) total += v.size();
+        net.reserve(total);
+    }
     for (uint32_t g = 0; g < info.G; g++) {
         printf("Working on genome %u/%u\n", g, info.G);
-        pd_edges e;
-        if (pd_genome_edges(ix, g, &e) != PD_OK) {
-            fprintf(stderr, "pangenes: %s\n", pd_last_error());
-            return 1;
-        }
-        printf("Filtered count: %llu\n", (unsigned long long)e.cells);
-        net.reserve(net.size() + e.count);
-        for (uint64_t i = 0; i < e.count; i++) {
-            const uint32_t a = e.src[i], b = e.dst[i];
-            // an intra-genome edge is added as (src, dest) only (Pangenes.java:171); it is reported with src < dest
-            net.push_back(Edge{a <= b ? ((uint64_t)a << 32) | b : ((uint64_t)b << 32) | a, e.score[i]});
-        }
-        pd_edges_release(ix, &e);
+        printf("Filtered count: %llu\n", filtered[g]);
+        net.insert(net.end(), per_genome[g].begin(), per_genome[g].end());
+        std::vector<Edge>().swap(per_genome[g]);
     }
     pd_free(ix);
+    timer.lap("scores + filter");
     std::stable_sort(net.begin(), net.end(), [](const Edge& x, const Edge& y) { return x.key < y.key; });
+    timer.lap("sort edges");
 
     // ---- PangeneNet.saveToFile(file, false)
     FILE* o = fopen(out.c_str(), "w");
@@ -197,16 +294,30 @@ int main(int argc, char** argv) {
         fprintf(stderr, "cannot write %s\n", out.c_str());
         return 1;
     }
-    std::vector<char> obuf(1 << 22);
-    setvbuf(o, obuf.data(), _IOFBF, obuf.size());
+    // lines are formatted into a large buffer with to_chars: per-line fprintf and string building cost more than the
+    // whole GPU job on networks of millions of edges
+    std::vector<char> obuf((size_t)8 << 20);
+    size_t used = 0;
     uint64_t lines = 0;
     for (size_t i = 0; i < net.size(); i++) {
         if (i && net[i].key == net[i - 1].key) continue;  // a later report of the same pair
-        const uint32_t src = (uint32_t)(net[i].key >> 32), dst = (uint32_t)net[i].key;
-        fprintf(o, "%u\t%u\t%s\n", src, dst, java_double_to_string((double)net[i].score).c_str());
+        if (used + 96 > obuf.size()) {
+            fwrite(obuf.data(), 1, used, o);
+            used = 0;
+        }
+        char* p = obuf.data() + used;
+        p = std::to_chars(p, p + 12, (uint32_t)(net[i].key >> 32)).ptr;
+        *p++ = '\t';
+        p = std::to_chars(p, p + 12, (uint32_t)net[i].key).ptr;
+        *p++ = '\t';
+        p = append_java_double(p, (double)net[i].score);
+        *p++ = '\n';
+        used = (size_t)(p - obuf.data());
         lines++;
     }
+    fwrite(obuf.data(), 1, used, o);
     fclose(o);
+    timer.lap("write .net");
     printf("Network: %llu undirected edges written to %s\n", (unsigned long long)lines, out.c_str());
     return 0;
 }

@@ -53,6 +53,15 @@ def emu_lib():
     native._lib = None
 
 
+def test_native_cli_fast_number_formatter_matches_the_java_rule():
+    """The CLI's .net writer formats scores with to_chars; it must print what Double.toString prints (CPU only)."""
+    import subprocess
+    from pandelos_b200 import build
+    build.build_host()
+    r = subprocess.run([build.CLI_BIN, "--selftest-format", "300000"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 def test_java_double_to_string_known_values():
     j = pangenes_java.java_double_to_string
     assert j(np.float32(1 / 3)) == "0.3333333432674408" and j(np.float32(0.5)) == "0.5" and j(np.float32(1.0)) == "1.0"
