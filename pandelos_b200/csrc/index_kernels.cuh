@@ -345,21 +345,26 @@ __global__ void __launch_bounds__(kPartThreads) fwd_partition_kernel(const uint3
     }
 }
 
-// record -> its gene's forward list: class segment from cls, slot inside the segment from a running cursor (same
-// packing as cls, zero at entry)
-__global__ void __launch_bounds__(256) fwd_place_kernel(const uint4* __restrict__ records, uint32_t R,
-                                                         const unsigned long long* __restrict__ cls, const uint32_t* __restrict__ fwd_ptr,
-                                                         unsigned long long* __restrict__ cursor, uint2* __restrict__ fwd,
-                                                         uint32_t* __restrict__ fwd_cnt) {
+// cur3[3 s + c] = first slot of gene s's class-c segment (short, long, huge): fwd_place_kernel only has to bump it
+__global__ void __launch_bounds__(256) fwd_cursor_init_kernel(const unsigned long long* __restrict__ cls, const uint32_t* __restrict__ fwd_ptr,
+                                                               uint32_t S, uint32_t* __restrict__ cur3) {
+    const uint32_t s = blockIdx.x * 256u + threadIdx.x;
+    if (s >= S) return;
+    const unsigned long long cl = cls[s];
+    const uint32_t b = fwd_ptr[s], n0 = (uint32_t)(cl & kClsMask), n1 = (uint32_t)((cl >> kClsBits) & kClsMask);
+    cur3[3 * (size_t)s] = b;
+    cur3[3 * (size_t)s + 1] = b + n0;
+    cur3[3 * (size_t)s + 2] = b + n0 + n1;
+}
+
+// record -> its gene's forward list: one atomic on the segment's running slot, one 8-byte store (the per-gene bases are
+// folded into the cursors beforehand: two fewer L2 gathers per record than reading cls and fwd_ptr here)
+__global__ void __launch_bounds__(256) fwd_place_kernel(const uint4* __restrict__ records, uint32_t R, uint32_t* __restrict__ cur3,
+                                                         uint2* __restrict__ fwd, uint32_t* __restrict__ fwd_cnt) {
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
     if (i >= R) return;
     const uint4 r = records[i];
-    const uint32_t gene = r.x, c = r.w & 3u;
-    const unsigned long long old = atomicAdd(&cursor[gene], 1ull << (kClsBits * c));
-    const unsigned long long cl = cls[gene];
-    uint32_t slot = fwd_ptr[gene] + (uint32_t)((old >> (kClsBits * c)) & kClsMask);
-    if (c >= 1) slot += (uint32_t)(cl & kClsMask);
-    if (c == 2) slot += (uint32_t)((cl >> kClsBits) & kClsMask);
+    const uint32_t slot = atomicAdd(&cur3[3 * (size_t)r.x + (r.w & 3u)], 1u);
     fwd[slot] = make_uint2(r.y, r.z);  // bit 31 of the length: the gene's own multiplicity > 1 (then fwd_cnt is read)
     if (r.z & 0x80000000u) fwd_cnt[slot] = r.w >> 2;
 }
