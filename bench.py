@@ -427,6 +427,8 @@ def main():
             barrier()
             if i > 0:
                 e2e_ms.append((time.perf_counter() - t0) * 1e3)
+            if rank == 0:
+                log("[bench] e2e pass %d: %.1f ms%s" % (i, (time.perf_counter() - t0) * 1e3, " (untimed)" if i == 0 else ""))
             pn.close()
         te = torch.tensor([float(np.mean(e2e_ms)), float(pairs_e)], dtype=torch.float64, device=dev)
         if world > 1:
