@@ -27,6 +27,7 @@ ENGINE_LIB = os.path.join(HERE, "libpandelos_b200.so")
 JNI_LIB = os.path.join(HERE, "libnative.so")
 CLI_BIN = os.path.join(HERE, "pangenes")
 CALCK_BIN = os.path.join(HERE, "calculate_k")
+NETCLU_BIN = os.path.join(HERE, "netclu_cc")
 SYNTH_LIB = os.path.join(HERE, "libpdsynth.so")
 
 
@@ -101,7 +102,7 @@ def build_jni(force=False):
 
 
 def build_host(force=False):
-    """The native hosts: `pangenes` (links the engine) and `calculate_k` (CPU only, no engine)."""
+    """The native hosts: `pangenes` (links the engine); `calculate_k` and `netclu_cc` (CPU only, no engine)."""
     build_engine(force=False)
     hdir = os.path.join(CSRC, "host")
     if not os.path.isdir(hdir):
@@ -114,6 +115,9 @@ def build_host(force=False):
     src = os.path.join(hdir, "calculate_k_main.cpp")
     if force or _stale(CALCK_BIN, [src] + headers):
         _run([CXX, "-std=c++17", "-O2", "-Wall", "-I", hdir, "-o", CALCK_BIN, src])
+    src = os.path.join(hdir, "netclu_cc_main.cpp")
+    if force or _stale(NETCLU_BIN, [src] + headers):
+        _run([CXX, "-std=c++17", "-O2", "-Wall", "-I", hdir, "-o", NETCLU_BIN, src])
     return CLI_BIN
 
 
