@@ -417,7 +417,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         rt::DevBuf<unsigned long long> d_lookups(2);
         rt::DevBuf<uint32_t> gene_tot((size_t)S + 1), cur3(std::max<size_t>((size_t)3 * S, 1));
         rt::zero(d_lookups.p, 2 * sizeof(unsigned long long), st);
-        PD_LAUNCH(ik::fwd_count_kernel, blocks_for(U), 256, 0, st, (const uint32_t*)post.p, (const uint32_t*)ent_gid.p,
+        PD_LAUNCH(ik::fwd_count_kernel, blocks_for(U, 256 * ik::kFwdItems), 256, 0, st, (const uint32_t*)post.p, (const uint32_t*)ent_gid.p,
                   (const uint32_t*)grp_head.p, U, sk::kShortList, sk::kHugeList, cls.p);
         PD_LAUNCH(ik::fwd_totals_kernel, blocks_for((uint64_t)S + 1), 256, 0, st, (const unsigned long long*)cls.p, S, gene_tot.p);
         launches += 2;
@@ -440,7 +440,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
                       bshift, (const uint32_t*)fwd_ptr.p, bucket_cur.p, records.p);
             PD_LAUNCH(ik::fwd_cursor_init_kernel, blocks_for(S), 256, 0, st, (const unsigned long long*)cls.p, (const uint32_t*)fwd_ptr.p, S,
                       cur3.p);
-            PD_LAUNCH(ik::fwd_place_kernel, blocks_for(R), 256, 0, st, (const uint4*)records.p, R, cur3.p, fwd.p, fwd_cnt.p);
+            PD_LAUNCH(ik::fwd_place_kernel, blocks_for(R, 256 * ik::kFwdItems), 256, 0, st, (const uint4*)records.p, R, cur3.p, fwd.p, fwd_cnt.p);
             launches += 3;
         }
         PD_LAUNCH(ik::gene_visited_kernel, blocks_for((uint64_t)S * 32), 256, 0, st, (const uint2*)fwd.p, (const uint32_t*)fwd_ptr.p, S,

@@ -254,15 +254,26 @@ __device__ __forceinline__ uint32_t list_class(uint32_t gl, uint32_t short_max, 
     return gl <= short_max ? 0u : (gl > huge_min ? 2u : 1u);
 }
 
-// cls[gene] += 1 in the field of the entry's list class, for every entry of a shared group (length >= 2)
+// cls[gene] += 1 in the field of the entry's list class, for every entry of a shared group (length >= 2).
+// kFwdItems entries per thread, all their gathers issued before the first atomic: the kernel is bound by the latency of
+// the dependent gathers (ent_gid -> grp_head), not by DRAM (profiles/r01_fwd_kernels_ncu_full.txt).
+static const int kFwdItems = 4;
 __global__ void __launch_bounds__(256) fwd_count_kernel(const uint32_t* __restrict__ post, const uint32_t* __restrict__ ent_gid,
                                                          const uint32_t* __restrict__ grp_head, uint32_t U, uint32_t short_max,
                                                          uint32_t huge_min, unsigned long long* __restrict__ cls) {
-    const uint32_t e = blockIdx.x * 256u + threadIdx.x;
-    if (e >= U) return;
-    const uint32_t g = ent_gid[e];
-    const uint32_t gl = grp_head[g + 1] - grp_head[g];
-    if (gl >= 2) atomicAdd(&cls[post[e] & 0x7FFFFFFFu], 1ull << (kClsBits * list_class(gl, short_max, huge_min)));
+    const uint64_t e0 = (uint64_t)blockIdx.x * (256u * kFwdItems) + threadIdx.x;
+    uint32_t g[kFwdItems], gl[kFwdItems], p[kFwdItems];
+#pragma unroll
+    for (int j = 0; j < kFwdItems; j++) {
+        const uint64_t e = e0 + (uint64_t)j * 256u;
+        g[j] = e < U ? ent_gid[e] : 0xFFFFFFFFu;
+        p[j] = e < U ? post[e] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kFwdItems; j++) gl[j] = g[j] != 0xFFFFFFFFu ? grp_head[g[j] + 1] - grp_head[g[j]] : 0u;
+#pragma unroll
+    for (int j = 0; j < kFwdItems; j++)
+        if (gl[j] >= 2) atomicAdd(&cls[p[j] & 0x7FFFFFFFu], 1ull << (kClsBits * list_class(gl[j], short_max, huge_min)));
 }
 
 // tot[s] = forward entries of gene s (tot has S + 1 entries, the last one 0: its exclusive scan is fwd_ptr)
@@ -359,14 +370,27 @@ __global__ void __launch_bounds__(256) fwd_cursor_init_kernel(const unsigned lon
 
 // record -> its gene's forward list: one atomic on the segment's running slot, one 8-byte store (the per-gene bases are
 // folded into the cursors beforehand: two fewer L2 gathers per record than reading cls and fwd_ptr here)
+// kFwdItems records per thread: all loads, then all atomics, then all stores, so that a thread keeps several of the
+// dependent chains (record -> cursor atomic -> store) in flight.
 __global__ void __launch_bounds__(256) fwd_place_kernel(const uint4* __restrict__ records, uint32_t R, uint32_t* __restrict__ cur3,
                                                          uint2* __restrict__ fwd, uint32_t* __restrict__ fwd_cnt) {
-    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= R) return;
-    const uint4 r = records[i];
-    const uint32_t slot = atomicAdd(&cur3[3 * (size_t)r.x + (r.w & 3u)], 1u);
-    fwd[slot] = make_uint2(r.y, r.z);  // bit 31 of the length: the gene's own multiplicity > 1 (then fwd_cnt is read)
-    if (r.z & 0x80000000u) fwd_cnt[slot] = r.w >> 2;
+    const uint64_t i0 = (uint64_t)blockIdx.x * (256u * kFwdItems) + threadIdx.x;
+    uint4 r[kFwdItems];
+    uint32_t slot[kFwdItems];
+#pragma unroll
+    for (int j = 0; j < kFwdItems; j++) {
+        const uint64_t i = i0 + (uint64_t)j * 256u;
+        r[j] = i < R ? records[i] : make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < kFwdItems; j++)
+        slot[j] = r[j].x != 0xFFFFFFFFu ? atomicAdd(&cur3[3 * (size_t)r[j].x + (r[j].w & 3u)], 1u) : 0u;
+#pragma unroll
+    for (int j = 0; j < kFwdItems; j++) {
+        if (r[j].x == 0xFFFFFFFFu) continue;
+        fwd[slot[j]] = make_uint2(r[j].y, r[j].z);  // bit 31 of the length: the gene's own multiplicity > 1 (then fwd_cnt is read)
+        if (r[j].z & 0x80000000u) fwd_cnt[slot[j]] = r[j].w >> 2;
+    }
 }
 
 // visited[s] = sum of the posting-list lengths of gene s's forward entries (computation_costs[].total_visited,
