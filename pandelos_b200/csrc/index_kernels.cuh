@@ -302,21 +302,6 @@ struct FwdRecord {  // 16 B
     uint32_t gene, gs, gl_multi, cls_cnt;  // gl | own-count>1 flag; list class | own count << 2
 };
 
-__device__ __forceinline__ bool fwd_record_of(const uint32_t* __restrict__ post, const uint32_t* __restrict__ post_cnt,
-                                              const uint32_t* __restrict__ ent_gid, const uint32_t* __restrict__ grp_head, uint32_t e,
-                                              uint32_t short_max, uint32_t huge_min, FwdRecord* r) {
-    const uint32_t g = ent_gid[e];
-    const uint32_t gs = grp_head[g];
-    const uint32_t gl = grp_head[g + 1] - gs;
-    if (gl < 2) return false;
-    const uint32_t p = post[e];
-    r->gene = p & 0x7FFFFFFFu;
-    r->gs = gs;
-    r->gl_multi = gl | (p & 0x80000000u);
-    r->cls_cnt = list_class(gl, short_max, huge_min) | ((p & 0x80000000u) ? (post_cnt[e] << 2) : (1u << 2));
-    return true;
-}
-
 __global__ void __launch_bounds__(kPartThreads) fwd_partition_kernel(const uint32_t* __restrict__ post, const uint32_t* __restrict__ post_cnt,
                                                                       const uint32_t* __restrict__ ent_gid,
                                                                       const uint32_t* __restrict__ grp_head, uint32_t U, uint32_t S,
@@ -332,13 +317,34 @@ __global__ void __launch_bounds__(kPartThreads) fwd_partition_kernel(const uint3
     FwdRecord rec[kPartItems];
     uint32_t pos[kPartItems];
     unsigned have = 0;
+    // the gathers level by level over all items (entry -> group -> group bounds), then the ranking atomics: the chains
+    // of the items overlap instead of running one after the other
 #pragma unroll
     for (int j = 0; j < kPartItems; j++) {
         const uint32_t e = e0 + j * kPartThreads + tid;
-        if (e < U && fwd_record_of(post, post_cnt, ent_gid, grp_head, e, short_max, huge_min, &rec[j])) {
-            have |= 1u << j;
-            pos[j] = atomicAdd(&cnt[rec[j].gene >> bshift], 1u);
-        }
+        const bool in = e < U;
+        rec[j].gs = in ? ent_gid[e] : 0u;  // the group id for now
+        rec[j].gene = in ? post[e] : 0u;   // gene | bit 31
+        if (in) have |= 1u << j;
+    }
+#pragma unroll
+    for (int j = 0; j < kPartItems; j++) {
+        const uint32_t g = rec[j].gs;
+        const uint32_t gs = (have >> j & 1u) ? grp_head[g] : 0u;
+        const uint32_t gl = (have >> j & 1u) ? grp_head[g + 1] - gs : 0u;
+        rec[j].gs = gs;
+        rec[j].gl_multi = gl;
+        if (gl < 2) have &= ~(1u << j);
+    }
+#pragma unroll
+    for (int j = 0; j < kPartItems; j++) {
+        if (!(have >> j & 1u)) continue;
+        const uint32_t p = rec[j].gene, gl = rec[j].gl_multi;
+        const uint32_t e = e0 + j * kPartThreads + tid;
+        rec[j].gene = p & 0x7FFFFFFFu;
+        rec[j].gl_multi = gl | (p & 0x80000000u);
+        rec[j].cls_cnt = list_class(gl, short_max, huge_min) | ((p & 0x80000000u) ? (post_cnt[e] << 2) : (1u << 2));
+        pos[j] = atomicAdd(&cnt[rec[j].gene >> bshift], 1u);
     }
     __syncthreads();
     const uint32_t nb = ((S - 1) >> bshift) + 1;
