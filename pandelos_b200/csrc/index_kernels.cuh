@@ -293,8 +293,8 @@ __global__ void __launch_bounds__(256) fwd_totals_kernel(const unsigned long lon
 // BUCKET (2^bshift consecutive genes; the region of bucket b is exactly the forward-list range of its genes, so
 // fwd_ptr gives the region bounds for free); (2) fwd_place_kernel reads the records region after region and places
 // them: now all writes of the CTAs in flight fall into one bucket's window of `fwd`, which the L2 holds.
-static const int kPartThreads = 256;
-static const int kPartItems = 8;
+static const int kPartThreads = 512;
+static const int kPartItems = 4;
 static const int kPartTile = kPartThreads * kPartItems;
 static const int kMaxBuckets = 512;
 
