@@ -178,6 +178,15 @@ static void report() {
     for (int i = 0; i < kCalls; i++) fprintf(stderr, " %s %.1f ms;", names[i], (double)ns[i].exchange(0) * 1e-6);
     fprintf(stderr, "\n");
     ns[kCalls] = 0;
+#ifndef PD_EMU
+    for (int d = 0; d < 16; d++) {  // the block cache since the last report: a steady state should show no cudaMalloc at all
+        uint64_t hits, misses, bytes, mns;
+        rt::cache_stats(d, &hits, &misses, &bytes, &mns);
+        if (hits | misses)
+            fprintf(stderr, "[pd trace] device %d block cache: %llu hits, %llu cudaMalloc (%.1f MB, %.1f ms)\n", d, (unsigned long long)hits,
+                    (unsigned long long)misses, (double)bytes / 1048576.0, (double)mns * 1e-6);
+    }
+#endif
 }
 }  // namespace trace
 

@@ -20,6 +20,7 @@
 #include <chrono>
 #else
 #include <cuda_runtime.h>
+#include <chrono>
 
 #include <map>
 #include <mutex>
@@ -78,6 +79,7 @@ struct BlockCache {
     std::vector<void*> pending;                                    // freed, possibly still in use by queued kernels
     size_t cached = 0;
     size_t keep_limit = 0;                                         // idle bytes kept before trimming (0 = not asked yet)
+    uint64_t misses = 0, miss_bytes = 0, miss_ns = 0, hits = 0;    // dmalloc() calls that went to cudaMalloc / were served from the cache
 };
 inline BlockCache& block_cache(int dev) {
     static BlockCache caches[16];
@@ -134,10 +136,12 @@ inline void* dmalloc(size_t n) {
             void* p = it->second;
             c.cached -= it->first;
             c.free_blocks.erase(it);
+            c.hits++;
             return p;
         }
     }
     void* p = nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     cudaError_t e = cudaMalloc(&p, n);
     if (e != cudaSuccess) {  // give everything cached back to the driver and try once more
         cudaGetLastError();
@@ -154,6 +158,9 @@ inline void* dmalloc(size_t n) {
     }
     std::lock_guard<std::mutex> lk(c.mu);
     c.live[p] = std::make_pair(n, dev);
+    c.misses++;
+    c.miss_bytes += n;
+    c.miss_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
     return p;
 }
 inline void dfree(void* p) {
@@ -167,6 +174,13 @@ inline void dfree(void* p) {
         }
     }
     cudaFree(p);
+}
+// allocator statistics since the last call (PD_TRACE): cache hits, cudaMalloc calls, their bytes and host time
+inline void cache_stats(int dev, uint64_t* hits, uint64_t* misses, uint64_t* miss_bytes, uint64_t* miss_ns) {
+    BlockCache& c = block_cache(dev);
+    std::lock_guard<std::mutex> lk(c.mu);
+    *hits = c.hits; *misses = c.misses; *miss_bytes = c.miss_bytes; *miss_ns = c.miss_ns;
+    c.hits = c.misses = c.miss_bytes = c.miss_ns = 0;
 }
 // pinned host blocks are cached the same way (cudaMallocHost of the per-call result buffers costs milliseconds)
 struct HostCache {
