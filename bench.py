@@ -2,22 +2,34 @@
 """bench.py — the PanDelos Pangenes similarity hot path on B200, one process per GPU.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
+                    [--scaling strong|weak] [--exchange none|allgather]
 
-A STEP is one pass of the hot path over the rank's share of one synthetic pan-genome (SURVEY.md §8d shapes):
-index build from residues already in HBM (k-mer encode, sort, dedup, groups, forward lists = preprocessSequences)
-followed by scoring of the rank's query genes against the whole index (computeScores: accumulate along posting
-lists, float32 Jaccard, best hits), cells left in HBM.  With N > 1 every rank holds the whole index (built
-redundantly, "built once and replicated"); the query genomes of the job (N x 125 of the 1,000) are split into N
-genome-aligned blocks of equal posting-list volume (pandelos_b200/multigpu.py), each rank scores its block, and the
-best-hit slices are all-gathered over NCCL.  Per-rank work is fixed as N grows (scaling "weak"): N = 8 covers the
-whole data set.
+THE JOB (default workload scaleout1000, BASELINE.json configs[4]): preprocessSequences + computeScores of EVERY genome of
+the 1,000-genome synthetic pan-genome (3.8 M genes, 1.12 G k-mers, k = 7 from calculate_k.py's formula).
 
-metric  = candidate gene pairs scored per second (distinct (row, col != row) cells evaluated, library.cpp:493)
-e2e     = the same through the reference-facing C ABI with HOST buffers: pd_build from host residues, then one
-          pd_compute_scores per query genome with every Scores array copied back to pinned host memory.
+A STEP (--scaling strong, the default) is one pass of that whole job: index build from residues already in HBM (k-mer
+encode, sort, dedup, rank groups, forward lists = preprocessSequences, reference library.cpp:189-371) followed by the
+scoring of all query genes (computeScores, library.cpp:409-527: accumulate along posting lists, float32 Jaccard, best
+hits), cells left in HBM.  With N > 1 the genomes are split into N genome-aligned blocks of equal posting-list volume
+(the reference's own cost model, library.cpp:327); every computeScores(g) of the reference is served by exactly one rank,
+so no best-hit exchange is needed (colmax_g[c] is a maximum over the rows of genome g, all on one rank).  `--exchange
+allgather` adds the NCCL all-gather of the best-hit slices (the north star's design) as a cross-check mode.
+--scaling weak keeps round 1's fixed 125 genomes per rank.
+
+metric  = candidate gene pairs scored per second (distinct (row, col != row) cells evaluated, library.cpp:493), whole job
+e2e     = the same job through the reference-facing C ABI with HOST buffers: pd_build from host residues, then one
+          pd_compute_scores per genome from a pool of host threads (Pangenes.java:54-66), every Scores array copied
+          back to pinned host memory.
 roofline= scoring kernels: algorithmic bytes / CUDA-event time of the kernels, vs measured HBM peak.
-cpu_baseline / --impl reference = the UNMODIFIED reference library (oracle/_ref, fake JNIEnv driver, thread pool
-          over genomes as Pangenes.java:54-66) on the box's host cores, on a bounded sample of the same workload.
+parity  = after the timed steps the engine's Scores of the reference arm's sample genomes are digest-compared with the
+          goldens of tests/golden/digests/ (same index, same genomes); a mismatch fails the bench.
+cpu_baseline = the UNMODIFIED reference library (oracle/_ref, fake JNIEnv driver, thread pool over genomes) on a bounded
+          sub-index (first 80 genomes), the engine digest-compared with it live.
+--impl reference = the unmodified reference library on the box's host cores on THE SAME JOB: the full 1,000-genome index
+          is built once (single thread, as the reference does; reported as preprocess_s), each step times computeScores of
+          a fixed genome sample (0,125,..,875[, +8 more with 16 or more cores]) with one thread per genome, and
+          value = sample pairs / (sample scoring time + preprocess_s x sample/1000): the whole job's rate, EXTRAPOLATED
+          from the sample (a full CPU pass is hours) — SURVEY.md §8d, BASELINE.md §3.
 """
 import argparse
 import json
@@ -33,10 +45,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DEFAULT_WORKLOAD = "scaleout1000"
-# genomes scored per rank (weak scaling); None = all genomes on every rank count once (N must be 1)
-QUERY_GENOMES = {"scaleout1000": 125}
-# genomes of the workload the CPU reference is timed on (bounded sample: ~10-30 s of host work)
-CPU_SAMPLE_GENOMES = {"scaleout1000": 48, "mycoplasma64": 64}
+WEAK_QUERY_GENOMES = {"scaleout1000": 125}   # --scaling weak: genomes scored per rank
+SMALL_CONFIGS = ["salmonella7", "ecoli10", "xanthomonas14", "mycoplasma64"]
+CPU_SUBINDEX_GENOMES = 80                    # cpu_baseline leg of the b200 arm: reference on the first 80 genomes
+REF_FULL_INDEX_GB = 100                      # host RAM the unmodified reference needs for the 1,000-genome index (measured ~70)
+DIGESTS = os.path.join(ROOT, "tests", "golden", "digests")
 # host threads calling pd_compute_scores in the e2e arm (the Java host uses a thread pool, Pangenes.java:54-66)
 E2E_THREADS = int(os.environ.get("PD_E2E_THREADS", "0")) or max(
     1, min(4, (os.cpu_count() or 4) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
@@ -161,66 +174,225 @@ def make_workload(name):
     return w, k
 
 
-def genome_bounds(w):
-    return np.searchsorted(w.genome_of, np.arange(w.G + 1), side="left").astype(np.int64)
-
-
-def cpu_reference_sample(w, k, name, threads):
-    """Times the unmodified reference on the first `n` genomes of the workload.  Returns dict or None."""
-    from oracle import refjni
-    if not refjni.available():
+def golden(name):
+    p = os.path.join(DIGESTS, name + ".json")
+    if not os.path.exists(p):
         return None
-    n = min(CPU_SAMPLE_GENOMES.get(name, w.G), w.G)
-    sub = w.subset_genomes(n) if n < w.G else w
-    ref = refjni.RefJni()
-    t_pre = ref.preprocess(sub.residues, sub.offsets, sub.genome_of, k)
-    t_sc, cells = ref.compute_scores_pool(0, n, threads)
-    return {"sample": sub, "genomes": n, "preprocess_s": t_pre, "scores_s": t_sc, "cells": cells}
+    with open(p) as f:
+        return json.load(f)
+
+
+def gold_total(gold, key):
+    """Job total of `key` ("pairs" / "cells") from a golden file: stored, or summed when every genome is in the file."""
+    if "total_" + key in gold:
+        return gold["total_" + key]
+    if len(gold["per_genome"]) == gold["genomes"]:
+        return sum(e[key] for e in gold["per_genome"].values())
+    return None
+
+
+def host_kmers(w, k):
+    ln = np.diff(w.offsets.astype(np.int64))
+    return int(np.maximum(ln - k + 1, 0).sum())
+
+
+def job_config(name, w, k):
+    """The `config` object: identical in both arms (what is run on it differs by arm and is described beside it)."""
+    return {"workload": name, "k": int(k), "genes": int(w.S), "genomes": int(w.G), "kmers": host_kmers(w, k),
+            "job": "preprocessSequences + computeScores of every genome"}
+
+
+def mem_available_gb():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) / 1048576.0
+    except Exception:
+        pass
+    return 0.0
+
+
+def sample_order(gold):
+    """Sample genomes in the order of the golden file's generator: 0,125,..,875 first, then the others ascending."""
+    gs = sorted(int(g) for g in gold["per_genome"])
+    first = [g for g in gs if g % 125 == 0]
+    return first + [g for g in gs if g % 125]
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation, all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the same job on the box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from pandelos_b200 import native
+    from oracle import refjni
     name = args.workload
+    if not refjni.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this box"}))
+        return 0
     w, k = make_workload(name)
-    threads = os.cpu_count() or 1
-    times = []
-    res = None
+    cores = os.cpu_count() or 1
+    cfg = job_config(name, w, k)
+    big = name == "scaleout1000"
+    gold = golden(name + "_sample") if big else golden(name)
+    index_w, index_note, fallback = w, "full index (all %d genomes)" % w.G, False
+    if big and (gold is None or mem_available_gb() < REF_FULL_INDEX_GB or os.environ.get("PD_REF_SUBINDEX")):
+        # not enough host RAM for the reference's data layout at 1.12 G k-mers (16-B kmer_rank + radix temp + 24-B ranges)
+        gold = golden("scaleout1000_first80")
+        index_w = w.subset_genomes(CPU_SUBINDEX_GENOMES)
+        index_note = "SUB-INDEX of the first %d genomes (host RAM %.0f GB < %d GB needed for the full reference index)" % (
+            CPU_SUBINDEX_GENOMES, mem_available_gb(), REF_FULL_INDEX_GB)
+        fallback = True
+    if gold is None:
+        print(json.dumps({"impl": "reference", "unavailable": "no golden pair counts for %s (tests/golden/digests)" % name}))
+        return 0
+    if big and not fallback:
+        order = sample_order(gold)
+        sample = order[:8] if cores < 16 else order[:16]
+        pairs = sum(gold["per_genome"][str(g)]["pairs"] for g in sample)
+        want_cells = np.array([gold["per_genome"][str(g)]["cells"] for g in sample], np.int64)
+    else:
+        sample = list(range(index_w.G))
+        pairs = gold_total(gold, "pairs")
+        want_cells = None
+    threads = max(1, min(cores, len(sample)))
+    log("[bench] reference: %s; preprocessSequences (1 thread) ..." % index_note)
+    ref = refjni.RefJni()
+    pre_s = ref.preprocess(index_w.residues, index_w.offsets, index_w.genome_of, k)
+    share = pre_s * len(sample) / float(index_w.G)   # the sample's share of the one-off preprocess
+    log("[bench] reference: preprocess %.1fs; each step = computeScores of %d genomes on %d threads" % (pre_s, len(sample), threads))
+    times, cells_ok = [], True
     for i in range(args.warmup + args.steps):
-        res = cpu_reference_sample(w, k, name, threads)
-        if res is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this box"}))
-            return 0
+        t, per = ref.compute_scores_list(sample, threads)
+        if want_cells is not None:
+            cells_ok = cells_ok and bool((per == want_cells).all())
+        else:
+            cells_ok = cells_ok and int(per.sum()) == gold_total(gold, "cells")
         if i >= args.warmup:
-            times.append(res["preprocess_s"] + res["scores_s"])
-    # pair count of the sample (denominator only) from the engine when a GPU is here, else from the C port
-    sub = res["sample"]
-    try:
-        pn = native.PangeneNative(k, native.PangeneIData(sub.residues, sub.offsets, sub.genome_of))
-        pairs = pn.score_partition_device(0, sub.S).pairs
-        lookups = pn.info.lookups
-        pn.close()
-    except Exception:
-        from oracle import cport
-        o = cport.OracleIndex(sub.residues, sub.offsets, sub.genome_of, k)
-        pairs = sum(o.candidate_pairs(g) for g in range(sub.G))
-        lookups = o.total_lookups
-    t = float(np.mean(times))
+            times.append(t)
+        log("[bench] reference step %d: %.2fs" % (i, t))
+    t_sc = float(np.mean(times))
+    t = t_sc + share
     val = pairs / t
-    sample = "first %d of %d genomes of %s (%d genes, k=%d, %d lookups); preprocess 1 thread %.2fs + computeScores %d threads %.2fs" % (
-        res["genomes"], w.G, name, sub.S, k, lookups, res["preprocess_s"], threads, res["scores_s"])
+    lookups = sum(gold["per_genome"][str(g)]["lookups"] for g in sample) if want_cells is not None else gold["total_cost"]
+    desc = "%s; preprocessSequences once, 1 thread: %.1fs; per step computeScores of genomes %s on %d threads: %.2fs (%.3g lookups/s); " \
+           "value = sample pairs / (scoring + preprocess x %d/%d)%s" % (
+               index_note, pre_s, sample if len(sample) <= 16 else "0..%d" % (len(sample) - 1), threads, t_sc, lookups / t_sc,
+               len(sample), index_w.G, ", extrapolated to the whole job" if len(sample) < w.G else "")
     out = {"impl": "reference", "metric": "gene-pair Jaccard scores/sec", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
-           "config": {"workload": name, "k": k, "genes": int(w.S), "genomes": int(w.G)},
-           "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "reference", "sample": sample},
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": args.scaling,
+           "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic", "config": cfg,
+           "extrapolated": len(sample) < w.G, "same_index": not fallback, "preprocess_s": pre_s, "scores_s_per_step": t_sc,
+           "sample_genomes": sample if len(sample) <= 32 else len(sample), "sample_pairs": int(pairs),
+           "pairs_source": "tests/golden/digests (oracle restatement), not the engine",
+           "reference_cells_match_golden": cells_ok,
+           "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "reference", "sample": desc},
            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
     return 0
 
+
+# ------------------------------------------------------------------------------------------------ parity legs
+
+def parity_against_golden(pn, gold, genomes, what):
+    """Digest-compares the engine's computeScores of `genomes` with the golden file's; returns (ok, detail)."""
+    from pandelos_b200 import digest
+    bad = []
+    for g in genomes:
+        e = gold["per_genome"][str(g)]
+        s = pn.generateScoresPart(g)
+        d = digest.scores_digest(s)
+        if d != {x: e[x] for x in ("cells", "sum", "xor", "tables")} or pn.last_stats.pairs != e["pairs"] or pn.last_stats.lookups != e["lookups"]:
+            bad.append(int(g))
+    ok = not bad and pn.info.lookups == gold["total_cost"] and pn.info.N == gold["kmers"] and pn.info.U == gold["entries"]
+    return ok, {"against": what, "genomes": [int(g) for g in genomes], "mismatches": bad, "total_cost": int(pn.info.lookups),
+                "fields": "every Scores field (cells as a multiset of bit patterns, the three tables), candidate pairs, lookups, N, U"}
+
+
+def cpu_baseline_leg(w, k, name, local):
+    """The unmodified reference on a bounded sub-index + the engine on the same sub-index, digest-compared live."""
+    from oracle import refjni
+    from pandelos_b200 import digest, native
+    if not refjni.available():
+        return None
+    threads = os.cpu_count() or 1
+    big = name == "scaleout1000"
+    sub = w.subset_genomes(CPU_SUBINDEX_GENOMES) if big else w
+    gold = golden("scaleout1000_first80") if big else golden(name)
+    ref = refjni.RefJni()
+    t_pre = ref.preprocess(sub.residues, sub.offsets, sub.genome_of, k)
+    t_sc, per = ref.compute_scores_list(list(range(sub.G)), min(threads, sub.G))
+    pn = native.PangeneNative(k, native.PangeneIData(sub.residues, sub.offsets, sub.genome_of), device=local)
+    sp = pn.score_partition_device(0, sub.S)
+    check = list(range(0, sub.G, max(1, sub.G // 8)))[:8]
+    bad = [g for g in check if digest.scores_digest(pn.generateScoresPart(g)) != digest.scores_digest(ref.compute_scores(g))]
+    ok = not bad and int(per.sum()) == int(sp.cells)
+    if gold is not None:
+        ok = ok and gold_total(gold, "pairs") == int(sp.pairs) and gold_total(gold, "cells") == int(sp.cells) and gold["total_cost"] == int(pn.info.lookups)
+    tt = t_pre + t_sc
+    out = {"value": sp.pairs / tt, "unit": "pairs/s", "cores": min(threads, sub.G), "kind": "reference",
+           "sample": "%s of %s (%d genes, k=%d, %d lookups): preprocess (1 thread) %.2fs + computeScores of all its genomes (%d threads) %.2fs; "
+                     "scoring only %.3g lookups/s" % ("sub-index of the first %d genomes" % sub.G if big else "the whole index", name, sub.S, k,
+                                                       pn.info.lookups, t_pre, min(threads, sub.G), t_sc, pn.info.lookups / max(t_sc, 1e-9)),
+           "parity_checked": True, "parity_ok": bool(ok),
+           "parity": "engine vs the unmodified library.cpp on this sub-index: Scores digests of genomes %s, total cells%s" % (
+               check, ", pairs / cells / Total cost vs tests/golden/digests" if gold is not None else "")}
+    pn.close()
+    return out, ok
+
+
+def small_config_line(name, local, dev, steps=3, warmup=2):
+    """One bench line for a CPU-runnable config (whole job on one GPU) + its parity against the reference goldens."""
+    import torch
+    from pandelos_b200 import native
+    w, k = make_workload(name)
+    gold = golden(name)
+    data = native.PangeneIData(w.residues, w.offsets, w.genome_of)
+    res_host = torch.from_numpy(w.residues).pin_memory()
+    res_dev = res_host.to(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms, kms, st, info = [], [], None, None
+    for i in range(warmup + steps):
+        torch.cuda.synchronize()
+        ev0.record()
+        pn = native.PangeneNative(k, data, device=local, residues_device_ptr=res_dev.data_ptr())
+        st = pn.score_partition_device(0, w.S)
+        ev1.record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ms.append(ev0.elapsed_time(ev1))
+            kms.append(st.kernel_ms)
+        info = pn.info
+        pn.close()
+    # e2e: host buffers in, every Scores array out, one call per genome
+    data_pinned = native.PangeneIData(res_host.numpy(), w.offsets, w.genome_of)
+    e_ms = []
+    for i in range(1 + steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pn = native.PangeneNative(k, data_pinned, device=local)
+        for g in range(w.G):
+            stt, rel = pn.compute_scores_raw(g)
+            rel()
+        if i:
+            e_ms.append((time.perf_counter() - t0) * 1e3)
+        pn.close()
+    line = {"value": st.pairs / (np.mean(ms) * 1e-3), "unit": "pairs/s", "ms_per_step": float(np.mean(ms)), "k": int(k), "genes": int(w.S),
+            "genomes": int(w.G), "kmers": int(info.N), "lookups": int(info.lookups), "pairs": int(st.pairs), "cells": int(st.cells),
+            "build_ms": float(info.build_ms[5]), "score_kernel_ms": float(np.mean(kms)),
+            "e2e": {"value": st.pairs / (np.mean(e_ms) * 1e-3), "unit": "pairs/s", "ms_per_step": float(np.mean(e_ms))}}
+    ok = True
+    if gold is not None:
+        pn = native.PangeneNative(k, data, device=local)
+        ok, det = parity_against_golden(pn, gold, list(range(w.G)), "tests/golden/digests/%s.json (unmodified library.cpp)" % name)
+        ok = ok and int(st.pairs) == gold_total(gold, "pairs") and int(st.cells) == gold_total(gold, "cells")
+        pn.close()
+        line["parity_checked"], line["parity_ok"] = True, bool(ok)
+    else:
+        line["parity_checked"] = False
+    return line, ok
+
+
+# ------------------------------------------------------------------------------------------------ the b200 arm
 
 def main():
     ap = argparse.ArgumentParser()
@@ -229,9 +401,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--query-genomes", type=int, default=0, help="genomes scored per rank (0 = workload default)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--exchange", default="none", choices=["none", "allgather"], help="best-hit slices between ranks (strong scaling)")
+    ap.add_argument("--query-genomes", type=int, default=0, help="--scaling weak: genomes scored per rank (0 = workload default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library
     # chatter) is sent to stderr, and the JSON line goes to the saved descriptor
@@ -266,24 +442,30 @@ def main():
 
     from pandelos_b200 import multigpu
     name = args.workload
+    strong = args.scaling == "strong"
     w, k = make_workload(name)
+    cfg = job_config(name, w, k)
     gb = multigpu.genome_bounds(w.genome_of, w.G)
-    q = args.query_genomes or QUERY_GENOMES.get(name) or w.G
-    q = min(q, w.G)
-    if world * q > w.G:
-        q = max(1, w.G // world)
+    if strong:
+        job_genomes = w.G
+    else:
+        q = args.query_genomes or WEAK_QUERY_GENOMES.get(name) or w.G
+        q = min(q, w.G)
+        if world * q > w.G:
+            q = max(1, w.G // world)
+        job_genomes = world * q
     # the O(S) gene table (offsets, genome ids) in pinned host memory: it is re-sent with every index build
     off_pin = torch.from_numpy(w.offsets.astype(np.int64)).pin_memory()
     gid_pin = torch.from_numpy(w.genome_of.astype(np.int32)).pin_memory()
     data = native.PangeneIData(w.residues, off_pin.numpy().view(np.uint64), gid_pin.numpy().view(np.uint32))
-    # the job's query genes = the first world x q genomes, split by posting-list volume at genome boundaries
+    # the job's query genes, split by posting-list volume at genome boundaries
     if world > 1:
         pn0 = native.PangeneNative(k, data, device=local)
         _, visited = pn0.gene_stats()
         pn0.close()
-        bounds = multigpu.balanced_bounds(visited, 0, int(gb[world * q]), world, snap=gb)
+        bounds = multigpu.balanced_bounds(visited, 0, int(gb[job_genomes]), world, snap=gb)
     else:
-        bounds = np.array([0, int(gb[q])], np.int64)
+        bounds = np.array([0, int(gb[job_genomes])], np.int64)
     row0, row1 = int(bounds[rank]), int(bounds[rank + 1])
     g0, g1 = int(np.searchsorted(gb, row0)), int(np.searchsorted(gb, row1))
 
@@ -294,13 +476,13 @@ def main():
 
     G = w.G
     rows_of_rank = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
+    exchange = world > 1 and (args.exchange == "allgather" or not strong)
     gather = None
-    if world > 1:
+    bh_local = None
+    if exchange:
         # best-hit slices are all-gathered chunk by chunk behind the scoring of the next chunk (multigpu.py)
         gather = multigpu.ChunkedBestHitGather(dist, rows_of_rank, G, dev, chunks=max(1, -(-max(rows_of_rank) // 65536)))
-        bh_local = gather.local
-    else:
-        bh_local = torch.zeros((max(rows_of_rank), G), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
 
     host_ms = [0.0, 0.0]  # wall clock of the last step's two calls (log only)
 
@@ -318,7 +500,8 @@ def main():
         if gather is not None:
             st = Stats(multigpu.score_and_gather(pn, gather, rank, row0))
         else:
-            st = pn.score_partition_device(row0, row1, best_hit_ptr=bh_local.data_ptr())
+            # best hits stay in the engine's own table (served per genome by pd_compute_scores / pd_genome_edges)
+            st = pn.score_partition_device(row0, row1)
         host_ms[0], host_ms[1] = (t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3
         return pn, st
 
@@ -382,18 +565,49 @@ def main():
     achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
     # DRAM traffic of the dominant kernel: one `ncu --set full` capture of its largest launch, committed under profiles/
     traffic, traffic_launch = None, None
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_score_traffic.json")
-    if args.workload == "scaleout1000" and os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        traffic = tj["dram_bytes"]
-        traffic_launch = {"launch": tj["launch"], "algorithmic_bytes": tj["block_algorithmic_bytes"],
-                          "traffic_over_algorithmic": tj["traffic_over_algorithmic"], "source": tj["source"]}
+    for tname in ("r02_score_traffic.json", "r01_score_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if args.workload == "scaleout1000" and os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes"]
+            traffic_launch = {"launch": tj["launch"], "algorithmic_bytes": tj["block_algorithmic_bytes"],
+                              "traffic_over_algorithmic": tj["traffic_over_algorithmic"], "source": tj["source"]}
+            break
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_launch": traffic_launch,
                 "bytes_per_lookup_model": 8, "bytes_per_lookup_read": 4,
                 "kernel": "score_rows_kernel", "kernel_ms_per_step": kms, "peak_kind": peak_kind,
+                "launches_per_step": int(stats["launches"]),
                 "lookups_per_s": stats["lookups"] / (kms * 1e-3) if kms > 0 else 0.0}
+
+    # ---- parity on the timed index: the reference arm's sample genomes that this rank owns, against the goldens
+    parity, parity_ok = None, True
+    if not args.no_parity:
+        gold = golden(name + "_sample") if name == "scaleout1000" else golden(name)
+        if gold is not None:
+            mine = [g for g in (sample_order(gold) if name == "scaleout1000" else sorted(int(x) for x in gold["per_genome"])) if g0 <= g < g1]
+            mine = mine[:max(1, 8 // world)] if name == "scaleout1000" else mine
+            pn = native.PangeneNative(k, data, device=local, residues_device_ptr=res_dev.data_ptr())
+            parity_ok, parity = parity_against_golden(pn, gold, mine, "tests/golden/digests/%s.json (%s)" % (
+                name + "_sample" if name == "scaleout1000" else name, gold.get("oracle", "unmodified library.cpp")))
+            pn.close()
+            if strong:
+                tot_ok = int(lookups_all) == gold["total_cost"] and (gold_total(gold, "pairs") is None or int(pairs_all) == gold_total(gold, "pairs"))
+                parity_ok = parity_ok and tot_ok
+                parity["job_lookups_match_total_cost"] = bool(int(lookups_all) == gold["total_cost"])
+            tp = torch.tensor([1.0 if parity_ok else 0.0, float(len(mine))], dtype=torch.float64, device=dev)
+            if world > 1:
+                tmin = tp.clone()
+                dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+                dist.all_reduce(tp, op=dist.ReduceOp.SUM)
+                parity_ok = bool(tmin[0].item() > 0.5)
+                parity["genomes_checked_all_ranks"] = int(tp[1].item())
+            parity["checked"], parity["ok"] = True, bool(parity_ok)
+            if rank == 0:
+                log("[bench] parity on the timed index: %s" % ("ok" if parity_ok else "MISMATCH"), parity)
+        else:
+            parity = {"checked": False, "why": "no golden file for %s" % name}
 
     # ---- e2e through the C ABI with host buffers (this rank's query genomes), max over ranks
     e2e = None
@@ -415,7 +629,8 @@ def main():
             rel()
             return nbytes, ss.pairs
 
-        E2E_WARM = 2  # untimed passes: every score context has to have met a large genome before the timed ones
+        E2E_WARM = 1  # untimed: the first pass of a process grows the pinned / device result buffers (reported as cold_ms)
+        cold_ms = None
         for i in range(E2E_WARM + e2e_steps):
             barrier()
             t0 = time.perf_counter()
@@ -426,22 +641,26 @@ def main():
             d2h = sum(r[0] for r in res_g)
             pairs_e = sum(r[1] for r in res_g)
             barrier()
+            dt = (time.perf_counter() - t0) * 1e3
             if i >= E2E_WARM:
-                e2e_ms.append((time.perf_counter() - t0) * 1e3)
+                e2e_ms.append(dt)
+            elif i == 0:
+                cold_ms = dt
             if rank == 0:
-                log("[bench] e2e pass %d: %.1f ms%s" % (i, (time.perf_counter() - t0) * 1e3, " (untimed)" if i < E2E_WARM else ""))
+                log("[bench] e2e pass %d: %.1f ms%s" % (i, dt, " (untimed, cold)" if i < E2E_WARM else ""))
             pn.close()
-        te = torch.tensor([float(np.mean(e2e_ms)), float(pairs_e)], dtype=torch.float64, device=dev)
+        te = torch.tensor([float(np.mean(e2e_ms)), float(pairs_e), float(cold_ms), float(d2h)], dtype=torch.float64, device=dev)
         if world > 1:
             tm = te.clone()
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             ts = te.clone()
             dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-            e_ms, e_pairs = float(tm[0].item()), float(ts[1].item())
+            e_ms, e_pairs, cold_ms, d2h_all = float(tm[0].item()), float(ts[1].item()), float(tm[2].item()), float(ts[3].item())
         else:
-            e_ms, e_pairs = float(te[0].item()), float(te[1].item())
+            e_ms, e_pairs, d2h_all = float(te[0].item()), float(te[1].item()), float(d2h)
         e2e = {"value": e_pairs / (e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e_ms, "call": "pd_build + pd_compute_scores per genome (the JNI boundary), %d host threads" % E2E_THREADS}
+               "d2h_bytes_per_step_all_ranks": int(d2h_all), "ms_per_step": e_ms, "cold_ms": cold_ms,
+               "call": "pd_build + pd_compute_scores per genome (the JNI boundary), %d host threads" % E2E_THREADS}
 
         # the same step through the native-CLI call path: pd_genome_edges runs the Java host's BBH filter on the device,
         # so only network edges come back (reported next to e2e, not instead of it)
@@ -475,35 +694,41 @@ def main():
                                "call": "pd_build + pd_genome_edges per genome (native pangenes CLI path), %d host threads" % E2E_THREADS}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        res = cpu_reference_sample(w, k, name, threads)
-        if res is not None:
-            sub = res["sample"]
-            pn = native.PangeneNative(k, native.PangeneIData(sub.residues, sub.offsets, sub.genome_of), device=local)
-            sp = pn.score_partition_device(0, sub.S)
-            tt = res["preprocess_s"] + res["scores_s"]
-            cpu = {"value": sp.pairs / tt, "unit": "pairs/s", "cores": threads, "kind": "reference",
-                   "sample": "first %d of %d genomes of %s (%d genes, k=%d, %d lookups): preprocess (1 thread) %.2fs + computeScores (%d threads) %.2fs; "
-                             "scoring only %.3g lookups/s" % (res["genomes"], w.G, name, sub.S, k, pn.info.lookups, res["preprocess_s"], threads,
-                                                               res["scores_s"], pn.info.lookups / max(res["scores_s"], 1e-9))}
-            pn.close()
+    others = None
+    if rank == 0 and world == 1:
+        if not args.no_cpu_baseline:
+            r = cpu_baseline_leg(w, k, name, local)
+            if r is not None:
+                cpu, ok = r
+                parity_ok = parity_ok and ok
+        if not args.no_other_configs and name == "scaleout1000":
+            others = {}
+            for cname in SMALL_CONFIGS:
+                line, ok = small_config_line(cname, local, dev)
+                others[cname] = line
+                parity_ok = parity_ok and ok
 
     if rank == 0:
+        step_desc = "index build from HBM-resident residues + scoring of the rank's query rows (cells left in HBM)"
+        if gather is not None:
+            step_desc += ", NCCL allgather of the best-hit slices chunk by chunk behind the scoring"
         out = {"metric": "gene-pair Jaccard scores/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "int32+f32", "data": "synthetic",
-               "config": {"workload": name, "k": int(k), "genes": int(w.S), "genomes": int(G), "kmers": int(info.N),
-                          "query_genomes_per_rank": int(q), "query_rows_per_rank": int(rows_n), "query_genomes_this_rank": [g0, g1],
-                          "parallelism": "index replicated, query genomes split by posting-list volume" if world > 1 else "single GPU",
-                          "l2": "flushed between timed steps (256 MiB fill)",
-                          "step": "index build from HBM-resident residues + scoring of the rank's query rows" + (", NCCL allgather of the best-hit slices chunk by chunk behind the scoring" if world > 1 else "")},
+               "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+               "dtype": "int32+f32", "data": "synthetic", "config": cfg,
+               "run": {"query_genomes": int(job_genomes), "query_rows_this_rank": int(rows_n), "query_genomes_this_rank": [g0, g1],
+                       "parallelism": ("index replicated, query genomes split by posting-list volume at genome boundaries; best-hit exchange: %s" %
+                                       ("NCCL all-gather" if gather is not None else "none needed (every genome on one rank)")) if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps (256 MiB fill)", "step": step_desc},
                "lookups_per_s": lookups_all / (ms * 1e-3), "cells_per_step": cells_all, "pairs_per_step": pairs_all,
                "build_ms_per_step": build_ms / args.steps, "score_kernel_ms_per_step": kms,
-               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+               "roofline": roofline, "parity": parity, "parity_checked": bool(parity and parity.get("checked")), "parity_ok": bool(parity_ok),
+               "cpu_baseline": cpu, "e2e": e2e, "other_configs": others, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    if not parity_ok:
+        log("[bench] PARITY MISMATCH: the numbers above are void")
+        return 3
     return 0
 
 

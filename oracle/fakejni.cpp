@@ -420,4 +420,32 @@ double fj_compute_scores_pool(void* lib, int g_begin, int g_end, int threads, in
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// The same over an explicit genome list (bench.py's reference arm: a fixed sample of genomes of the full index);
+// per_genome_cells[i] (may be null) receives scoresCount of genomes[i].
+double fj_compute_scores_list(void* lib, const int* genomes, int n, int threads, int quiet, int64_t* cells_out, int64_t* per_genome_cells) {
+    Lib* l = static_cast<Lib*>(lib);
+    std::atomic<int> next(0);
+    std::atomic<int64_t> cells(0);
+    Quiet q(quiet != 0);
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) {
+        pool.emplace_back([&]() {
+            for (;;) {
+                int i = next.fetch_add(1);
+                if (i >= n) break;
+                Obj* sc = run_scores(l, genomes[i]);
+                const int64_t c = sc->ifields["scoresCount"];
+                cells.fetch_add(c);
+                if (per_genome_cells) per_genome_cells[i] = c;
+                free_scores_obj(sc);
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    auto t1 = std::chrono::steady_clock::now();
+    if (cells_out) *cells_out = cells.load();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
 }  // extern "C"

@@ -50,6 +50,8 @@ def fj():
         L.fj_scores_free.argtypes = [C.POINTER(ScoresStruct)]
         L.fj_compute_scores_pool.restype = C.c_double
         L.fj_compute_scores_pool.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+        L.fj_compute_scores_list.restype = C.c_double
+        L.fj_compute_scores_list.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_void_p]
         _fj = L
     return _fj
 
@@ -84,3 +86,11 @@ class RefJni:
         cells = C.c_int64(0)
         t = fj().fj_compute_scores_pool(self._lib, int(g_begin), int(g_end), int(threads), int(quiet), C.byref(cells))
         return t, cells.value
+
+    def compute_scores_list(self, genomes, threads, quiet=True):
+        """The same pool over an explicit list of genomes; returns (wall seconds, cells per genome as int64[])."""
+        gl = np.ascontiguousarray(genomes, dtype=np.int32)
+        per = np.zeros(len(gl), np.int64)
+        cells = C.c_int64(0)
+        t = fj().fj_compute_scores_list(self._lib, gl.ctypes.data, len(gl), int(threads), int(quiet), C.byref(cells), per.ctypes.data)
+        return t, per

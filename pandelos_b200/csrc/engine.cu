@@ -19,6 +19,7 @@
 #include "index_kernels.cuh"
 #include "prims.cuh"
 #include "score_kernels.cuh"
+#include "sort_kernels.cuh"
 
 namespace pd {
 
@@ -361,7 +362,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     }
     const int rank_bits = std::max(1, bits_for((uint64_t)pw - 1));
     const int seq_bits = std::max(1, bits_for(S ? (uint64_t)S - 1 : 0));
-    if (rank_bits + seq_bits > 64) throw Error(PD_ERR_UNSUPPORTED, "k-mer rank and gene id do not fit one 64-bit sort key");
+    if (rank_bits + seq_bits > 63) throw Error(PD_ERR_UNSUPPORTED, "k-mer rank and gene id do not fit one 64-bit sort key");
     info.rank_bits = rank_bits;
     info.seq_bits = seq_bits;
 
@@ -377,22 +378,70 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     unsigned long long lookups = 0;
 
     if (N > 0) {
-        // ---- encode (library.cpp:234-265)
-        t_enc.start();
+        // ---- k-mer keys + sort by rank in one sweep per digit (library.cpp:234-265, 270-278): the keys are made from the
+        // residues twice (digit counts, first pass) instead of being written and re-read in gene order; stability keeps
+        // genes ascending inside a rank
         rt::DevBuf<uint64_t> keys_a(N), keys_b(N);
+        const uint32_t stiles = sortk::tiles_of(N);
+        const int passes = sortk::passes_of(rank_bits);
+        rt::DevBuf<uint32_t> tile_gene((size_t)stiles + 1), sort_ctl((size_t)2 * passes * sortk::kRadix + 32);
+        rt::DevBuf<uint32_t> sort_status((size_t)passes * stiles * sortk::kRadix);
+        uint64_t* sorted = nullptr;
         {
-            unsigned grid = std::min<uint64_t>((uint64_t)sms * 16, ((uint64_t)S + 7) / 8);
-            PD_LAUNCH(ik::encode_kernel, std::max(1u, grid), 256, 0, st, d_res, (const uint64_t*)d_gene_off.p,
-                      (const uint32_t*)d_key_off.p, S, (int)k, base, seq_bits, vt, keys_a.p);
-            launches++;
-        }
-        t_enc.stop();
+            t_enc.start();
+            uint32_t* d_hist = sort_ctl.p;
+            uint32_t* d_bins = d_hist + passes * sortk::kRadix;
+            uint32_t* d_tot = d_bins + passes * sortk::kRadix;  // [0] keys kept, [8 + p] tile tickets
+            rt::zero(sort_ctl.p, sort_ctl.bytes(), st);
+            rt::zero(sort_status.p, sort_status.bytes(), st);
+            PD_LAUNCH(sortk::tile_gene_kernel, blocks_for(std::max<uint32_t>(S, 1)), 256, 0, st, (const uint32_t*)d_key_off.p, S, stiles, tile_gene.p);
+            sortk::EncodeSrc es;
+            memset(&es, 0, sizeof(es));
+            es.res = d_res;
+            es.gene_off = d_gene_off.p;
+            es.key_off = d_key_off.p;
+            es.tile_gene = tile_gene.p;
+            es.S = S;
+            es.k = (int)k;
+            es.base = base;
+            es.mult = (uint64_t)(pw / (base ? base : 1));
+            es.seq_bits = seq_bits;
+            es.lo = 0;
+            es.hi = 1ull << 63;
+            es.N = N;
+            es.vt = vt;
+            const bool r32 = rank_bits <= 32;
+            const unsigned hgrid = std::min<uint32_t>(stiles, (uint32_t)sms * 8);
+            if (r32) PD_LAUNCH(sortk::kmer_hist_kernel<uint32_t>, hgrid, sortk::kThreads, 0, st, es, stiles, passes, d_hist);
+            else PD_LAUNCH(sortk::kmer_hist_kernel<uint64_t>, hgrid, sortk::kThreads, 0, st, es, stiles, passes, d_hist);
+            PD_LAUNCH(sortk::digit_bins_kernel, 1, sortk::kRadix, 0, st, (const uint32_t*)d_hist, passes, d_bins, d_tot);
+            launches += 3;
+            t_enc.stop();
 
-        // ---- sort by rank; stability keeps genes ascending inside a rank (library.cpp:270-278)
-        t_sort.start();
-        scratch.ensure(prims::radix_tmp_words(N) + 16);
-        uint64_t* sorted = prims::radix_sort_u64(keys_a.p, keys_b.p, N, seq_bits, seq_bits + rank_bits, scratch.p, st, &launches);
-        t_sort.stop();
+            t_sort.start();
+            const size_t smem = sortk::sweep_smem_bytes();
+            uint64_t* src = nullptr;
+            uint64_t* dst = keys_a.p;
+            for (int p = 0; p < passes; p++) {
+                sortk::SweepArgs sa;
+                sa.keys = src;
+                sa.out = dst;
+                sa.n = N;
+                sa.shift = seq_bits + 8 * p;
+                sa.bins = d_bins + p * sortk::kRadix;
+                sa.status = sort_status.p + (size_t)p * stiles * sortk::kRadix;
+                sa.counter = d_tot + 8 + p;
+                void (*kfn)(sortk::SweepArgs, sortk::EncodeSrc) = sortk::onesweep_kernel<0, uint32_t>;
+                if (p == 0) kfn = r32 ? sortk::onesweep_kernel<1, uint32_t> : sortk::onesweep_kernel<1, uint64_t>;
+                rt::allow_smem(kfn, smem);
+                PD_LAUNCH(kfn, stiles, sortk::kThreads, smem, st, sa, es);
+                launches++;
+                src = dst;
+                dst = (dst == keys_a.p) ? keys_b.p : keys_a.p;
+            }
+            sorted = src;
+            t_sort.stop();
+        }
 
         // ---- count dedup (library.cpp:280-287) and rank groups incl. the tail merge (library.cpp:297-306)
         t_grp.start();
