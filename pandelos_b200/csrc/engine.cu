@@ -813,6 +813,22 @@ void launch_rows(ScoreContext& c, sk::ScoreArgs a, const Level& lv, int cursor_i
         a.hmul = (uint32_t)std::min<uint64_t>(((1ull << lv.hbits) << 32) / S, 0xFFFFFFFFull);
         a.t1mul = (uint32_t)std::min<uint64_t>(((uint64_t)lv.t1 << 32) / S, 0xFFFFFFFFull);
     }
+    {   // bank spread of tier 1 (score_kernels.cuh, t1_slot): with many genomes, rotate so that the bank is ~ the genome number
+        a.t1rot = 0;
+        a.t1hi = 31;
+        const uint32_t lg = log2_floor(lv.t1), G = c.ix->info.G;
+        if ((1u << lg) == lv.t1) {
+            uint32_t gbits = 0;
+            while ((1u << gbits) < G) gbits++;
+            uint32_t rot = (G >= 512 && lg > gbits) ? lg - gbits : 0;
+            static const char* const e = getenv("PD_T1ROT");  // tuning
+            if (e) rot = std::min<uint32_t>((uint32_t)atoi(e), lg > 5 ? lg - 5 : 0);
+            if (rot) {
+                a.t1rot = rot;
+                a.t1hi = lg - rot;
+            }
+        }
+    }
     a.fcap = lv.fcap;
     a.cursor = c.d_cursors.p + cursor_id;
     const size_t smem = sk::score_smem_bytes(lv.t1, lv.hbits, lv.fcap, lv.threads);

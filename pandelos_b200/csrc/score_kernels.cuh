@@ -82,6 +82,8 @@ struct ScoreArgs {
     uint32_t nslots;  // T1 + H
     uint32_t t1;      // tier-1 slots (a multiple of 32)
     uint32_t t1mul;   // tier-1 slot of column c = floor(c * T1 / S) = umulhi(c, t1mul): ORDER PRESERVING on purpose, see Tab
+    uint32_t t1rot;   // ... rotated right by t1rot bits inside its log2(T1) bits (0: not rotated), see t1_slot
+    uint32_t t1hi;    // log2(T1) - t1rot
     uint32_t fcap;    // forward entries staged per segment
     // outputs
     float* o_score;
@@ -226,7 +228,15 @@ __device__ __forceinline__ XTab xtab_of(const ScoreArgs& a, const Tab& t) {
 }
 
 // (clamped: kNone items, which are never counted, still compute an address)
-__device__ __forceinline__ uint32_t t1_slot(const ScoreArgs& a, uint32_t c) { return min(__umulhi(c, a.t1mul), a.t1 - 1); }
+// The order-preserving tier-1 index floor(c * T1 / S) is rotated right by `t1rot` bits inside its log2(T1) bits (a
+// bijection on the slots: nothing changes for collisions).  The lanes of a warp hold consecutive postings of a list,
+// for a conserved k-mer one homolog per genome: with 2^(log2 T1 - t1rot) ~ G the low bits of the rotated slot — the
+// bank — are the (approximate) genome number, consecutive across the lanes, instead of the random low bits of
+// c * T1 / S: the 4-byte key loads and the counter atomics of a round spread over the 32 banks.
+__device__ __forceinline__ uint32_t t1_slot(const ScoreArgs& a, uint32_t c) {
+    const uint32_t s = min(__umulhi(c, a.t1mul), a.t1 - 1);
+    return (s >> a.t1rot) | ((s << a.t1hi) & (a.t1 - 1));
+}
 __device__ __forceinline__ uint32_t t2_home(const ScoreArgs& a, uint32_t c) { return min(__umulhi(c, a.hmul), a.hmask); }
 
 __device__ __forceinline__ uint32_t x_find_or_insert(const XTab& x, uint32_t c) {
@@ -279,11 +289,12 @@ struct GenArgs {
     saddr_t keys_sa;
     RowCtl* ctl;
     uint32_t* xbase;
-    uint32_t t1, t1mul, hmask, hmul, plimit, nslots;
+    uint32_t t1, t1mul, t1rot, t1hi, hmask, hmul, plimit, nslots;
 };
 __device__ __noinline__ void add_general(const GenArgs g, uint32_t c, uint32_t n, uint32_t m) {
     // the slot of column c in either tier (claimed if new)
     uint32_t h = min(__umulhi(c, g.t1mul), g.t1 - 1);
+    h = (h >> g.t1rot) | ((h << g.t1hi) & (g.t1 - 1));
     {
         const saddr_t a1 = g.keys_sa + h * 4u;
         uint32_t k = lds_u32(a1);
@@ -335,6 +346,8 @@ __device__ __forceinline__ GenArgs gen_args(const ScoreArgs& a, const Tab& t) {
     g.xbase = a.xtab + (size_t)blockIdx.x * (5 * kXSlots);
     g.t1 = a.t1;
     g.t1mul = a.t1mul;
+    g.t1rot = a.t1rot;
+    g.t1hi = a.t1hi;
     g.hmask = a.hmask;
     g.hmul = a.hmul;
     g.plimit = a.plimit;
@@ -344,12 +357,15 @@ __device__ __forceinline__ GenArgs gen_args(const ScoreArgs& a, const Tab& t) {
 
 // ---- accumulate, the common case: postings with n = m = 1.  One "item" is one posting per lane (kNone: none).
 //
-// Per-warp queue of the postings that missed tier 1: a ring of kQueue words; the tail lives in shared memory (lanes
-// push on their own, one shared atomic each), the head in a register (drains are warp-wide).
+// A posting whose tier-1 slot does not hold its column (a few per cent of them: first touches, second paralogs, chance
+// hits) is NOT handled where it is found — that would be a divergent branch with one or two lanes active in almost every
+// round.  It goes to a per-warp ring of kQueue words: the missing lanes are compacted with one ballot (slot = tail +
+// rank of the lane among the missing ones), head and tail live in warp-uniform registers, no atomic, no shared-memory
+// control word.  As soon as 32 are queued they are resolved together, every lane busy: claim the tier-1 slot if it is
+// still free, count there if the column owns it, else probe / insert into tier 2.
 struct WarpQueue {
     uint32_t* q;
-    uint32_t* tail;
-    uint32_t head;
+    uint32_t head, tail;  // warp-uniform
 };
 
 __device__ __forceinline__ void queue_drain32(const ScoreArgs& a, const Tab& t, WarpQueue& wq, uint32_t n) {  // n queued (uniform)
@@ -357,30 +373,25 @@ __device__ __forceinline__ void queue_drain32(const ScoreArgs& a, const Tab& t, 
     const uint32_t cur = lane < n ? wq.q[(wq.head + lane) & (kQueue - 1)] : kNone;
     wq.head += n < 32u ? n : 32u;
     if (cur != kNone) {
-        const uint32_t h = t2_find_or_insert(a, t, cur);
-        if (h != kEmpty) reds_inc(cnt_sa(a, t) + h * 4u);
+        const uint32_t s1 = t1_slot(a, cur);
+        const saddr_t a1 = t.keys_sa + s1 * 4u;
+        uint32_t k1 = lds_u32(a1);
+        if (k1 == kEmpty) {
+            const uint32_t old = atoms_cas(a1, kEmpty, cur);
+            k1 = (old == kEmpty) ? cur : old;
+        }
+        if (k1 == cur) {
+            reds_inc(cnt_sa(a, t) + s1 * 4u);
+        } else {
+            const uint32_t h = t2_find_or_insert(a, t, cur);
+            if (h != kEmpty) reds_inc(cnt_sa(a, t) + h * 4u);
+        }
     }
     __syncwarp();
 }
 __device__ __forceinline__ void queue_flush(const ScoreArgs& a, const Tab& t, WarpQueue& wq) {
     __syncwarp();
-    for (;;) {
-        const uint32_t n = *(volatile uint32_t*)wq.tail - wq.head;
-        if (n == 0) break;
-        queue_drain32(a, t, wq, n);
-    }
-}
-
-// a posting that did not find its column in tier 1: claim the slot if it is free, else queue for tier 2
-__device__ __forceinline__ void item_miss(const ScoreArgs& a, const Tab& t, WarpQueue& wq, uint32_t c, uint32_t s1, uint32_t k1) {
-    if (k1 == kEmpty) {
-        const uint32_t old = atoms_cas(t.keys_sa + s1 * 4u, kEmpty, c);
-        if (old == kEmpty || old == c) {
-            reds_inc(cnt_sa(a, t) + s1 * 4u);
-            return;
-        }
-    }
-    wq.q[atomicAdd(wq.tail, 1u) & (kQueue - 1)] = c;
+    while (wq.tail != wq.head) queue_drain32(a, t, wq, wq.tail - wq.head);
 }
 
 // two items at a time: both tier-1 loads are in flight before either is compared
@@ -394,17 +405,17 @@ __device__ __forceinline__ void items_add2(const ScoreArgs& a, const Tab& t, War
     const bool hit0 = k0 == c0, hit1 = k1 == c1;  // kNone is never a key: no hit
     if (hit0) reds_inc(cnt_sa(a, t) + s0 * 4u);
     if (hit1) reds_inc(cnt_sa(a, t) + s1 * 4u);
-    const bool miss0 = !hit0 && c0 != kNone, miss1 = !hit1 && c1 != kNone;
-    if (__any_sync(0xffffffffu, miss0 | miss1)) {
-        if (miss0) item_miss(a, t, wq, c0, s0, k0);
-        if (miss1) item_miss(a, t, wq, c1, s1, k1);
+    const unsigned m0 = __ballot_sync(0xffffffffu, !hit0 && c0 != kNone);
+    const unsigned m1 = __ballot_sync(0xffffffffu, !hit1 && c1 != kNone);
+    if (m0 | m1) {  // uniform
+        const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+        if ((m0 >> (threadIdx.x & 31)) & 1u) wq.q[(wq.tail + __popc(m0 & lt)) & (kQueue - 1)] = c0;
+        wq.tail += __popc(m0);
+        if ((m1 >> (threadIdx.x & 31)) & 1u) wq.q[(wq.tail + __popc(m1 & lt)) & (kQueue - 1)] = c1;
+        wq.tail += __popc(m1);
         __syncwarp();
         // at most 31 entries stay queued between calls, a call adds at most 64: the ring (kQueue = 128) never laps
-        for (;;) {
-            const uint32_t n = *(volatile uint32_t*)wq.tail - wq.head;
-            if (n < 32u) break;
-            queue_drain32(a, t, wq, n);
-        }
+        while (wq.tail - wq.head >= 32u) queue_drain32(a, t, wq, wq.tail - wq.head);
     }
 }
 
@@ -460,10 +471,7 @@ __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t, con
     WarpScratch& ws = ws_all[warp];
     WarpQueue wq;
     wq.q = ws.queue;
-    wq.tail = &ws.qtail;
-    wq.head = 0;
-    if (lane == 0) ws.qtail = 0;
-    __syncwarp();
+    wq.head = wq.tail = 0;
     const unsigned le = 0xffffffffu >> (31 - lane);  // lanes <= mine
     // ---- long lists: one warp per list
     {
