@@ -50,7 +50,6 @@ static const uint32_t kNone = 0x7FFFFFFFu;      // "no posting" in a lane's item
 #endif
 static const int kItems = PD_KITEMS;            // postings per lane per round of a long list
 static const int kItemsA = 4;                   // ... of the flattened short lists
-static const uint32_t kQueue = 128;             // per-warp ring of postings that missed tier 1
 static const int kDenseThreads = 256;
 
 struct __align__(16) RowDesc {  // 32 B, built on the host per call
@@ -81,9 +80,9 @@ struct ScoreArgs {
     uint32_t plimit;  // tier-2 probe limit
     uint32_t nslots;  // T1 + H
     uint32_t t1;      // tier-1 slots (a multiple of 32)
-    uint32_t t1mul;   // tier-1 slot of column c = floor(c * T1 / S) = umulhi(c, t1mul): ORDER PRESERVING on purpose, see Tab
-    uint32_t t1rot;   // ... rotated right by t1rot bits inside its log2(T1) bits (0: not rotated), see t1_slot
-    uint32_t t1hi;    // log2(T1) - t1rot
+    uint32_t t1mul;   // floor(2^32 * (T1 >> t1rot) / S): tier-1 slot of column c from the 64-bit product c * t1mul, see t1_slot_of
+    uint32_t t1rot;   // bits the order-preserving slot index is rotated by (0: not rotated)
+    uint32_t t1hi;    // log2(T1) - t1rot (with t1rot = 0: unused)
     uint32_t fcap;    // forward entries staged per segment
     // outputs
     float* o_score;
@@ -227,16 +226,23 @@ __device__ __forceinline__ XTab xtab_of(const ScoreArgs& a, const Tab& t) {
     return x;
 }
 
-// (clamped: kNone items, which are never counted, still compute an address)
-// The order-preserving tier-1 index floor(c * T1 / S) is rotated right by `t1rot` bits inside its log2(T1) bits (a
-// bijection on the slots: nothing changes for collisions).  The lanes of a warp hold consecutive postings of a list,
-// for a conserved k-mer one homolog per genome: with 2^(log2 T1 - t1rot) ~ G the low bits of the rotated slot — the
-// bank — are the (approximate) genome number, consecutive across the lanes, instead of the random low bits of
-// c * T1 / S: the 4-byte key loads and the counter atomics of a round spread over the 32 banks.
-__device__ __forceinline__ uint32_t t1_slot(const ScoreArgs& a, uint32_t c) {
-    const uint32_t s = min(__umulhi(c, a.t1mul), a.t1 - 1);
-    return (s >> a.t1rot) | ((s << a.t1hi) & (a.t1 - 1));
+// Tier-1 slot of column c.  The order-preserving index floor(c * T1 / S) is used ROTATED right by `t1rot` bits inside its
+// log2(T1) bits (a bijection on the slots: nothing changes for collisions): slot = coarse | sub << t1hi with
+// coarse = floor(c * (T1 >> t1rot) / S) = the high word of c * t1mul, sub = the next t1rot bits of that product.  The
+// lanes of a warp hold consecutive postings of a list, for a conserved k-mer one homolog per genome: with T1 >> t1rot
+// ~ G the low bits of the slot — the bank — are the (approximate) genome number, consecutive across the lanes, instead
+// of the random low bits of c * T1 / S, so the 4-byte key loads and the counter atomics of a round spread over the banks.
+// c must be a gene (< S): the hot loop pads with the row's own gene, whose cell is dropped anyway.
+__device__ __forceinline__ uint32_t t1_slot_of(uint32_t c, uint32_t t1mul, uint32_t t1rot, uint32_t t1hi) {
+    const unsigned long long p = (unsigned long long)c * t1mul;
+#ifdef PD_EMU
+    const uint32_t sub = t1rot ? (uint32_t)p >> (32 - t1rot) : 0u;
+#else
+    const uint32_t sub = __funnelshift_l((uint32_t)p, 0u, t1rot);  // the top t1rot bits of the low word (0 for t1rot = 0)
+#endif
+    return (uint32_t)(p >> 32) | (sub << t1hi);
 }
+__device__ __forceinline__ uint32_t t1_slot(const ScoreArgs& a, uint32_t c) { return t1_slot_of(c, a.t1mul, a.t1rot, a.t1hi); }
 __device__ __forceinline__ uint32_t t2_home(const ScoreArgs& a, uint32_t c) { return min(__umulhi(c, a.hmul), a.hmask); }
 
 __device__ __forceinline__ uint32_t x_find_or_insert(const XTab& x, uint32_t c) {
@@ -293,8 +299,7 @@ struct GenArgs {
 };
 __device__ __noinline__ void add_general(const GenArgs g, uint32_t c, uint32_t n, uint32_t m) {
     // the slot of column c in either tier (claimed if new)
-    uint32_t h = min(__umulhi(c, g.t1mul), g.t1 - 1);
-    h = (h >> g.t1rot) | ((h << g.t1hi) & (g.t1 - 1));
+    uint32_t h = t1_slot_of(c, g.t1mul, g.t1rot, g.t1hi);
     {
         const saddr_t a1 = g.keys_sa + h * 4u;
         uint32_t k = lds_u32(a1);
@@ -355,67 +360,101 @@ __device__ __forceinline__ GenArgs gen_args(const ScoreArgs& a, const Tab& t) {
     return g;
 }
 
-// ---- accumulate, the common case: postings with n = m = 1.  One "item" is one posting per lane (kNone: none).
+// ---- accumulate, the common case: postings with n = m = 1.  One "item" is one posting per lane; lanes past the end of
+// a list hold the row's own gene (its cell is dropped by finalize), so the hot path has no "no posting" case.
 //
 // A posting whose tier-1 slot does not hold its column (a few per cent of them: first touches, second paralogs, chance
-// hits) is NOT handled where it is found — that would be a divergent branch with one or two lanes active in almost every
-// round.  It goes to a per-warp ring of kQueue words: the missing lanes are compacted with one ballot (slot = tail +
-// rank of the lane among the missing ones), head and tail live in warp-uniform registers, no atomic, no shared-memory
-// control word.  As soon as 32 are queued they are resolved together, every lane busy: claim the tier-1 slot if it is
-// still free, count there if the column owns it, else probe / insert into tier 2.
-struct WarpQueue {
-    uint32_t* q;
-    uint32_t head, tail;  // warp-uniform
+// hits) is NOT handled where it is found: with 64 postings per pair of items almost every pair has one, and a branch
+// taken for one or two lanes costs the whole warp its issue slots.  Each LANE appends its misses to its own column of a
+// per-warp buffer (kLaneQueue rows of 32 words: one predicated store, no vote, no atomic); every four items one vote
+// asks whether some lane is about to run out of rows, and only then the warp resolves everything queued: claim the
+// tier-1 slot if it is still free, count there if the column owns it, else probe / insert into tier 2.
+static const uint32_t kLaneQueue = 8;   // rows per lane
+static const uint32_t kLaneDrain = 5;   // drain when a lane holds this many: at most 4 + 4 between two checks
+struct LaneQueue {
+    saddr_t base;  // this lane's word of row 0
+    saddr_t wr;    // where this lane's next miss goes (base + 128 * queued)
 };
 
-__device__ __forceinline__ void queue_drain32(const ScoreArgs& a, const Tab& t, WarpQueue& wq, uint32_t n) {  // n queued (uniform)
-    const unsigned lane = threadIdx.x & 31;
-    const uint32_t cur = lane < n ? wq.q[(wq.head + lane) & (kQueue - 1)] : kNone;
-    wq.head += n < 32u ? n : 32u;
-    if (cur != kNone) {
-        const uint32_t s1 = t1_slot(a, cur);
-        const saddr_t a1 = t.keys_sa + s1 * 4u;
+__device__ __forceinline__ void sts_u32(saddr_t a, uint32_t v) {
+#ifdef PD_EMU
+    *reinterpret_cast<volatile uint32_t*>(a) = v;
+#else
+    asm volatile("st.volatile.shared.u32 [%0], %1;\n" ::"r"(a), "r"(v) : "memory");
+#endif
+}
+
+// one posting: count it if tier 1 holds its column, else queue it.  No branch: the increment of a miss is redirected to
+// the lane's own dump word (the row after its queue rows), the queue store is predicated.
+__device__ __forceinline__ void item_add(const ScoreArgs& a, const Tab& t, LaneQueue& lq, uint32_t c) {
+    const uint32_t s = t1_slot(a, c);
+    PD_CHECK(s < a.t1 && c < a.S, 1, c);
+    const saddr_t ka = t.keys_sa + s * 4u;
+    const uint32_t k = lds_u32(ka);
+#ifdef PD_EMU
+    if (k == c) reds_inc(ka + a.nslots * 4u);
+    else {
+        sts_u32(lq.wr, c);
+        lq.wr += 128u;
+    }
+#else
+    const saddr_t hit_at = ka + a.nslots * 4u, dump_at = lq.base + kLaneQueue * 128u;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 ad, nw;\n"
+        "setp.eq.u32 p, %1, %2;\n"
+        "selp.u32 ad, %3, %4, p;\n"
+        "red.shared.add.u32 [ad], 1;\n"
+        "@!p st.volatile.shared.u32 [%0], %2;\n"
+        "add.u32 nw, %0, 128;\n"
+        "selp.u32 %0, %0, nw, p;\n"
+        "}\n"
+        : "+r"(lq.wr)
+        : "r"(k), "r"(c), "r"(hit_at), "r"(dump_at)
+        : "memory");
+#endif
+}
+
+// resolves everything the lanes have queued (warp-uniform call)
+__device__ __noinline__ void queue_drain(const GenArgs g, saddr_t base, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t cur = lds_u32(base + i * 128u);
+        const uint32_t s1 = t1_slot_of(cur, g.t1mul, g.t1rot, g.t1hi);
+        const saddr_t a1 = g.keys_sa + s1 * 4u;
         uint32_t k1 = lds_u32(a1);
         if (k1 == kEmpty) {
             const uint32_t old = atoms_cas(a1, kEmpty, cur);
             k1 = (old == kEmpty) ? cur : old;
         }
-        if (k1 == cur) {
-            reds_inc(cnt_sa(a, t) + s1 * 4u);
-        } else {
-            const uint32_t h = t2_find_or_insert(a, t, cur);
-            if (h != kEmpty) reds_inc(cnt_sa(a, t) + h * 4u);
+        uint32_t slot = s1;
+        if (k1 != cur) {
+            uint32_t hh = min(__umulhi(cur, g.hmul), g.hmask), probes = 0;
+            for (;;) {
+                const saddr_t addr = g.keys_sa + (g.t1 + hh) * 4u;
+                uint32_t kk = lds_u32(addr);
+                if (kk == kEmpty) {
+                    const uint32_t old = atoms_cas(addr, kEmpty, cur);
+                    kk = (old == kEmpty) ? cur : old;
+                }
+                if (kk == cur) break;
+                hh = (hh + 1) & g.hmask;
+                if (++probes > g.plimit) {
+                    g.ctl->over = 1;
+                    hh = kEmpty;
+                    break;
+                }
+            }
+            if (hh == kEmpty) continue;
+            slot = g.t1 + hh;
         }
+        reds_inc(g.keys_sa + (g.nslots + slot) * 4u);
     }
-    __syncwarp();
 }
-__device__ __forceinline__ void queue_flush(const ScoreArgs& a, const Tab& t, WarpQueue& wq) {
-    __syncwarp();
-    while (wq.tail != wq.head) queue_drain32(a, t, wq, wq.tail - wq.head);
-}
-
-// two items at a time: both tier-1 loads are in flight before either is compared
-__device__ __forceinline__ void items_add2(const ScoreArgs& a, const Tab& t, WarpQueue& wq, uint32_t c0, uint32_t c1) {
-    const uint32_t s0 = t1_slot(a, c0), s1 = t1_slot(a, c1);
-    PD_CHECK(s0 < a.t1 && s1 < a.t1, 1, s0);
-    PD_CHECK(c0 == kNone || c0 < a.S, 11, c0);
-    PD_CHECK(c1 == kNone || c1 < a.S, 12, c1);
-    const uint32_t k0 = lds_u32(t.keys_sa + s0 * 4u);
-    const uint32_t k1 = lds_u32(t.keys_sa + s1 * 4u);
-    const bool hit0 = k0 == c0, hit1 = k1 == c1;  // kNone is never a key: no hit
-    if (hit0) reds_inc(cnt_sa(a, t) + s0 * 4u);
-    if (hit1) reds_inc(cnt_sa(a, t) + s1 * 4u);
-    const unsigned m0 = __ballot_sync(0xffffffffu, !hit0 && c0 != kNone);
-    const unsigned m1 = __ballot_sync(0xffffffffu, !hit1 && c1 != kNone);
-    if (m0 | m1) {  // uniform
-        const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
-        if ((m0 >> (threadIdx.x & 31)) & 1u) wq.q[(wq.tail + __popc(m0 & lt)) & (kQueue - 1)] = c0;
-        wq.tail += __popc(m0);
-        if ((m1 >> (threadIdx.x & 31)) & 1u) wq.q[(wq.tail + __popc(m1 & lt)) & (kQueue - 1)] = c1;
-        wq.tail += __popc(m1);
-        __syncwarp();
-        // at most 31 entries stay queued between calls, a call adds at most 64: the ring (kQueue = 128) never laps
-        while (wq.tail - wq.head >= 32u) queue_drain32(a, t, wq, wq.tail - wq.head);
+__device__ __forceinline__ void queue_check(const ScoreArgs& a, const Tab& t, LaneQueue& lq, uint32_t threshold) {
+    if (__any_sync(0xffffffffu, lq.wr - lq.base >= threshold * 128u)) {
+        queue_drain(gen_args(a, t), lq.base, (lq.wr - lq.base) >> 7);
+        lq.wr = lq.base;
     }
 }
 
@@ -423,55 +462,64 @@ __device__ __forceinline__ void items_add2(const ScoreArgs& a, const Tab& t, War
 struct WarpScratch {
     uint32_t bits[kShortList + kItemsA];  // 32 lists x kShortList postings = 2048 marks (+ the words a round reads ahead)
     uint32_t pre[32];
-    uint32_t queue[kQueue];
-    uint32_t qtail;
-    uint32_t pad[3];
+    uint32_t queue[kLaneQueue * 32];  // row i: the i-th queued miss of every lane
+    uint32_t dump[32];                // row kLaneQueue: where a lane's increment goes when its posting missed (item_add)
+    uint32_t pad[4];
 };
 
-// A list walk in rounds of kItems x 32 consecutive postings: lane l holds postings p0 + 32 u + l, u < kItems, in e[u].
-// round_step consumes e pair by pair and refills each pair at once with the NEXT round's postings (list `nq`,
-// `nrem` postings from this lane's first to that list's end; nrem <= 0: nothing), so kItems loads per warp stay in
-// flight while the table is updated.  cnt = postings in this round (uniform), the row holds this list's k-mer mj
-// times; pos = index of this round's first posting in the posting array (for post_cnt).
-__device__ __forceinline__ void round_step(const ScoreArgs& a, const Tab& t, WarpQueue& wq, uint32_t (&e)[kItems], uint32_t cnt,
-                                           uint32_t pos, uint32_t mj, const uint32_t* __restrict__ nq, int nrem) {
+// A list walk in rounds of kItems x 32 consecutive postings: lane l holds postings p0 + 32 u + l, u < kItems, in e[u]
+// (the row's own gene `self` past the end of the list).  round_step consumes e pair by pair and refills each pair at
+// once with the NEXT round's postings (list `nq`, `nrem` postings from this lane's first to that list's end; nrem <= 0:
+// nothing), so kItems loads per warp stay in flight while the table is updated.  cnt = postings in this round
+// (uniform), the row holds this list's k-mer mj times; pos = index of this round's first posting in the posting array
+// (for post_cnt).
+__device__ __forceinline__ void round_step(const ScoreArgs& a, const Tab& t, LaneQueue& lq, uint32_t (&e)[kItems], uint32_t cnt,
+                                           uint32_t pos, uint32_t mj, const uint32_t* __restrict__ nq, int nrem, uint32_t self) {
     const unsigned lane = threadIdx.x & 31;
 #pragma unroll
     for (int u = 0; u < kItems; u += 2) {
         uint32_t c0 = e[u], c1 = e[u + 1];
-        e[u] = nrem > 32 * u ? nq[32 * u] : kNone;
-        e[u + 1] = nrem > 32 * (u + 1) ? nq[32 * (u + 1)] : kNone;
+        e[u] = nrem > 32 * u ? nq[32 * u] : self;
+        e[u + 1] = nrem > 32 * (u + 1) ? nq[32 * (u + 1)] : self;
         if (32u * u < cnt) {  // uniform: the tail of a list does not pay for empty items
             // bit 31: a repeated k-mer; the row's own repeat count is uniform over the list
             if (((c0 | c1) & kMulti) || mj > 1) {
-                if (c0 != kNone && ((c0 & kMulti) || mj > 1)) {
+                if (32u * u + lane < cnt && ((c0 & kMulti) || mj > 1)) {
                     add_general(gen_args(a, t), c0 & ~kMulti, (c0 & kMulti) ? a.post_cnt[pos + 32u * u + lane] : 1u, mj);
-                    c0 = kNone;
+                    c0 = self;
                 }
-                if (c1 != kNone && ((c1 & kMulti) || mj > 1)) {
+                if (32u * (u + 1) + lane < cnt && ((c1 & kMulti) || mj > 1)) {
                     add_general(gen_args(a, t), c1 & ~kMulti, (c1 & kMulti) ? a.post_cnt[pos + 32u * (u + 1) + lane] : 1u, mj);
-                    c1 = kNone;
+                    c1 = self;
                 }
             }
-            items_add2(a, t, wq, c0, c1);
+            item_add(a, t, lq, c0);
+            item_add(a, t, lq, c1);
         }
+        if ((u & 2) != 0) queue_check(a, t, lq, kLaneDrain);  // every four items
     }
 }
 
-// Accumulates the staged forward entries fbuf[0, n_stage) = forward entries [f0, f0 + n_stage) of the row.
+// Accumulates the staged forward entries fbuf[0, n_stage) = forward entries [f0, f0 + n_stage) of the row `self`.
 // Classes by position: [0, ns) short, [ns, nl) long, [nl, n_stage) huge.  ctr[0..1] are shared work counters, zero
 // at entry.  No ordering is needed between the three parts (every update is an atomic on the table); the long lists
 // go first so that the row's frequent columns — its homologs — claim the tier-1 slots before the chance hits of the
 // short lists arrive.
 template <int THREADS>
-__device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t, const uint2* fbuf, uint32_t f0, uint32_t ns, uint32_t nl,
-                                           uint32_t n_stage, WarpScratch* ws_all, uint32_t* ctr) {
+__device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t_in, const uint2* fbuf, uint32_t f0, uint32_t ns, uint32_t nl,
+                                           uint32_t n_stage, WarpScratch* ws_all, uint32_t* ctr, uint32_t self) {
     constexpr int WARPS = THREADS / 32;
+    Tab t = t_in;
+#ifndef PD_EMU
+    // the table's shared-window address stays in a register: left to itself the compiler re-derives it (special register
+    // read + three integer ops) for every pair of postings
+    asm volatile("" : "+r"(t.keys_sa));
+#endif
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& ws = ws_all[warp];
-    WarpQueue wq;
-    wq.q = ws.queue;
-    wq.head = wq.tail = 0;
+    LaneQueue lq;
+    lq.base = smem_addr(ws.queue + lane);
+    lq.wr = lq.base;
     const unsigned le = 0xffffffffu >> (31 - lane);  // lanes <= mine
     // ---- long lists: one warp per list
     {
@@ -491,7 +539,7 @@ __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t, con
         bool have = claim(gs, gl, mj);
         if (have) {
 #pragma unroll
-            for (int u = 0; u < kItems; u++) e[u] = 32u * u + lane < gl ? a.post[gs + 32u * u + lane] : kNone;
+            for (int u = 0; u < kItems; u++) e[u] = 32u * u + lane < gl ? a.post[gs + 32u * u + lane] : self;
         }
         while (have) {
             uint32_t ngs = gs, ngl = gl, nmj = mj, np0 = p0 + 32 * kItems;
@@ -501,7 +549,7 @@ __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t, con
                 np0 = 0;
             }
             const int nrem = nhave ? (int)(ngl - np0) - (int)lane : 0;
-            round_step(a, t, wq, e, gl - p0, gs + p0, mj, a.post + ngs + np0 + lane, nrem);
+            round_step(a, t, lq, e, gl - p0, gs + p0, mj, a.post + ngs + np0 + lane, nrem, self);
             gs = ngs;
             gl = ngl;
             mj = nmj;
@@ -520,12 +568,12 @@ __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t, con
         if (p0 >= gl) continue;
         uint32_t e[kItems];
 #pragma unroll
-        for (int u = 0; u < kItems; u++) e[u] = p0 + 32u * u + lane < gl ? a.post[fw.x + p0 + 32u * u + lane] : kNone;
+        for (int u = 0; u < kItems; u++) e[u] = p0 + 32u * u + lane < gl ? a.post[fw.x + p0 + 32u * u + lane] : self;
         for (;;) {
             const uint32_t np0 = p0 + stride;
             const bool more = np0 < gl && !((np0 & 0x7FFFu) < stride && __any_sync(0xffffffffu, *t.over() != 0));  // poll now and then
             const int nrem = more ? (int)(gl - np0) - (int)lane : 0;
-            round_step(a, t, wq, e, gl - p0, fw.x + p0, mj, a.post + fw.x + np0 + lane, nrem);
+            round_step(a, t, lq, e, gl - p0, fw.x + p0, mj, a.post + fw.x + np0 + lane, nrem, self);
             if (!more) break;
             p0 = np0;
         }
@@ -568,7 +616,7 @@ __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t, con
 #pragma unroll
             for (int u = 0; u < kItemsA; u++) {
                 const uint32_t tt = t0 + 32u * u + lane;
-                e[u] = kNone;
+                e[u] = self;
                 if (tt < total) {
                     const uint2 fw = fbuf[b0 + o[u]];
                     e[u] = a.post[fw.x + (tt - ws.pre[o[u]])];
@@ -585,20 +633,21 @@ __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t, con
                             const uint32_t n = (e[u] & kMulti) ? a.post_cnt[fw.x + (tt - ws.pre[o[u]])] : 1u;
                             const uint32_t m = (fw.y & kMulti) ? a.fwd_cnt[f0 + b0 + o[u]] : 1u;
                             add_general(gen_args(a, t), e[u] & ~kMulti, n, m);
-                            e[u] = kNone;
+                            e[u] = self;
                         }
                     }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kItemsA; u += 2) {
+            for (int u = 0; u < kItemsA; u++) {
                 if (t0 + 32u * u >= total) break;
-                items_add2(a, t, wq, e[u], e[u + 1]);
+                item_add(a, t, lq, e[u]);
             }
+            queue_check(a, t, lq, kLaneDrain);
         }
         __syncwarp();
     }
-    queue_flush(a, t, wq);
+    queue_check(a, t, lq, 1);
 }
 
 // (inter, pc, tc) of a table slot
@@ -725,7 +774,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
                 const uint32_t f1 = fe - f0 < fcap ? fe : f0 + fcap;
                 const uint32_t ns = fm > f0 ? (fm < f1 ? fm - f0 : f1 - f0) : 0u;
                 const uint32_t nl = fh > f0 ? (fh < f1 ? fh - f0 : f1 - f0) : 0u;
-                accumulate<THREADS>(a, t, fbuf, f0, ns, nl, f1 - f0, ws, s_ctl[buf].ctr);
+                accumulate<THREADS>(a, t, fbuf, f0, ns, nl, f1 - f0, ws, s_ctl[buf].ctr, s_desc[buf][0].x);
                 if (f1 >= fe) break;
                 __syncthreads();
                 f0 = f1;
