@@ -416,10 +416,29 @@ __device__ __forceinline__ void item_add(const ScoreArgs& a, const Tab& t, LaneQ
 #endif
 }
 
-// resolves everything the lanes have queued (warp-uniform call)
+// resolves everything the lanes have queued (warp-uniform call; n = this lane's count).  The lanes' columns are first
+// packed into one dense list (exclusive prefix of the counts) so that the resolve loop runs with every lane busy instead
+// of as many times as the fullest lane has entries.
 __device__ __noinline__ void queue_drain(const GenArgs g, saddr_t base, uint32_t n) {
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t cur = lds_u32(base + i * 128u);
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t v[kLaneQueue];
+#pragma unroll
+    for (uint32_t i = 0; i < kLaneQueue; i++) v[i] = i < n ? lds_u32(base + i * 128u) : 0u;
+    uint32_t incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (unsigned)d) incl += o;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const saddr_t flat = base - lane * 4u + (incl - n) * 4u;  // the rows as one array of 32 * kLaneQueue words
+    __syncwarp();
+#pragma unroll
+    for (uint32_t i = 0; i < kLaneQueue; i++)
+        if (i < n) sts_u32(flat + i * 4u, v[i]);
+    __syncwarp();
+    for (uint32_t j = lane; j < total; j += 32) {
+        const uint32_t cur = lds_u32(base + (j - lane) * 4u);
         const uint32_t s1 = t1_slot_of(cur, g.t1mul, g.t1rot, g.t1hi);
         const saddr_t a1 = g.keys_sa + s1 * 4u;
         uint32_t k1 = lds_u32(a1);
@@ -450,6 +469,7 @@ __device__ __noinline__ void queue_drain(const GenArgs g, saddr_t base, uint32_t
         }
         reds_inc(g.keys_sa + (g.nslots + slot) * 4u);
     }
+    __syncwarp();
 }
 __device__ __forceinline__ void queue_check(const ScoreArgs& a, const Tab& t, LaneQueue& lq, uint32_t threshold) {
     if (__any_sync(0xffffffffu, lq.wr - lq.base >= threshold * 128u)) {

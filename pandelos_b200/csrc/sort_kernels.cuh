@@ -33,7 +33,6 @@ static const int kItems = 16;
 static const int kTile = kThreads * kItems;  // 4096 keys per tile
 static const int kWarps = kThreads / 32;
 static const int kRadix = 256;
-static const int kGroup = 8;       // keys ranked together
 static const int kMaxPasses = 8;   // 63 rank bits at most
 static const uint64_t kNoKey = ~0ull;  // never a key: rank_bits + seq_bits <= 63
 static const uint32_t kInclusive = 0x80000000u;  // status word: 0 = not ready; bit 31 = inclusive prefix; else aggregate + 1
@@ -169,7 +168,23 @@ inline size_t sweep_smem_bytes() {
     return sizeof(uint64_t) * (kTile + kTile / 16) + sizeof(uint32_t) * (kWarps * kRadix + 2 * kRadix + 33 + 3) + 256;
 }
 
+// Lanes of the warp whose 8-bit digit equals mine, from eight ballots (one per digit bit) instead of match.any: the match
+// instruction was the top stall of the first version of this kernel (36 % of the samples waited on its result).
+// `vm` = ballot of the lanes that hold a key; the result is only meaningful for those.
+__device__ __forceinline__ unsigned match_digit(unsigned dig, unsigned vm) {
+    unsigned r = vm;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const bool p = (dig >> b) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, p);
+        r &= p ? bal : ~bal;
+    }
+    return r;
+}
+
 // MODE 0: keys from `a.keys`.  MODE 1: keys made from the residues (EncodeSrc).
+// Order of work in a tile: load -> per-warp digit counts (shared-memory atomics) -> offsets, tile counts PUBLISHED ->
+// rank (ballots) -> keys to their place in the tile buffer -> look-back (by now the tiles before have published) -> out.
 template <int MODE, typename RankT>
 __global__ void __launch_bounds__(kThreads, 4) onesweep_kernel(SweepArgs a, EncodeSrc s) {
     PD_DYNAMIC_SMEM(smem_raw);
@@ -204,7 +219,6 @@ __global__ void __launch_bounds__(kThreads, 4) onesweep_kernel(SweepArgs a, Enco
             const uint32_t local = warp * (32 * kItems) + j * 32 + lane;
             key[j] = stage[local + (local >> 4)];
         }
-        __syncthreads();  // the buffer is reused for the ranked keys
     } else {
 #pragma unroll
         for (int j = 0; j < kItems; j++) {
@@ -212,40 +226,17 @@ __global__ void __launch_bounds__(kThreads, 4) onesweep_kernel(SweepArgs a, Enco
             key[j] = local < tile_n ? a.keys[tile_base + local] : kNoKey;
         }
     }
+    const bool full = MODE == 0 && tile_n == (uint32_t)kTile;  // uniform: every lane holds a key in every round
 
-    // ---- rank inside the warp's 512 keys: key order = (round j, lane).  Peer masks of a group first (independent match
-    // instructions), then the per-digit counter updates in key order
-    uint16_t rnk[kItems];
+    // ---- per-warp digit counts
     uint32_t* my_wc = wc + warp * kRadix;
-    const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
-    for (int j0 = 0; j0 < kItems; j0 += kGroup) {
-        unsigned peers[kGroup];
-        unsigned dig[kGroup];
-#pragma unroll
-        for (int jj = 0; jj < kGroup; jj++) {
-            const int j = j0 + jj;
-            // dropped keys take a private pseudo-digit so they never join a kept key's peer group
-            dig[jj] = key[j] != kNoKey ? ((unsigned)(key[j] >> a.shift) & 0xFFu) : (256u + lane);
-            peers[jj] = __match_any_sync(0xffffffffu, dig[jj]);
-        }
-#pragma unroll
-        for (int jj = 0; jj < kGroup; jj++) {
-            const int j = j0 + jj;
-            const unsigned leader = __ffs(peers[jj]) - 1;
-            uint32_t base_cnt = 0;
-            if (dig[jj] < 256u && lane == leader) {
-                base_cnt = my_wc[dig[jj]];
-                my_wc[dig[jj]] = base_cnt + __popc(peers[jj]);
-            }
-            base_cnt = __shfl_sync(0xffffffffu, base_cnt, leader);
-            rnk[j] = (uint16_t)(base_cnt + __popc(peers[jj] & lt_mask));
-            __syncwarp();
-        }
-    }
-    __syncthreads();
+    for (int j = 0; j < kItems; j++)
+        if (key[j] != kNoKey) atomicAdd(&my_wc[(unsigned)(key[j] >> a.shift) & 0xFFu], 1u);
+    __syncthreads();  // (also: the buffer of the first pass's transpose is free again)
 
-    // ---- per digit (thread = digit): exclusive scan over the warps, tile total, exclusive scan over the digits
+    // ---- per digit (thread = digit): exclusive scan over the warps, tile total, exclusive scan over the digits;
+    // the tile's counts go out at once so that later tiles can look back over them while this one still ranks
     uint32_t cnt = 0;
     {
         uint32_t run = 0;
@@ -257,18 +248,37 @@ __global__ void __launch_bounds__(kThreads, 4) onesweep_kernel(SweepArgs a, Enco
         }
         cnt = run;
     }
+    volatile uint32_t* st = a.status + (size_t)tile * kRadix + tid;
+    *st = tile == 0 ? (kInclusive | cnt) : cnt + 1u;
     uint32_t tile_kept;
     const uint32_t ex = prims::block_excl_scan<kThreads>(cnt, scratch, &tile_kept);
     tile_excl[tid] = ex;
+    __syncthreads();
+
+    // ---- rank and place: key order inside the warp's 512 keys = (round j, lane).  The warp's counter of a digit runs
+    // from its exclusive offset; the first lane of every peer group advances it
+    const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+        const bool has = key[j] != kNoKey;
+        const unsigned d = (unsigned)(key[j] >> a.shift) & 0xFFu;
+        const unsigned vm = full ? 0xffffffffu : __ballot_sync(0xffffffffu, has);
+        const unsigned peers = match_digit(d, vm);
+        const unsigned leader = __ffs(peers) - 1;
+        uint32_t base_cnt = 0;
+        if (has && lane == leader) {
+            base_cnt = my_wc[d];
+            my_wc[d] = base_cnt + __popc(peers);
+        }
+        base_cnt = __shfl_sync(0xffffffffu, base_cnt, has ? leader : lane);
+        if (has) stage[tile_excl[d] + base_cnt + __popc(peers & lt_mask)] = key[j];
+        __syncwarp();
+    }
 
     // ---- decoupled look-back over the tiles before mine, one digit per thread
     {
-        volatile uint32_t* st = a.status + (size_t)tile * kRadix + tid;
         uint32_t before = 0;
-        if (tile == 0) {
-            *st = kInclusive | cnt;
-        } else {
-            *st = cnt + 1u;
+        if (tile != 0) {
             for (uint32_t t = tile; t-- > 0;) {
                 volatile uint32_t* sp = a.status + (size_t)t * kRadix + tid;
                 uint32_t v;
@@ -286,15 +296,7 @@ __global__ void __launch_bounds__(kThreads, 4) onesweep_kernel(SweepArgs a, Enco
     }
     __syncthreads();
 
-    // ---- keys to their place inside the tile, then out in runs of equal digit
-#pragma unroll
-    for (int j = 0; j < kItems; j++) {
-        if (key[j] != kNoKey) {
-            const unsigned d = (unsigned)(key[j] >> a.shift) & 0xFFu;
-            stage[tile_excl[d] + my_wc[d] + rnk[j]] = key[j];
-        }
-    }
-    __syncthreads();
+    // ---- out, in runs of equal digit
 #pragma unroll
     for (int i = 0; i < kItems; i++) {
         const uint32_t idx = i * kThreads + tid;

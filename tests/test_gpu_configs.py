@@ -101,7 +101,9 @@ def test_config_full_size_against_the_unmodified_reference(name, tmp_path):
     r = subprocess.run([build.NETCLU_BIN, faa, out, "-r", rest], capture_output=True, text=True)
     assert r.returncode in (0, 3), r.stderr     # 3: some components are left to the script's Girvan-Newman split
     fam_lines = [ln for ln in r.stdout.splitlines() if ln.startswith("F{ ")]
-    assert 0 < len(fam_lines) <= gold["clus"]["lines"]
+    assert len(fam_lines) > 0
+    if "lines" in gold["clus"]:   # mycoplasma64: the script's Girvan-Newman split does not end in reasonable time (golden says so)
+        assert len(fam_lines) <= gold["clus"]["lines"]
     # .clus itself: golden of the unmodified netclu_ng.py on the identical .net (sha256 in the golden; the script and
     # /root/reference do not exist on the GPU box — tests/test_config_goldens.py re-derives it in the build container)
 
