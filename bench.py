@@ -403,6 +403,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--exchange", default="none", choices=["none", "allgather"], help="best-hit slices between ranks (strong scaling)")
+    ap.add_argument("--build", default="sharded", choices=["sharded", "replicated"],
+                    help="N > 1, strong scaling: ranks build ONE index together (rank-range slices, postings all-gathered) or each its own copy")
     ap.add_argument("--query-genomes", type=int, default=0, help="--scaling weak: genomes scored per rank (0 = workload default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -458,8 +460,26 @@ def main():
     off_pin = torch.from_numpy(w.offsets.astype(np.int64)).pin_memory()
     gid_pin = torch.from_numpy(w.genome_of.astype(np.int32)).pin_memory()
     data = native.PangeneIData(w.residues, off_pin.numpy().view(np.uint64), gid_pin.numpy().view(np.uint32))
-    # the job's query genes, split by posting-list volume at genome boundaries
-    if world > 1:
+    # residues resident in HBM before the timed region
+    res_host = torch.from_numpy(w.residues).pin_memory()
+    res_dev = res_host.to(dev, non_blocking=False)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    sharded = world > 1 and strong and args.build == "sharded"
+
+    def make_index(host_residues=False, **kw):
+        """The index as this run builds it: one per rank (single GPU, replicated) or one for all ranks (sharded)."""
+        d = data_pinned if host_residues else data
+        ptr = None if host_residues else res_dev.data_ptr()
+        if sharded:
+            return multigpu.build_sharded(dist, native, k, d, device=dev, device_index=local, residues_device_ptr=ptr, **kw)
+        return native.PangeneNative(k, d, device=local, residues_device_ptr=ptr, **kw), None
+
+    data_pinned = native.PangeneIData(res_host.numpy(), w.offsets, w.genome_of)
+    # the job's query genes, split by posting-list volume at genome boundaries (the sharded build does it itself)
+    if sharded:
+        pn0, bounds = make_index()
+        pn0.close()
+    elif world > 1:
         pn0 = native.PangeneNative(k, data, device=local)
         _, visited = pn0.gene_stats()
         pn0.close()
@@ -468,11 +488,6 @@ def main():
         bounds = np.array([0, int(gb[job_genomes])], np.int64)
     row0, row1 = int(bounds[rank]), int(bounds[rank + 1])
     g0, g1 = int(np.searchsorted(gb, row0)), int(np.searchsorted(gb, row1))
-
-    # residues resident in HBM before the timed region
-    res_host = torch.from_numpy(w.residues).pin_memory()
-    res_dev = res_host.to(dev, non_blocking=False)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     G = w.G
     rows_of_rank = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
@@ -495,7 +510,7 @@ def main():
 
     def step():
         t0 = time.perf_counter()
-        pn = native.PangeneNative(k, data, device=local, residues_device_ptr=res_dev.data_ptr())
+        pn, _ = make_index()
         t1 = time.perf_counter()
         if gather is not None:
             st = Stats(multigpu.score_and_gather(pn, gather, rank, row0))
@@ -588,7 +603,7 @@ def main():
         if gold is not None:
             mine = [g for g in (sample_order(gold) if name == "scaleout1000" else sorted(int(x) for x in gold["per_genome"])) if g0 <= g < g1]
             mine = mine[:max(1, 8 // world)] if name == "scaleout1000" else mine
-            pn = native.PangeneNative(k, data, device=local, residues_device_ptr=res_dev.data_ptr())
+            pn, _ = make_index()
             parity_ok, parity = parity_against_golden(pn, gold, mine, "tests/golden/digests/%s.json (%s)" % (
                 name + "_sample" if name == "scaleout1000" else name, gold.get("oracle", "unmodified library.cpp")))
             pn.close()
@@ -619,7 +634,6 @@ def main():
         # inputs in pinned host memory; computeScores from a pool of E2E_THREADS host threads, as Pangenes.java:54-66
         # calls it from its thread pool: one call's device->host copies overlap the other calls' kernels
         from concurrent.futures import ThreadPoolExecutor
-        data_pinned = native.PangeneIData(res_host.numpy(), w.offsets, w.genome_of)
 
         def one_genome(pn, g):
             stt, rel = pn.compute_scores_raw(g)
@@ -634,7 +648,7 @@ def main():
         for i in range(E2E_WARM + e2e_steps):
             barrier()
             t0 = time.perf_counter()
-            pn = native.PangeneNative(k, data_pinned, device=local, contexts=E2E_THREADS)
+            pn, _ = make_index(host_residues=True, contexts=E2E_THREADS)
             h2d = len(w.residues) + 8 * (w.S + 1) + 4 * w.S
             with ThreadPoolExecutor(max_workers=E2E_THREADS) as pool:
                 res_g = list(pool.map(lambda g: one_genome(pn, g), range(g0, g1)))
@@ -674,7 +688,7 @@ def main():
         for i in range(1 + e2e_steps):  # first pass untimed, like the arm above
             barrier()
             t0 = time.perf_counter()
-            pn = native.PangeneNative(k, data_pinned, device=local, contexts=E2E_THREADS)
+            pn, _ = make_index(host_residues=True, contexts=E2E_THREADS)
             with ThreadPoolExecutor(max_workers=E2E_THREADS) as pool:
                 res_e = list(pool.map(lambda g: one_genome_edges(pn, g), range(g0, g1)))
             barrier()
@@ -716,8 +730,10 @@ def main():
                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                "dtype": "int32+f32", "data": "synthetic", "config": cfg,
                "run": {"query_genomes": int(job_genomes), "query_rows_this_rank": int(rows_n), "query_genomes_this_rank": [g0, g1],
-                       "parallelism": ("index replicated, query genomes split by posting-list volume at genome boundaries; best-hit exchange: %s" %
-                                       ("NCCL all-gather" if gather is not None else "none needed (every genome on one rank)")) if world > 1 else "single GPU",
+                       "parallelism": ("%s; query genomes split by posting-list volume at genome boundaries; best-hit exchange: %s" % (
+                                       "ONE index built by all ranks (k-mer rank slices sorted per rank; NCCL: all-gather of 4 B per posting + group bits, "
+                                       "all-reduce of 16 B per gene), forward lists per rank for its own rows" if sharded else "index replicated",
+                                       "NCCL all-gather" if gather is not None else "none needed (every genome on one rank)")) if world > 1 else "single GPU",
                        "l2": "flushed between timed steps (256 MiB fill)", "step": step_desc},
                "lookups_per_s": lookups_all / (ms * 1e-3), "cells_per_step": cells_all, "pairs_per_step": pairs_all,
                "build_ms_per_step": build_ms / args.steps, "score_kernel_ms_per_step": kms,

@@ -145,6 +145,36 @@ void pd_edges_release(pd_index* ix, pd_edges* e);
 int pd_score_partition_device(pd_index* ix, uint32_t row_begin, uint32_t row_end, uint32_t rows_per_launch,
                               float* d_best_hit, pd_score_stats* stats);
 
+/* ---- One index built by several GPUs (one process per GPU; the reference has no counterpart: its preprocessSequences is
+ * single-threaded, library.cpp:189-371).  The rank space of the k-mers is cut into `world` slices; rank r makes, sorts,
+ * count-dedups and groups the k-mers of slice r (every rank reads all residues, 1 B per k-mer).  The caller then
+ *   1. all-gathers (entries, multi) of pd_shard_info over the ranks,
+ *   2. all-reduces (sum, uint64) pd_shard_info.d_gene_counts [2 x S] in place,
+ *   3. calls pd_shard_buffers(max entries, max multi) and all-gathers each of the three arrays IN PLACE (segment r of each
+ *      array is rank r's, already filled on that rank),
+ *   4. calls pd_shard_finish: group structure of the whole entry list, genome-aligned query partition by posting-list
+ *      volume (bounds[world + 1], identical on every rank), forward lists for THIS rank's rows [bounds[rank],
+ *      bounds[rank + 1]).
+ * Afterwards pd_compute_scores / pd_genome_edges / pd_score_partition_device serve this rank's genomes / rows only
+ * (PD_ERR_INVALID for others), with results bit-identical to a single-GPU index.  Needs the genes of a genome to be
+ * contiguous and genomes in ascending order (as in every .faa PanDelos reads); pd_entries is not available. */
+typedef struct pd_shard_info {
+    uint64_t entries;         /* entries of this rank's slice */
+    uint64_t multi;           /* ... of which held more than once by their gene */
+    uint64_t kmers;           /* k-mer occurrences in this rank's slice */
+    uint64_t* d_gene_counts;  /* device, 2 x S: per gene forward entries per list class (packed) and total_visited — partial */
+} pd_shard_info;
+typedef struct pd_shard_arrays {
+    uint32_t* d_post;   /* world x seg  : postings */
+    uint32_t* d_heads;  /* world x seg / 32 : one bit per entry, set where a rank group starts */
+    uint32_t* d_multi;  /* world x mseg x 2 : (entry inside its slice, multiplicity) */
+    uint64_t seg, mseg;
+} pd_shard_arrays;
+int pd_build_shard(const uint8_t* residues, int32_t residues_on_device, const uint64_t* offsets, const uint32_t* genome_of, uint32_t S,
+                   int32_t k, const pd_options* opt, uint32_t rank, uint32_t world, pd_index** out, pd_shard_info* info);
+int pd_shard_buffers(pd_index* ix, uint64_t max_entries, uint64_t max_multi, pd_shard_arrays* out);
+int pd_shard_finish(pd_index* ix, const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds);
+
 /* Splits [0, S) into `parts` contiguous gene ranges of near-equal total_visited (query partitioning by
  * posting-list volume); bounds[parts+1].  snap_to_genomes != 0 moves boundaries to genome boundaries. */
 int pd_partition_rows(const pd_index* ix, uint32_t parts, int32_t snap_to_genomes, uint32_t* bounds);

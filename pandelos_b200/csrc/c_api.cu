@@ -32,7 +32,7 @@ int guarded(F f) {
 }
 
 int build_common(const uint8_t* residues, bool on_device, const uint64_t* offsets, const uint32_t* genome_of, uint32_t S, int32_t k,
-                 const pd_options* opt, pd_index** out) {
+                 const pd_options* opt, pd_index** out, uint32_t rank = 0, uint32_t world = 1) {
     if (!out) {
         pd::set_last_error("null output pointer");
         return PD_ERR_INVALID;
@@ -41,6 +41,8 @@ int build_common(const uint8_t* residues, bool on_device, const uint64_t* offset
     pd_index* h = nullptr;
     int rc = guarded([&] {
         h = new pd_index;
+        h->ix.shard_rank = rank;
+        h->ix.shard_world = world;
         h->ix.build(residues, on_device, offsets, genome_of, S, k, opt);
     });
     if (rc != PD_OK) {
@@ -67,6 +69,32 @@ int pd_build(const uint8_t* residues, const uint64_t* offsets, const uint32_t* g
 int pd_build_device(const uint8_t* d_residues, const uint64_t* offsets, const uint32_t* genome_of, uint32_t S, int32_t k,
                     const pd_options* opt, pd_index** out) {
     return build_common(d_residues, true, offsets, genome_of, S, k, opt, out);
+}
+
+int pd_build_shard(const uint8_t* residues, int32_t residues_on_device, const uint64_t* offsets, const uint32_t* genome_of, uint32_t S, int32_t k,
+                   const pd_options* opt, uint32_t rank, uint32_t world, pd_index** out, pd_shard_info* info) {
+    if (!info || world < 2 || rank >= world) {
+        pd::set_last_error("pd_build_shard: needs world >= 2, rank < world, info");
+        return PD_ERR_INVALID;
+    }
+    const int rc = build_common(residues, residues_on_device != 0, offsets, genome_of, S, k, opt, out, rank, world);
+    if (rc != PD_OK) return rc;
+    pd::Index& x = (*out)->ix;
+    info->entries = x.shard->U_r;
+    info->multi = x.shard->M_r;
+    info->kmers = 0;
+    info->d_gene_counts = reinterpret_cast<uint64_t*>(x.shard->gene_counts.p);
+    return PD_OK;
+}
+
+int pd_shard_buffers(pd_index* ix, uint64_t max_entries, uint64_t max_multi, pd_shard_arrays* out) {
+    if (!ix || !out) return PD_ERR_INVALID;
+    return guarded([&] { ix->ix.shard_buffers(max_entries, max_multi, out); });
+}
+
+int pd_shard_finish(pd_index* ix, const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds) {
+    if (!ix || !entries_of_rank || !multi_of_rank || !bounds) return PD_ERR_INVALID;
+    return guarded([&] { ix->ix.shard_finish(entries_of_rank, multi_of_rank, bounds); });
 }
 
 void pd_free(pd_index* ix) { delete ix; }

@@ -209,6 +209,7 @@ const size_t kParkedPerDevice = 8;
 }  // namespace
 
 Index::~Index() {
+    delete shard;
     trace::report();
     ContextPool& pool = context_pool();
     for (ScoreContext* c : all_ctx) {
@@ -377,6 +378,154 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     uint32_t U = 0, n_groups = 0, R = 0;
     unsigned long long lookups = 0;
 
+    if (shard_world > 1) {
+        // ================================================================ sharded build: this rank's slice of the rank space
+        if (opt.keep_sorted) throw Error(PD_ERR_INVALID, "keep_sorted is not available in a sharded build");
+        if (N == 0 || S == 0) throw Error(PD_ERR_UNSUPPORTED, "sharded build of an empty input");
+        shard = new Shard;
+        Shard& sh = *shard;
+        // Slice bounds in the rank space, identical on every rank: cut at multiples of base^(k-2) (a pair of leading
+        // letters) so that every slice holds about 1 / world of the k-mers if letters were independent — balance of the
+        // sort only, any cut is correct.  Counts of leading pairs are estimated from the alphabet histogram.
+        uint64_t lo = 0, hi = (uint64_t)pw;
+        {
+            const int lead = k >= 2 ? 2 : 1;
+            std::vector<double> f(base);
+            {
+                uint32_t v = 0;
+                for (int b = 0; b < 256; b++)
+                    if (h_hist[b]) f[v++] = (double)h_hist[b] / (double)total;
+            }
+            const uint64_t unit = (uint64_t)pw / (lead == 2 ? (uint64_t)base * base : (uint64_t)base);
+            const uint64_t bins = lead == 2 ? (uint64_t)base * base : base;
+            auto cut = [&](uint32_t r) -> uint64_t {   // first bin of slice r
+                if (r == 0) return 0;
+                if (r >= shard_world) return bins;
+                const double want = (double)r / (double)shard_world;
+                double cum = 0;
+                for (uint64_t b = 0; b < bins; b++) {
+                    const double p = lead == 2 ? f[b / base] * f[b % base] : f[b];
+                    if (cum + p / 2 >= want) return b;
+                    cum += p;
+                }
+                return bins;
+            };
+            lo = cut(shard_rank) * unit;
+            hi = shard_rank + 1 == shard_world ? (uint64_t)pw : cut(shard_rank + 1) * unit;
+        }
+        Timer t_sh(st);
+        t_sh.start();
+        rt::DevBuf<uint64_t> keys_a(N), keys_b(N);
+        const uint32_t stiles = sortk::tiles_of(N);
+        const int passes = sortk::passes_of(rank_bits);
+        rt::DevBuf<uint32_t> tile_gene((size_t)stiles + 1), sort_ctl((size_t)2 * passes * sortk::kRadix + 32), slice_status((size_t)stiles + 1);
+        uint32_t* d_hist = sort_ctl.p;
+        uint32_t* d_bins = d_hist + passes * sortk::kRadix;
+        uint32_t* d_tot = d_bins + passes * sortk::kRadix;  // [0] keys kept, [4] slice ticket, [8 + p] tile tickets
+        rt::zero(sort_ctl.p, sort_ctl.bytes(), st);
+        rt::zero(slice_status.p, slice_status.bytes(), st);
+        t_enc.start();
+        PD_LAUNCH(sortk::tile_gene_kernel, blocks_for(std::max<uint32_t>(S, 1)), 256, 0, st, (const uint32_t*)d_key_off.p, S, stiles, tile_gene.p);
+        sortk::EncodeSrc es;
+        memset(&es, 0, sizeof(es));
+        es.res = d_res; es.gene_off = d_gene_off.p; es.key_off = d_key_off.p; es.tile_gene = tile_gene.p;
+        es.S = S; es.k = (int)k; es.base = base; es.mult = (uint64_t)(pw / (base ? base : 1)); es.seq_bits = seq_bits;
+        es.lo = lo; es.hi = hi; es.N = N; es.vt = vt;
+        const bool r32 = rank_bits <= 32;
+        const unsigned sgrid = std::min<uint32_t>(stiles, (uint32_t)sms * 8);
+        if (r32) PD_LAUNCH(sortk::kmer_slice_kernel<uint32_t>, sgrid, sortk::kThreads, 0, st, es, stiles, passes, d_hist, d_tot + 4, slice_status.p, keys_a.p);
+        else PD_LAUNCH(sortk::kmer_slice_kernel<uint64_t>, sgrid, sortk::kThreads, 0, st, es, stiles, passes, d_hist, d_tot + 4, slice_status.p, keys_a.p);
+        PD_LAUNCH(sortk::digit_bins_kernel, 1, sortk::kRadix, 0, st, (const uint32_t*)d_hist, passes, d_bins, d_tot);
+        uint32_t h_Nr = 0;
+        rt::d2h(&h_Nr, d_tot, sizeof(uint32_t), st);
+        t_enc.stop();
+        rt::sync(st);
+        launches += 3;
+        const uint64_t Nr = h_Nr;
+        if (Nr < 2) throw Error(PD_ERR_UNSUPPORTED, "sharded build: a rank's slice of the k-mer ranks is (nearly) empty — use fewer ranks for this input");
+        t_sort.start();
+        const uint32_t rtiles = sortk::tiles_of(Nr);
+        rt::DevBuf<uint32_t> sort_status((size_t)passes * rtiles * sortk::kRadix);
+        rt::zero(sort_status.p, sort_status.bytes(), st);
+        uint64_t* src = keys_a.p;
+        uint64_t* dst = keys_b.p;
+        {
+            const size_t smem = sortk::sweep_smem_bytes();
+            void (*kfn)(sortk::SweepArgs, sortk::EncodeSrc) = sortk::onesweep_kernel<0, uint32_t>;
+            rt::allow_smem(kfn, smem);
+            for (int p = 0; p < passes; p++) {
+                sortk::SweepArgs sa;
+                sa.keys = src; sa.out = dst; sa.n = Nr; sa.shift = seq_bits + 8 * p;
+                sa.bins = d_bins + p * sortk::kRadix;
+                sa.status = sort_status.p + (size_t)p * rtiles * sortk::kRadix;
+                sa.counter = d_tot + 8 + p;
+                PD_LAUNCH(kfn, rtiles, sortk::kThreads, smem, st, sa, es);
+                launches++;
+                std::swap(src, dst);
+            }
+        }
+        const uint64_t* sorted = src;
+        t_sort.stop();
+
+        // count dedup + rank groups of the slice (group boundaries are rank boundaries: no group straddles two slices)
+        t_grp.start();
+        const uint32_t tiles = (uint32_t)((Nr + ik::kEntTile - 1) / ik::kEntTile);
+        rt::DevBuf<uint32_t> tile_h((size_t)tiles + 1), tile_g((size_t)tiles + 1), d_spur(4);
+        rt::zero(d_spur.p, 4 * sizeof(uint32_t), st);
+        PD_LAUNCH(ik::entry_count_kernel, tiles, ik::kEntThreads, 0, st, sorted, Nr, seq_bits, tile_h.p, tile_g.p);
+        scratch.ensure(prims::scan_tmp_words(tiles) + 16);
+        prims::exclusive_scan_u32(tile_h.p, tile_h.p, tiles, scratch.p, d_total.p, st, &launches);
+        prims::exclusive_scan_u32(tile_g.p, tile_g.p, tiles, scratch.p, d_total.p + 1, st, &launches);
+        uint32_t h_tot[2] = {0, 0};
+        rt::d2h(h_tot, d_total.p, sizeof(h_tot), st);
+        rt::sync(st);
+        const uint32_t Ur = h_tot[0], g_counted = h_tot[1];
+        sh.U_r = Ur;
+        sh.post_slice.alloc(Ur);
+        sh.heads_slice.alloc((size_t)Ur / 32 + 2);
+        const uint32_t multi_cap = (uint32_t)std::min<uint64_t>((uint64_t)Ur, (uint64_t)(Nr - Ur) + 16);  // every repeated entry merged at least one key
+        sh.multi_slice.alloc((size_t)2 * multi_cap + 2);
+        rt::DevBuf<uint32_t> cnt_tmp(Ur), gid_tmp(Ur), head_tmp((size_t)g_counted + 1);
+        rt::zero(sh.heads_slice.p, sh.heads_slice.bytes(), st);
+        ik::ShardOut so;
+        memset(&so, 0, sizeof(so));
+        so.head_bits = sh.heads_slice.p;
+        so.multi = sh.multi_slice.p;
+        so.n_multi = d_spur.p + 1;
+        so.multi_cap = multi_cap;
+        so.tail_merge = shard_rank + 1 == shard_world ? 1u : 0u;
+        PD_LAUNCH(ik::entry_apply_kernel, tiles, ik::kEntThreads, 0, st, sorted, Nr, seq_bits, (const uint32_t*)tile_h.p, (const uint32_t*)tile_g.p, Ur,
+                  sh.post_slice.p, cnt_tmp.p, gid_tmp.p, head_tmp.p, (uint64_t*)nullptr, d_spur.p, so);
+        PD_LAUNCH(ik::group_tail_kernel, 1, 32, 0, st, head_tmp.p, g_counted, (const uint32_t*)d_spur.p, Ur);
+        // this slice's part of the per-gene list-class counts and of total_visited (library.cpp:327)
+        sh.gene_counts.alloc((size_t)2 * S);
+        rt::zero(sh.gene_counts.p, sh.gene_counts.bytes(), st);
+        PD_LAUNCH(ik::fwd_count_kernel, blocks_for(Ur, 256 * ik::kFwdItems), 256, 0, st, (const uint32_t*)sh.post_slice.p, (const uint32_t*)gid_tmp.p,
+                  (const uint32_t*)head_tmp.p, Ur, sk::kShortList, sk::kHugeList, sh.gene_counts.p, sh.gene_counts.p + S);
+        uint32_t h_sp[2] = {0, 0};
+        rt::d2h(h_sp, d_spur.p, sizeof(h_sp), st);
+        launches += 4;
+        t_grp.stop();
+        t_sh.stop();
+        t_all.stop();
+        rt::sync(st);
+        if (h_sp[1] > multi_cap) throw Error(PD_ERR_CUDA, "sharded build: repeated-entry list overflow");
+        sh.M_r = h_sp[1];
+        sh.launches = launches;
+        sh.ms = t_all.ms();
+        info.U = Ur;   // until pd_shard_finish: this slice only
+        info.build_ms[0] = total ? t_hist.ms() : 0;
+        info.build_ms[1] = t_enc.ms();
+        info.build_ms[2] = t_sort.ms();
+        info.build_ms[3] = t_grp.ms();
+        info.build_ms[5] = sh.ms;
+        info.build_ms[6] = t_h2d.ms();
+        info.build_ms[7] = (double)launches;
+        info.max_kseq = h_flags[2];
+        rt::stream_destroy(st);
+        return;
+    }
+
     if (N > 0) {
         // ---- k-mer keys + sort by rank in one sweep per digit (library.cpp:234-265, 270-278): the keys are made from the
         // residues twice (digit counts, first pass) instead of being written and re-read in gene order; stability keeps
@@ -463,9 +612,12 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         ent_gid.alloc(U);
         grp_head.alloc((size_t)g_counted + 1);
         if (opt.keep_sorted) ent_rank.alloc(U);
+        ik::ShardOut so;
+        memset(&so, 0, sizeof(so));
+        so.tail_merge = 1;
         PD_LAUNCH(ik::entry_apply_kernel, tiles, ik::kEntThreads, 0, st, (const uint64_t*)sorted, N, seq_bits, (const uint32_t*)tile_h.p,
                   (const uint32_t*)tile_g.p, U, post.p, post_cnt.p, ent_gid.p, grp_head.p, opt.keep_sorted ? ent_rank.p : (uint64_t*)nullptr,
-                  d_spur.p);
+                  d_spur.p, so);
         PD_LAUNCH(ik::group_tail_kernel, 1, 32, 0, st, grp_head.p, g_counted, (const uint32_t*)d_spur.p, U);
         launches += 2;
         t_grp.stop();
@@ -476,8 +628,8 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         rt::DevBuf<uint32_t> gene_tot((size_t)S + 1), cur3(std::max<size_t>((size_t)3 * S, 1));
         rt::zero(d_lookups.p, 2 * sizeof(unsigned long long), st);
         PD_LAUNCH(ik::fwd_count_kernel, blocks_for(U, 256 * ik::kFwdItems), 256, 0, st, (const uint32_t*)post.p, (const uint32_t*)ent_gid.p,
-                  (const uint32_t*)grp_head.p, U, sk::kShortList, sk::kHugeList, cls.p);
-        PD_LAUNCH(ik::fwd_totals_kernel, blocks_for((uint64_t)S + 1), 256, 0, st, (const unsigned long long*)cls.p, S, gene_tot.p);
+                  (const uint32_t*)grp_head.p, U, sk::kShortList, sk::kHugeList, cls.p, (unsigned long long*)nullptr);
+        PD_LAUNCH(ik::fwd_totals_kernel, blocks_for((uint64_t)S + 1), 256, 0, st, (const unsigned long long*)cls.p, S, 0u, S, gene_tot.p);
         launches += 2;
         scratch.ensure(prims::scan_tmp_words((uint64_t)S + 1) + 16);
         prims::exclusive_scan_u32(gene_tot.p, fwd_ptr.p, (uint64_t)S + 1, scratch.p, nullptr, st, &launches);
@@ -495,7 +647,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
             rt::zero(bucket_cur.p, sizeof(uint32_t) * ik::kMaxBuckets, st);
             PD_LAUNCH(ik::fwd_partition_kernel, blocks_for(U, ik::kPartTile), ik::kPartThreads, 0, st, (const uint32_t*)post.p,
                       (const uint32_t*)post_cnt.p, (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, U, S, sk::kShortList, sk::kHugeList,
-                      bshift, (const uint32_t*)fwd_ptr.p, bucket_cur.p, records.p);
+                      bshift, (const uint32_t*)fwd_ptr.p, bucket_cur.p, records.p, 0u, S);
             PD_LAUNCH(ik::fwd_cursor_init_kernel, blocks_for(S), 256, 0, st, (const unsigned long long*)cls.p, (const uint32_t*)fwd_ptr.p, S,
                       cur3.p);
             PD_LAUNCH(ik::fwd_place_kernel, blocks_for(R, 256 * ik::kFwdItems), 256, 0, st, (const uint4*)records.p, R, cur3.p, fwd.p, fwd_cnt.p);
@@ -545,6 +697,176 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
                N ? (double)((float)lookups / (float)N) : 0.0);
         printf("Index: %u genes, %u genomes, k=%d, base=%u, %llu k-mers, %llu postings, %llu shared (gene,k-mer) pairs\n", S, G, k, base,
                (unsigned long long)N, (unsigned long long)info.U, (unsigned long long)info.R);
+        printf("------------\n\n");
+        fflush(stdout);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ sharded build, steps 2 and 3
+
+void Index::shard_buffers(uint64_t max_entries, uint64_t max_multi, pd_shard_arrays* out) {
+    if (!shard) throw Error(PD_ERR_INVALID, "not a sharded build in progress");
+    rt::set_device(device);
+    Shard& sh = *shard;
+    if (max_entries < sh.U_r || max_multi < sh.M_r) throw Error(PD_ERR_INVALID, "segment smaller than this rank's slice");
+    sh.seg = (max_entries + 4095) / 4096 * 4096;
+    sh.mseg = std::max<uint64_t>(max_multi, 1);
+    if (sh.seg * shard_world >= 0x7FFFFFFFull) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more (padded) entries");
+    rt::stream_t st = rt::stream_create();
+    post.alloc((size_t)sh.seg * shard_world);
+    sh.heads_all.alloc((size_t)sh.seg / 32 * shard_world);
+    sh.multi_all.alloc((size_t)2 * sh.mseg * shard_world);
+    uint32_t* my_post = post.p + (size_t)sh.seg * shard_rank;
+    uint32_t* my_heads = sh.heads_all.p + (size_t)sh.seg / 32 * shard_rank;
+    rt::zero(my_heads, sizeof(uint32_t) * (sh.seg / 32), st);
+    rt::d2d(my_post, sh.post_slice.p, sizeof(uint32_t) * sh.U_r, st);
+    rt::d2d(my_heads, sh.heads_slice.p, sizeof(uint32_t) * (((size_t)sh.U_r + 31) / 32), st);
+    if (sh.seg > sh.U_r)
+        PD_LAUNCH(ik::shard_pad_kernel, blocks_for(sh.seg - sh.U_r), 256, 0, st, my_post, my_heads, sh.U_r, (uint32_t)sh.seg);
+    rt::d2d(sh.multi_all.p + (size_t)2 * sh.mseg * shard_rank, sh.multi_slice.p, sizeof(uint32_t) * 2 * sh.M_r, st);
+    rt::sync(st);
+    rt::stream_destroy(st);
+    sh.post_slice.release();
+    sh.heads_slice.release();
+    sh.multi_slice.release();
+    out->d_post = post.p;
+    out->d_heads = sh.heads_all.p;
+    out->d_multi = sh.multi_all.p;
+    out->seg = sh.seg;
+    out->mseg = sh.mseg;
+}
+
+void Index::shard_finish(const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds) {
+    if (!shard || !shard->seg) throw Error(PD_ERR_INVALID, "pd_shard_buffers has not been called");
+    rt::set_device(device);
+    Shard& sh = *shard;
+    const uint32_t S = info.S, G = info.G, W = shard_world;
+    const uint64_t E = sh.seg * W;   // entries incl. padding
+    rt::stream_t st = rt::stream_create();
+    Timer t_fin(st);
+    t_fin.start();
+    uint64_t launches = 0;
+    uint64_t U_all = 0;
+    std::vector<uint32_t> h_nm(W);
+    for (uint32_t r = 0; r < W; r++) {
+        if (entries_of_rank[r] > sh.seg || multi_of_rank[r] > sh.mseg) throw Error(PD_ERR_INVALID, "a rank's slice exceeds the segment size");
+        U_all += entries_of_rank[r];
+        h_nm[r] = (uint32_t)multi_of_rank[r];
+    }
+    // ---- multiplicities of the repeated entries of all slices
+    post_cnt.alloc((size_t)E);
+    {
+        rt::DevBuf<uint32_t> d_nm(W);
+        rt::h2d(d_nm.p, h_nm.data(), sizeof(uint32_t) * W, st);
+        PD_LAUNCH(ik::shard_multi_kernel, blocks_for(sh.mseg * W), 256, 0, st, (const uint32_t*)sh.multi_all.p, (const uint32_t*)d_nm.p, (uint32_t)sh.mseg,
+                  (uint32_t)sh.seg, W, post_cnt.p);
+        launches++;
+        rt::sync(st);  // d_nm, h_nm
+    }
+    // ---- every entry's group, every group's first entry, from the head bits
+    const uint64_t words = E / 32;
+    const uint32_t htiles = (uint32_t)((words + ik::kHeadTileWords - 1) / ik::kHeadTileWords);
+    rt::DevBuf<uint32_t> tile_heads((size_t)htiles + 1), d_tot(4), scratch(prims::scan_tmp_words(std::max<uint64_t>(htiles, (uint64_t)S + 1)) + 16);
+    PD_LAUNCH(ik::head_count_kernel, htiles, 128, 0, st, (const uint32_t*)sh.heads_all.p, words, tile_heads.p);
+    prims::exclusive_scan_u32(tile_heads.p, tile_heads.p, htiles, scratch.p, d_tot.p, st, &launches);
+    uint32_t h_heads = 0;
+    rt::d2h(&h_heads, d_tot.p, sizeof(uint32_t), st);
+    rt::sync(st);
+    ent_gid.alloc((size_t)E);
+    grp_head.alloc((size_t)h_heads + 1);
+    rt::zero(d_tot.p, 4 * sizeof(uint32_t), st);
+    PD_LAUNCH(ik::head_apply_kernel, htiles, 128, 0, st, (const uint32_t*)sh.heads_all.p, words, E, (const uint32_t*)tile_heads.p, ent_gid.p, grp_head.p);
+    PD_LAUNCH(ik::group_tail_kernel, 1, 32, 0, st, grp_head.p, h_heads, (const uint32_t*)d_tot.p, (uint32_t)E);
+    launches += 3;
+
+    // ---- per-gene class counts and total_visited: all-reduced by the caller; the query partition from per-genome sums
+    rt::d2d(cls.p, sh.gene_counts.p, sizeof(unsigned long long) * S, st);
+    rt::d2d(d_visited.p, sh.gene_counts.p + S, sizeof(unsigned long long) * S, st);
+    rt::DevBuf<unsigned long long> d_cost((size_t)G + 2);
+    rt::zero(d_cost.p, d_cost.bytes(), st);
+    PD_LAUNCH(ik::genome_cost_kernel, blocks_for(S), 256, 0, st, (const unsigned long long*)d_visited.p, (const uint2*)meta.p, S, d_cost.p, d_cost.p + G);
+    launches++;
+    std::vector<unsigned long long> h_cost((size_t)G + 2);
+    rt::d2h(h_cost.data(), d_cost.p, sizeof(unsigned long long) * ((size_t)G + 1), st);
+    rt::sync(st);
+    genome_lists();   // genome_ptr: genes per genome
+    {
+        // genes of a genome contiguous and genomes ascending  <=>  genome_rows is the identity
+        bool ok = true;
+        for (uint32_t s = 0; s < S && ok; s += 1 + S / 65536) ok = genome_rows[s] == s;
+        for (uint32_t g = 0; g <= G && ok; g++) ok = genome_ptr[g] <= S && (g == 0 || genome_ptr[g] >= genome_ptr[g - 1]);
+        if (ok) {   // exact check on the device-made list boundaries: first and last gene of every genome
+            for (uint32_t g = 0; g < G && ok; g++)
+                if (genome_ptr[g + 1] > genome_ptr[g]) ok = genome_rows[genome_ptr[g]] == genome_ptr[g] && genome_rows[genome_ptr[g + 1] - 1] == genome_ptr[g + 1] - 1;
+        }
+        if (!ok) throw Error(PD_ERR_UNSUPPORTED, "sharded build: genes of a genome must be contiguous and genomes ascending");
+    }
+    unsigned long long all_cost = 0;
+    for (uint32_t g = 0; g < G; g++) all_cost += h_cost[g];
+    std::vector<uint32_t> gcut(W + 1, 0);
+    gcut[W] = G;
+    {
+        unsigned long long cum = 0;
+        uint32_t g = 0;
+        for (uint32_t p = 1; p < W; p++) {
+            const unsigned long long target = all_cost / W * p + (all_cost % W) * p / W;
+            while (g < G && cum + h_cost[g] / 2 < target) cum += h_cost[g++];   // nearest genome boundary
+            gcut[p] = std::max(g, gcut[p - 1]);
+        }
+    }
+    for (uint32_t p = 0; p <= W; p++) bounds[p] = genome_ptr[gcut[p]];
+    own_g0 = gcut[shard_rank];
+    own_g1 = gcut[shard_rank + 1];
+    own_row0 = bounds[shard_rank];
+    own_row1 = bounds[shard_rank + 1];
+
+    // ---- forward lists of this rank's rows only (library.cpp:308-330)
+    rt::DevBuf<uint32_t> gene_tot((size_t)S + 1), cur3(std::max<size_t>((size_t)3 * S, 1));
+    PD_LAUNCH(ik::fwd_totals_kernel, blocks_for((uint64_t)S + 1), 256, 0, st, (const unsigned long long*)cls.p, S, own_row0, own_row1, gene_tot.p);
+    prims::exclusive_scan_u32(gene_tot.p, fwd_ptr.p, (uint64_t)S + 1, scratch.p, nullptr, st, &launches);
+    uint32_t h_R = 0;
+    rt::d2h(&h_R, fwd_ptr.p + S, sizeof(uint32_t), st);
+    rt::sync(st);
+    const uint32_t R = h_R;
+    fwd.alloc(std::max<size_t>(R, 1));
+    fwd_cnt.alloc(std::max<size_t>(R, 1));
+    if (R) {
+        const uint32_t bshift = (uint32_t)std::max(0, (int)info.seq_bits - 8);
+        rt::DevBuf<uint4> records(R);
+        rt::DevBuf<uint32_t> bucket_cur(ik::kMaxBuckets);
+        rt::zero(bucket_cur.p, sizeof(uint32_t) * ik::kMaxBuckets, st);
+        PD_LAUNCH(ik::fwd_partition_kernel, blocks_for(E, ik::kPartTile), ik::kPartThreads, 0, st, (const uint32_t*)post.p, (const uint32_t*)post_cnt.p,
+                  (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, (uint32_t)E, S, sk::kShortList, sk::kHugeList, bshift, (const uint32_t*)fwd_ptr.p,
+                  bucket_cur.p, records.p, own_row0, own_row1);
+        PD_LAUNCH(ik::fwd_cursor_init_kernel, blocks_for(S), 256, 0, st, (const unsigned long long*)cls.p, (const uint32_t*)fwd_ptr.p, S, cur3.p);
+        PD_LAUNCH(ik::fwd_place_kernel, blocks_for(R, 256 * ik::kFwdItems), 256, 0, st, (const uint4*)records.p, R, cur3.p, fwd.p, fwd_cnt.p);
+        launches += 3;
+        rt::sync(st);  // records, bucket_cur
+    }
+    PD_LAUNCH(ik::gene_visited_kernel, blocks_for((uint64_t)S * 32), 256, 0, st, (const uint2*)fwd.p, (const uint32_t*)fwd_ptr.p, S, sk::kShortList,
+              (unsigned long long*)nullptr, fam_key.p, (unsigned long long*)nullptr);
+    launches += 3;
+    t_fin.stop();
+    rt::sync(st);
+    uint64_t pad = 0;
+    for (uint32_t r = 0; r < W; r++) pad += sh.seg - entries_of_rank[r];
+    info.U = U_all;
+    info.groups = (uint64_t)h_heads - pad;
+    info.R = R;
+    info.lookups = h_cost[G];
+    info.build_ms[4] = t_fin.ms();
+    info.build_ms[5] += t_fin.ms();
+    info.build_ms[7] += (double)launches;
+    ent_gid.release();
+    grp_head.release();
+    rt::stream_destroy(st);
+    delete shard;
+    shard = nullptr;
+    if (opt.verbose) {
+        printf("------------\nCOMPUTATIONAL COSTS: \nTotal cost: %llu lookups\nLinear ratio: %g\n", (unsigned long long)info.lookups,
+               info.N ? (double)((float)info.lookups / (float)info.N) : 0.0);
+        printf("Index: %u genes, %u genomes, k=%d, %llu k-mers, %llu postings; rank %u of %u holds forward lists of genes [%u, %u): %llu entries\n", S, G,
+               info.k, (unsigned long long)info.N, (unsigned long long)info.U, shard_rank, W, own_row0, own_row1, (unsigned long long)info.R);
         printf("------------\n\n");
         fflush(stdout);
     }
@@ -994,6 +1316,8 @@ static uint64_t run_rows(ScoreContext& c, uint32_t n, const uint32_t* d_genes, u
 
 void Index::compute_scores(uint32_t genome, pd_scores* out) {
     if (genome >= info.G) throw Error(PD_ERR_INVALID, "unknown genome");
+    if (shard) throw Error(PD_ERR_INVALID, "sharded build not finished (pd_shard_finish)");
+    if (shard_world > 1 && (genome < own_g0 || genome >= own_g1)) throw Error(PD_ERR_INVALID, "genome belongs to another rank of the sharded index");
     rt::set_device(device);
     genome_lists();
     trace::Clock tc;
@@ -1083,6 +1407,8 @@ void Index::compute_scores(uint32_t genome, pd_scores* out) {
 
 void Index::genome_edges(uint32_t genome, pd_edges* out) {
     if (genome >= info.G) throw Error(PD_ERR_INVALID, "unknown genome");
+    if (shard) throw Error(PD_ERR_INVALID, "sharded build not finished (pd_shard_finish)");
+    if (shard_world > 1 && (genome < own_g0 || genome >= own_g1)) throw Error(PD_ERR_INVALID, "genome belongs to another rank of the sharded index");
     rt::set_device(device);
     genome_lists();
     ScoreContext* cp = acquire();
@@ -1177,6 +1503,9 @@ void Index::genome_edges(uint32_t genome, pd_edges* out) {
 
 void Index::score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_per_launch, float* d_best_hit, pd_score_stats* st_out) {
     if (row_begin > row_end || row_end > info.S) throw Error(PD_ERR_INVALID, "bad row range");
+    if (shard) throw Error(PD_ERR_INVALID, "sharded build not finished (pd_shard_finish)");
+    if (shard_world > 1 && row_begin < row_end && (row_begin < own_row0 || row_end > own_row1))
+        throw Error(PD_ERR_INVALID, "rows belong to another rank of the sharded index");
     rt::set_device(device);
     trace::Clock ta;
     ScoreContext* cp = acquire();
@@ -1259,6 +1588,7 @@ void Index::entries(uint64_t* rank, uint32_t* seq, uint32_t* count, uint32_t* gs
     rt::set_device(device);
     const uint32_t U = (uint32_t)info.U;
     if (!U) return;
+    if (shard_world > 1) throw Error(PD_ERR_INVALID, "pd_entries is not available on a sharded index");
     if ((rank || gs || gl) && !opt.keep_sorted) throw Error(PD_ERR_INVALID, "pd_entries: ranks and groups need pd_options.keep_sorted");
     rt::stream_t st = rt::stream_create();
     if (seq) {

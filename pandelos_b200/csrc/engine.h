@@ -62,6 +62,24 @@ struct Index {
     std::vector<ScoreContext*> free_ctx;
     std::vector<ScoreContext*> all_ctx;
 
+    // ---- sharded build (several GPUs, one process each, build ONE index together: pd_build_shard / pd_shard_buffers /
+    // pd_shard_finish).  Rank r sorts and groups the k-mers of the r-th slice of the rank space; the slices' postings are
+    // all-gathered by the caller; forward lists are made for the rank's own query rows [own_row0, own_row1) only.
+    uint32_t shard_rank = 0, shard_world = 1;
+    uint32_t own_row0 = 0, own_row1 = 0, own_g0 = 0, own_g1 = 0;
+    struct Shard {
+        uint32_t U_r = 0, M_r = 0;                     // entries / repeated entries of this rank's slice
+        uint64_t seg = 0, mseg = 0;                    // segment sizes of the gathered arrays
+        rt::DevBuf<uint32_t> post_slice, heads_slice, multi_slice;
+        rt::DevBuf<unsigned long long> gene_counts;    // [S] list-class counts, [S] total_visited: this slice's part, all-reduced in place by the caller
+        rt::DevBuf<uint32_t> heads_all, multi_all;
+        double ms = 0;
+        uint64_t launches = 0;
+    };
+    Shard* shard = nullptr;
+    void shard_buffers(uint64_t max_entries, uint64_t max_multi, pd_shard_arrays* out);
+    void shard_finish(const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds);
+
     ~Index();
     void build(const uint8_t* residues, bool residues_on_device, const uint64_t* offsets, const uint32_t* genome_ids, uint32_t S,
                int32_t k, const pd_options* o);

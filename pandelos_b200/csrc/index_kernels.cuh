@@ -183,12 +183,24 @@ __global__ void __launch_bounds__(kEntThreads) entry_count_kernel(const uint64_t
     }
 }
 
+// What a rank of a sharded build (rank-range slices, sort_kernels.cuh) sends to the others besides its postings: one bit per
+// entry, set where the entry opens a rank group, and the list of its entries held more than once (position, count).
+// All null / zero in a single-GPU build.
+struct ShardOut {
+    uint32_t* head_bits;   // zero-initialised, (U + 31) / 32 words
+    uint32_t* multi;       // pairs (entry, count)
+    uint32_t* n_multi;     // running length of `multi`
+    uint32_t multi_cap;    // pairs that fit (the counter keeps running)
+    uint32_t tail_merge;   // 0: this slice does not end the entry list, the reference's tail merge (library.cpp:300-306) is not its business
+};
+
 __global__ void __launch_bounds__(kEntThreads) entry_apply_kernel(const uint64_t* __restrict__ keys, uint64_t N, int seq_bits,
                                                                    const uint32_t* __restrict__ tile_head_off,
                                                                    const uint32_t* __restrict__ tile_ghead_off, uint32_t U,
                                                                    uint32_t* __restrict__ post, uint32_t* __restrict__ post_cnt,
                                                                    uint32_t* __restrict__ ent_gid, uint32_t* __restrict__ grp_head,
-                                                                   uint64_t* __restrict__ ent_rank, uint32_t* __restrict__ spurious) {
+                                                                   uint64_t* __restrict__ ent_rank, uint32_t* __restrict__ spurious,
+                                                                   ShardOut so) {
     __shared__ uint32_t w_h[kEntWarps], w_g[kEntWarps];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -223,7 +235,7 @@ __global__ void __launch_bounds__(kEntThreads) entry_apply_kernel(const uint64_t
             const uint32_t e = e0 + __popc(hm[j] & lt);
             bool gh = (gm[j] >> lane) & 1u;
             uint32_t gid = g0 + __popc(gm[j] & lt) + (gh ? 1u : 0u) - 1u;
-            if (gh && e == U - 1 && e != 0) {  // the tail merge: the last entry joins the group before it
+            if (gh && e == U - 1 && e != 0 && so.tail_merge) {  // the tail merge: the last entry joins the group before it
                 gh = false;
                 gid -= 1;
                 *spurious = 1;
@@ -237,6 +249,16 @@ __global__ void __launch_bounds__(kEntThreads) entry_apply_kernel(const uint64_t
             post_cnt[e] = cnt;
             ent_gid[e] = gid;
             if (gh) grp_head[gid] = e;
+            if (so.head_bits) {
+                if (gh) atomicOr(&so.head_bits[e >> 5], 1u << (e & 31u));
+                if (cnt > 1) {
+                    const uint32_t m = atomicAdd(so.n_multi, 1u);
+                    if (m < so.multi_cap) {
+                        so.multi[2 * (size_t)m] = e;
+                        so.multi[2 * (size_t)m + 1] = cnt;
+                    }
+                }
+            }
             if (ent_rank) ent_rank[e] = kv[j] >> seq_bits;
         }
         e0 += __popc(hm[j]);
@@ -260,7 +282,8 @@ __device__ __forceinline__ uint32_t list_class(uint32_t gl, uint32_t short_max, 
 static const int kFwdItems = 4;
 __global__ void __launch_bounds__(256) fwd_count_kernel(const uint32_t* __restrict__ post, const uint32_t* __restrict__ ent_gid,
                                                          const uint32_t* __restrict__ grp_head, uint32_t U, uint32_t short_max,
-                                                         uint32_t huge_min, unsigned long long* __restrict__ cls) {
+                                                         uint32_t huge_min, unsigned long long* __restrict__ cls,
+                                                         unsigned long long* __restrict__ visited) {
     const uint64_t e0 = (uint64_t)blockIdx.x * (256u * kFwdItems) + threadIdx.x;
     uint32_t g[kFwdItems], gl[kFwdItems], p[kFwdItems];
 #pragma unroll
@@ -273,15 +296,20 @@ __global__ void __launch_bounds__(256) fwd_count_kernel(const uint32_t* __restri
     for (int j = 0; j < kFwdItems; j++) gl[j] = g[j] != 0xFFFFFFFFu ? grp_head[g[j] + 1] - grp_head[g[j]] : 0u;
 #pragma unroll
     for (int j = 0; j < kFwdItems; j++)
-        if (gl[j] >= 2) atomicAdd(&cls[p[j] & 0x7FFFFFFFu], 1ull << (kClsBits * list_class(gl[j], short_max, huge_min)));
+        if (gl[j] >= 2) {
+            atomicAdd(&cls[p[j] & 0x7FFFFFFFu], 1ull << (kClsBits * list_class(gl[j], short_max, huge_min)));
+            if (visited) atomicAdd(&visited[p[j] & 0x7FFFFFFFu], (unsigned long long)gl[j]);  // sharded build: this slice's part of total_visited
+        }
 }
 
 // tot[s] = forward entries of gene s (tot has S + 1 entries, the last one 0: its exclusive scan is fwd_ptr)
-__global__ void __launch_bounds__(256) fwd_totals_kernel(const unsigned long long* __restrict__ cls, uint32_t S, uint32_t* __restrict__ tot) {
+// (genes outside [row0, row1) get none: a rank of a sharded build keeps forward lists for its own query rows only)
+__global__ void __launch_bounds__(256) fwd_totals_kernel(const unsigned long long* __restrict__ cls, uint32_t S, uint32_t row0, uint32_t row1,
+                                                          uint32_t* __restrict__ tot) {
     const uint32_t s = blockIdx.x * 256u + threadIdx.x;
     if (s > S) return;
     uint32_t t = 0;
-    if (s < S) {
+    if (s < S && s >= row0 && s < row1) {
         const unsigned long long c = cls[s];
         t = (uint32_t)(c & kClsMask) + (uint32_t)((c >> kClsBits) & kClsMask) + (uint32_t)((c >> (2 * kClsBits)) & kClsMask);
     }
@@ -307,7 +335,7 @@ __global__ void __launch_bounds__(kPartThreads) fwd_partition_kernel(const uint3
                                                                       const uint32_t* __restrict__ grp_head, uint32_t U, uint32_t S,
                                                                       uint32_t short_max, uint32_t huge_min, uint32_t bshift,
                                                                       const uint32_t* __restrict__ fwd_ptr, uint32_t* __restrict__ bucket_cur,
-                                                                      uint4* __restrict__ records) {
+                                                                      uint4* __restrict__ records, uint32_t row0, uint32_t row1) {
     __shared__ uint32_t cnt[kMaxBuckets];
     __shared__ uint32_t base[kMaxBuckets];
     const unsigned tid = threadIdx.x;
@@ -334,7 +362,8 @@ __global__ void __launch_bounds__(kPartThreads) fwd_partition_kernel(const uint3
         const uint32_t gl = (have >> j & 1u) ? grp_head[g + 1] - gs : 0u;
         rec[j].gs = gs;
         rec[j].gl_multi = gl;
-        if (gl < 2) have &= ~(1u << j);
+        const uint32_t gene = rec[j].gene & 0x7FFFFFFFu;
+        if (gl < 2 || gene < row0 || gene >= row1) have &= ~(1u << j);
     }
 #pragma unroll
     for (int j = 0; j < kPartItems; j++) {
@@ -432,13 +461,86 @@ __global__ void __launch_bounds__(256) gene_visited_kernel(const uint2* __restri
             ka = oa < ka ? oa : ka;
         }
         if (lane == 0) {
-            visited[s] = v;
+            if (visited) visited[s] = v;   // (null in a sharded build: the all-reduced totals are already there)
             fam_key[s] = kl != 0x7FFFFFFFu ? kl : ka;
             if (v) atomicAdd(&s_sum, v);
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0 && s_sum) atomicAdd(total, s_sum);
+    if (threadIdx.x == 0 && s_sum && total) atomicAdd(total, s_sum);
+}
+
+// ---- sharded build, after the all-gather: the entry list is `segs` segments of `seg` entries, segment r = rank r's slice
+// padded with filler entries (no gene, each its own group).
+// fill: the padding of this rank's own segment, before it is sent
+__global__ void __launch_bounds__(256) shard_pad_kernel(uint32_t* __restrict__ post, uint32_t* __restrict__ head_bits, uint32_t U, uint32_t seg) {
+    const uint32_t e = U + blockIdx.x * 256u + threadIdx.x;
+    if (e >= seg) return;
+    post[e] = 0x7FFFFFFFu;
+    atomicOr(&head_bits[e >> 5], 1u << (e & 31u));
+}
+// group heads per 4096-entry tile, then (after a scan) every entry's group and every group's first entry
+static const int kHeadTileWords = 128;
+__global__ void __launch_bounds__(128) head_count_kernel(const uint32_t* __restrict__ head_bits, uint64_t words, uint32_t* __restrict__ tile_heads) {
+    __shared__ uint32_t s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const uint64_t w = (uint64_t)blockIdx.x * kHeadTileWords + threadIdx.x;
+    uint32_t n = w < words ? (uint32_t)__popc(head_bits[w]) : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&s_n, n);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_heads[blockIdx.x] = s_n;
+}
+__global__ void __launch_bounds__(128) head_apply_kernel(const uint32_t* __restrict__ head_bits, uint64_t words, uint64_t E,
+                                                          const uint32_t* __restrict__ tile_head_off, uint32_t* __restrict__ ent_gid,
+                                                          uint32_t* __restrict__ grp_head) {
+    __shared__ uint32_t scratch[33];
+    const uint64_t w = (uint64_t)blockIdx.x * kHeadTileWords + threadIdx.x;
+    const uint32_t bits = w < words ? head_bits[w] : 0u;
+    uint32_t tot;
+    uint32_t g = tile_head_off[blockIdx.x] + prims::block_excl_scan<128>((uint32_t)__popc(bits), scratch, &tot);  // heads before this word
+    for (uint32_t b = 0; b < 32; b++) {
+        const uint64_t e = w * 32 + b;
+        if (e >= E) break;
+        if ((bits >> b) & 1u) {
+            grp_head[g] = (uint32_t)e;
+            g++;
+        }
+        ent_gid[e] = g - 1;
+    }
+}
+// post_cnt at the positions of the gathered multi lists (segment r: pairs (entry inside rank r's slice, count))
+__global__ void __launch_bounds__(256) shard_multi_kernel(const uint32_t* __restrict__ multi, const uint32_t* __restrict__ n_of_seg, uint32_t mseg,
+                                                           uint32_t seg, uint32_t segs, uint32_t* __restrict__ post_cnt) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256u + threadIdx.x;
+    const uint32_t r = (uint32_t)(i / mseg), j = (uint32_t)(i % mseg);
+    if (r >= segs || j >= n_of_seg[r]) return;
+    const uint32_t* m = multi + 2 * ((size_t)r * mseg + j);
+    post_cnt[(size_t)r * seg + m[0]] = m[1];
+}
+// cost[genome] += total_visited + 1 of its genes (query partitioning by posting-list volume, library.cpp:327)
+__global__ void __launch_bounds__(256) genome_cost_kernel(const unsigned long long* __restrict__ visited, const uint2* __restrict__ meta, uint32_t S,
+                                                           unsigned long long* __restrict__ cost, unsigned long long* __restrict__ total) {
+    const uint32_t s = blockIdx.x * 256u + threadIdx.x;
+    const bool in = s < S;
+    const uint32_t g = in ? meta[s].y : 0xFFFFFFFFu;
+    unsigned long long v = in ? visited[s] : 0ull;
+    // genes of a genome sit together: a warp whose lanes all belong to one genome adds once
+    const uint32_t g0 = __shfl_sync(0xffffffffu, g, 0);
+    const bool uniform = __all_sync(0xffffffffu, g == g0);
+    if (!uniform && in) atomicAdd(&cost[g], v + 1ull);
+    unsigned long long c = in ? v + 1ull : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        v += __shfl_xor_sync(0xffffffffu, v, d);
+        c += __shfl_xor_sync(0xffffffffu, c, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (uniform && g0 != 0xFFFFFFFFu) atomicAdd(&cost[g0], c);
+        if (v) atomicAdd(total, v);
+    }
 }
 
 // per-entry group (start, length) for pd_entries (tests / diagnostics)

@@ -139,6 +139,87 @@ __global__ void __launch_bounds__(kThreads) kmer_hist_kernel(EncodeSrc s, uint32
     }
 }
 
+// Rank-range sharding of the build (several GPUs build one index): the keys of THIS rank's slice [lo, hi), compacted in
+// gene order into `out`, and their digit counts for all passes.  Persistent CTAs take 4096-position tiles by ticket; a
+// tile's kept keys follow those of all tiles before it (one status word per tile, look-back by a whole warp: 32 tiles
+// per step).  Every rank reads all residues (1 B per k-mer) and keeps about 1 / world of the keys.
+template <typename RankT>
+__global__ void __launch_bounds__(kThreads) kmer_slice_kernel(EncodeSrc s, uint32_t tiles, int passes, uint32_t* __restrict__ hist,
+                                                               uint32_t* __restrict__ counter, uint32_t* status, uint64_t* __restrict__ out) {
+    __shared__ uint32_t h[2][kMaxPasses * kRadix];
+    __shared__ uint8_t val[256];
+    __shared__ uint32_t scratch[33];
+    __shared__ uint32_t s_tile, s_before;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (unsigned i = tid; i < 2 * kMaxPasses * kRadix; i += kThreads) (&h[0][0])[i] = 0;
+    val[tid] = s.vt.v[tid];
+    uint32_t* mine = h[(tid >> 5) & 1];
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(counter, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= tiles) break;
+        const uint64_t i0 = (uint64_t)tile * kTile + (uint64_t)tid * kItems;
+        const uint32_t n = i0 >= s.N ? 0u : (uint32_t)(s.N - i0 < (uint64_t)kItems ? s.N - i0 : (uint64_t)kItems);
+        uint64_t key[kItems];
+        uint32_t kept = 0;
+        const int seq_bits = s.seq_bits;
+        encode_keys<RankT>(s, val, i0, n, s.tile_gene[tile], s.tile_gene[tile + 1], [&](int j, uint64_t kv) {
+            key[j] = kv;
+            if (kv != kNoKey) {
+                kept++;
+                const uint64_t r = kv >> seq_bits;
+                for (int p = 0; p < passes; p++) atomicAdd(&mine[p * kRadix + ((unsigned)(r >> (8 * p)) & 0xFFu)], 1u);
+            }
+        });
+        uint32_t total;
+        const uint32_t off = prims::block_excl_scan<kThreads>(kept, scratch, &total);
+        if (warp == 0) {
+            uint32_t before = 0;
+            volatile uint32_t* st = status;
+            if (tile == 0) {
+                if (lane == 0) st[0] = kInclusive | total;
+            } else {
+                if (lane == 0) st[tile] = total + 1u;
+                for (long long hi = tile;; hi -= 32) {
+                    const long long idx = hi - 1 - (long long)lane;
+                    uint32_t v = 0;
+                    if (idx >= 0) {
+                        while ((v = st[idx]) == 0u) {
+                        }
+                    }
+                    const unsigned inc = __ballot_sync(0xffffffffu, idx >= 0 && (v & kInclusive) != 0u);
+                    uint32_t c = 0;
+                    if (idx >= 0) {
+                        if (!inc) c = v - 1u;
+                        else {
+                            const unsigned first = __ffs(inc) - 1;  // the nearest tile that knows its inclusive prefix
+                            c = lane < first ? v - 1u : (lane == first ? (v & ~kInclusive) : 0u);
+                        }
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+                    before += c;
+                    if (inc) break;
+                }
+                if (lane == 0) st[tile] = kInclusive | (before + total);
+            }
+            if (lane == 0) s_before = before;
+        }
+        __syncthreads();
+        uint64_t pos = (uint64_t)s_before + off;
+#pragma unroll
+        for (int j = 0; j < kItems; j++)
+            if (key[j] != kNoKey) out[pos++] = key[j];
+    }
+    __syncthreads();
+    for (unsigned i = tid; i < (unsigned)passes * kRadix; i += kThreads) {
+        const uint32_t v = h[0][i] + h[1][i];
+        if (v) atomicAdd(&hist[i], v);
+    }
+}
+
 // bins[p][d] = keys with a smaller digit p; totals[0] = number of keys
 __global__ void __launch_bounds__(kRadix) digit_bins_kernel(const uint32_t* __restrict__ hist, int passes, uint32_t* __restrict__ bins,
                                                              uint32_t* __restrict__ totals) {

@@ -124,3 +124,49 @@ def score_and_gather(pn, gather, rank, row_begin):
         gather.gather_chunk(c)
     gather.wait()
     return total
+
+
+class _DeviceArray:
+    """A raw device pointer as something torch.as_tensor understands (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+def _as_tensor(ptr, count, bits, device):
+    """int32 / int64 tensor over `count` elements at `ptr` (device memory of `device`, or host memory for the CPU tests)."""
+    import torch
+    if device is not None and getattr(device, "type", "cpu") == "cuda":
+        return torch.as_tensor(_DeviceArray(ptr, count, "<i4" if bits == 32 else "<i8"), device=device)
+    import ctypes as C
+    ct = C.c_int32 if bits == 32 else C.c_int64
+    return torch.from_numpy(np.ctypeslib.as_array((ct * int(count)).from_address(int(ptr))))
+
+
+def build_sharded(dist, native, k, data, device=None, device_index=-1, residues_device_ptr=None, **engine_kw):
+    """ONE index built by all ranks of `dist` together (include/pandelos_b200.h, pd_build_shard): every rank sorts and groups
+    the k-mers of its slice of the rank space, the slices' postings / group-head bits / repeated-entry lists are
+    all-gathered in place, the per-gene partial counts all-reduced, and every rank makes the forward lists of its own,
+    genome-aligned, posting-list-volume-balanced share of the query rows.  Returns (PangeneNative, bounds[world + 1]):
+    rank r serves genes [bounds[r], bounds[r + 1]).  The only collectives of the multi-GPU path (NCCL over NVLink on
+    GPUs; gloo in the CPU tests): 1 tiny all-gather, 1 all-reduce of 16 S bytes, 3 all-gathers (4 B per posting in all)."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    pn = native.PangeneNative(k, data, device=device_index, residues_device_ptr=residues_device_ptr, shard=(rank, world), **engine_kw)
+    si = pn.shard_info
+    cpu = device is None or getattr(device, "type", "cpu") != "cuda"
+    mine = torch.tensor([int(si.entries), int(si.multi)], dtype=torch.int64, device=None if cpu else device)
+    counts = torch.zeros(2 * world, dtype=torch.int64, device=None if cpu else device)
+    dist.all_gather_into_tensor(counts, mine)
+    counts = counts.cpu().numpy().reshape(world, 2)
+    S = data.sequences_count
+    dist.all_reduce(_as_tensor(si.d_gene_counts, 2 * S, 64, device))
+    arr = pn.shard_buffers(int(counts[:, 0].max()), int(counts[:, 1].max()))
+    seg, mseg = int(arr.seg), int(arr.mseg)
+    for ptr, per in ((arr.d_post, seg), (arr.d_heads, seg // 32), (arr.d_multi, 2 * mseg)):
+        whole = _as_tensor(ptr, per * world, 32, device)
+        dist.all_gather_into_tensor(whole, whole[rank * per:(rank + 1) * per])   # in place: segment r is rank r's
+    if not cpu:
+        torch.cuda.current_stream().synchronize()   # the engine works on its own streams
+    bounds = pn.shard_finish(counts[:, 0], counts[:, 1])
+    return pn, bounds.astype(np.int64)

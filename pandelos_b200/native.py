@@ -58,6 +58,14 @@ class EdgesStruct(C.Structure):
                 ("cells", C.c_uint64), ("owner", C.c_void_p)]
 
 
+class ShardInfo(C.Structure):
+    _fields_ = [("entries", C.c_uint64), ("multi", C.c_uint64), ("kmers", C.c_uint64), ("d_gene_counts", C.c_void_p)]
+
+
+class ShardArrays(C.Structure):
+    _fields_ = [("d_post", C.c_void_p), ("d_heads", C.c_void_p), ("d_multi", C.c_void_p), ("seg", C.c_uint64), ("mseg", C.c_uint64)]
+
+
 _lib = None
 _lib_path = None
 
@@ -90,6 +98,11 @@ def load(path=None):
     L.pd_edges_release.argtypes = [C.c_void_p, C.POINTER(EdgesStruct)]
     L.pd_score_partition_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(ScoreStats)]
     L.pd_partition_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p]
+    L.pd_build_shard.restype = C.c_int
+    L.pd_build_shard.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(Options), C.c_uint32, C.c_uint32,
+                                 C.POINTER(C.c_void_p), C.POINTER(ShardInfo)]
+    L.pd_shard_buffers.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(ShardArrays)]
+    L.pd_shard_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib, _lib_path = L, path
     return L
 
@@ -153,7 +166,10 @@ class PangeneNative:
     """Device-resident index + scoring calls: `new PangeneNative(k, pid)` / `generateScoresPart(g)`."""
 
     def __init__(self, k, data, device=-1, verbose=False, contexts=0, hash_log2=0, cell_capacity=0, keep_sorted=False,
-                 residues_device_ptr=None):
+                 residues_device_ptr=None, shard=None):
+        """shard = (rank, world): this process builds slice `rank` of an index that `world` processes build together
+        (pd_build_shard); the caller exchanges the slices and calls shard_buffers / shard_finish
+        (pandelos_b200.multigpu.build_sharded does all of it over torch.distributed)."""
         L = load()
         self._L = L
         self._data = data
@@ -161,7 +177,15 @@ class PangeneNative:
         opt = Options(int(device), int(verbose), int(contexts), int(hash_log2), int(cell_capacity), int(keep_sorted), 0)
         h = C.c_void_p()
         S = data.sequences_count
-        if residues_device_ptr is not None:
+        self.shard_info = None
+        if shard is not None:
+            rank, world = shard
+            self.shard_info = ShardInfo()
+            on_dev = residues_device_ptr is not None
+            rc = L.pd_build_shard(C.c_void_p(int(residues_device_ptr)) if on_dev else data.residues.ctypes.data, int(on_dev),
+                                  data.offsets.ctypes.data, data.sequenceGenome.ctypes.data, S, self.k, C.byref(opt), int(rank), int(world),
+                                  C.byref(h), C.byref(self.shard_info))
+        elif residues_device_ptr is not None:
             rc = L.pd_build_device(C.c_void_p(int(residues_device_ptr)), data.offsets.ctypes.data, data.sequenceGenome.ctypes.data, S,
                                    self.k, C.byref(opt), C.byref(h))
         else:
@@ -229,6 +253,20 @@ class PangeneNative:
         e = EdgesStruct()
         _check(self._L.pd_genome_edges(self._h, int(genome), C.byref(e)))
         return e, (lambda: self._L.pd_edges_release(self._h, C.byref(e)))
+
+    # ---- sharded build, steps 2 and 3 (include/pandelos_b200.h)
+    def shard_buffers(self, max_entries, max_multi):
+        a = ShardArrays()
+        _check(self._L.pd_shard_buffers(self._h, int(max_entries), int(max_multi), C.byref(a)))
+        return a
+
+    def shard_finish(self, entries_of_rank, multi_of_rank):
+        e = np.ascontiguousarray(entries_of_rank, dtype=np.uint64)
+        m = np.ascontiguousarray(multi_of_rank, dtype=np.uint64)
+        b = np.zeros(len(e) + 1, np.uint32)
+        _check(self._L.pd_shard_finish(self._h, e.ctypes.data, m.ctypes.data, b.ctypes.data))
+        _check(self._L.pd_info(self._h, C.byref(self.info)))
+        return b
 
     # ---- diagnostics / partitions
     def gene_stats(self):

@@ -84,3 +84,61 @@ def test_balanced_bounds_properties():
         assert set(bs.tolist()) <= set(gb.tolist())
     with pytest.raises(ValueError):
         multigpu.genome_bounds(np.array([0, 1, 0]), 2)
+
+
+def _shard_worker(rank, world, port, emu_path, out_dir, low_complexity):
+    """Sharded build (every rank sorts its slice of the k-mer ranks, postings all-gathered) vs one single-process index."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(HERE))
+    from pandelos_b200 import digest, multigpu, native, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    native.load(emu_path)
+    w = synth.generate(6, 25, 60.0, 0.1, 93, low_complexity=low_complexity)
+    k = 3
+    data = native.PangeneIData(w.residues, w.offsets, w.genome_of)
+    pn, bounds = multigpu.build_sharded(dist, native, k, data)
+    one = native.PangeneNative(k, data)
+    ok = pn.info.U == one.info.U and pn.info.lookups == one.info.lookups and pn.info.groups == one.info.groups and pn.info.N == one.info.N
+    gb = multigpu.genome_bounds(w.genome_of, one.info.G)
+    ok = ok and set(bounds.tolist()) <= set(gb.tolist()) and bounds[0] == 0 and bounds[-1] == one.info.S
+    kl, tv = pn.gene_stats()
+    kl1, tv1 = one.gene_stats()
+    ok = ok and (kl == kl1).all() and (tv == tv1).all()
+    g0, g1 = int(np.searchsorted(gb, bounds[rank])), int(np.searchsorted(gb, bounds[rank + 1]))
+    cells = 0
+    for g in range(one.info.G):
+        if g0 <= g < g1:
+            a, b = pn.generateScoresPart(g), one.generateScoresPart(g)
+            ok = ok and digest.scores_digest(a) == digest.scores_digest(b) and pn.last_stats.pairs == one.last_stats.pairs
+            src, dst, sc, _ = pn.genomeEdges(g)
+            src1, dst1, sc1, _ = one.genomeEdges(g)
+            ok = ok and sorted(zip(src.tolist(), dst.tolist(), sc.view(np.uint32).tolist())) == sorted(zip(src1.tolist(), dst1.tolist(), sc1.view(np.uint32).tolist()))
+            cells += a.scoresCount
+        else:
+            try:
+                pn.generateScoresPart(g)
+                ok = False
+            except native.PdError as e:
+                ok = ok and e.code == native.PD_ERR_INVALID
+    if g1 > g0:
+        st = pn.score_partition_device(int(bounds[rank]), int(bounds[rank + 1]))
+        ok = ok and st.cells == cells
+    open(os.path.join(out_dir, "result%d" % rank), "w").write("ok %d" % cells if ok else "mismatch")
+    pn.close()
+    one.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,low", [(2, 0.0), (3, 0.3)])
+def test_sharded_build_matches_the_single_process_index(tmp_path, world, low):
+    import build_emu
+    import torch.multiprocessing as mp
+    emu = build_emu.build()
+    port = 31500 + (os.getpid() % 2000) + world
+    mp.spawn(_shard_worker, args=(world, port, emu, str(tmp_path), low), nprocs=world, join=True)
+    res = [open(os.path.join(str(tmp_path), "result%d" % r)).read() for r in range(world)]
+    assert all(r.startswith("ok") for r in res), res
+    assert sum(int(r.split()[1]) for r in res) > 0
