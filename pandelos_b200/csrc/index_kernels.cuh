@@ -194,7 +194,7 @@ struct ShardOut {
     uint32_t tail_merge;   // 0: this slice does not end the entry list, the reference's tail merge (library.cpp:300-306) is not its business
 };
 
-__global__ void __launch_bounds__(kEntThreads) entry_apply_kernel(const uint64_t* __restrict__ keys, uint64_t N, int seq_bits,
+__global__ void __launch_bounds__(kEntThreads, 2) entry_apply_kernel(const uint64_t* __restrict__ keys, uint64_t N, int seq_bits,
                                                                    const uint32_t* __restrict__ tile_head_off,
                                                                    const uint32_t* __restrict__ tile_ghead_off, uint32_t U,
                                                                    uint32_t* __restrict__ post, uint32_t* __restrict__ post_cnt,

@@ -146,14 +146,15 @@ __global__ void __launch_bounds__(kThreads) kmer_hist_kernel(EncodeSrc s, uint32
 template <typename RankT>
 __global__ void __launch_bounds__(kThreads) kmer_slice_kernel(EncodeSrc s, uint32_t tiles, int passes, uint32_t* __restrict__ hist,
                                                                uint32_t* __restrict__ counter, uint32_t* status, uint64_t* __restrict__ out) {
-    __shared__ uint32_t h[2][kMaxPasses * kRadix];
+    __shared__ uint32_t h[kMaxPasses * kRadix];
+    __shared__ uint64_t stage[kTile];   // the tile's kept keys, packed: they leave in coalesced runs
     __shared__ uint8_t val[256];
     __shared__ uint32_t scratch[33];
     __shared__ uint32_t s_tile, s_before;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (unsigned i = tid; i < 2 * kMaxPasses * kRadix; i += kThreads) (&h[0][0])[i] = 0;
+    for (unsigned i = tid; i < kMaxPasses * kRadix; i += kThreads) h[i] = 0;
     val[tid] = s.vt.v[tid];
-    uint32_t* mine = h[(tid >> 5) & 1];
+    uint32_t* mine = h;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_tile = atomicAdd(counter, 1u);
@@ -175,6 +176,12 @@ __global__ void __launch_bounds__(kThreads) kmer_slice_kernel(EncodeSrc s, uint3
         });
         uint32_t total;
         const uint32_t off = prims::block_excl_scan<kThreads>(kept, scratch, &total);
+        {
+            uint32_t q = off;
+#pragma unroll
+            for (int j = 0; j < kItems; j++)
+                if (key[j] != kNoKey) stage[q++] = key[j];
+        }
         if (warp == 0) {
             uint32_t before = 0;
             volatile uint32_t* st = status;
@@ -208,14 +215,12 @@ __global__ void __launch_bounds__(kThreads) kmer_slice_kernel(EncodeSrc s, uint3
             if (lane == 0) s_before = before;
         }
         __syncthreads();
-        uint64_t pos = (uint64_t)s_before + off;
-#pragma unroll
-        for (int j = 0; j < kItems; j++)
-            if (key[j] != kNoKey) out[pos++] = key[j];
+        const uint64_t before = s_before;
+        for (uint32_t i = tid; i < total; i += kThreads) out[before + i] = stage[i];
     }
     __syncthreads();
     for (unsigned i = tid; i < (unsigned)passes * kRadix; i += kThreads) {
-        const uint32_t v = h[0][i] + h[1][i];
+        const uint32_t v = h[i];
         if (v) atomicAdd(&hist[i], v);
     }
 }
