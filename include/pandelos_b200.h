@@ -151,9 +151,10 @@ int pd_score_partition_device(pd_index* ix, uint32_t row_begin, uint32_t row_end
  *   1. all-gathers (entries, multi) of pd_shard_info over the ranks,
  *   2. all-reduces (sum, uint64) pd_shard_info.d_gene_counts [2 x S] in place,
  *   3. calls pd_shard_buffers(max entries, max multi) and all-gathers each of the three arrays IN PLACE (segment r of each
- *      array is rank r's, already filled on that rank),
- *   4. calls pd_shard_finish: group structure of the whole entry list, genome-aligned query partition by posting-list
- *      volume (bounds[world + 1], identical on every rank), forward lists for THIS rank's rows [bounds[rank],
+ *      array is rank r's, already filled on that rank); the postings — by far the largest — may still be in flight during 4a,
+ *   4a. calls pd_shard_groups: multiplicities, group structure of the whole entry list from the head bits, genome-aligned
+ *      query partition by posting-list volume (bounds[world + 1], identical on every rank),
+ *   4b. once the postings have arrived, calls pd_shard_finish: forward lists for THIS rank's rows [bounds[rank],
  *      bounds[rank + 1]).
  * Afterwards pd_compute_scores / pd_genome_edges / pd_score_partition_device serve this rank's genomes / rows only
  * (PD_ERR_INVALID for others), with results bit-identical to a single-GPU index.  Needs the genes of a genome to be
@@ -173,7 +174,8 @@ typedef struct pd_shard_arrays {
 int pd_build_shard(const uint8_t* residues, int32_t residues_on_device, const uint64_t* offsets, const uint32_t* genome_of, uint32_t S,
                    int32_t k, const pd_options* opt, uint32_t rank, uint32_t world, pd_index** out, pd_shard_info* info);
 int pd_shard_buffers(pd_index* ix, uint64_t max_entries, uint64_t max_multi, pd_shard_arrays* out);
-int pd_shard_finish(pd_index* ix, const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds);
+int pd_shard_groups(pd_index* ix, const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds);
+int pd_shard_finish(pd_index* ix);
 
 /* Splits [0, S) into `parts` contiguous gene ranges of near-equal total_visited (query partitioning by
  * posting-list volume); bounds[parts+1].  snap_to_genomes != 0 moves boundaries to genome boundaries. */

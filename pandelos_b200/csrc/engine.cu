@@ -647,7 +647,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
             rt::zero(bucket_cur.p, sizeof(uint32_t) * ik::kMaxBuckets, st);
             PD_LAUNCH(ik::fwd_partition_kernel, blocks_for(U, ik::kPartTile), ik::kPartThreads, 0, st, (const uint32_t*)post.p,
                       (const uint32_t*)post_cnt.p, (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, U, S, sk::kShortList, sk::kHugeList,
-                      bshift, (const uint32_t*)fwd_ptr.p, bucket_cur.p, records.p, 0u, S);
+                      bshift, (const uint32_t*)fwd_ptr.p, bucket_cur.p, records.p, 0u, S, (const uint32_t*)nullptr, (const uint32_t*)nullptr);
             PD_LAUNCH(ik::fwd_cursor_init_kernel, blocks_for(S), 256, 0, st, (const unsigned long long*)cls.p, (const uint32_t*)fwd_ptr.p, S,
                       cur3.p);
             PD_LAUNCH(ik::fwd_place_kernel, blocks_for(R, 256 * ik::kFwdItems), 256, 0, st, (const uint4*)records.p, R, cur3.p, fwd.p, fwd_cnt.p);
@@ -736,8 +736,11 @@ void Index::shard_buffers(uint64_t max_entries, uint64_t max_multi, pd_shard_arr
     out->mseg = sh.mseg;
 }
 
-void Index::shard_finish(const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds) {
+// Step 3a: everything that does not need the gathered postings — multiplicities, group structure from the head bits,
+// per-gene counts, the query partition.  The caller may run it while the all-gather of the postings is still in flight.
+void Index::shard_groups(const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds) {
     if (!shard || !shard->seg) throw Error(PD_ERR_INVALID, "pd_shard_buffers has not been called");
+    if (shard->grouped) throw Error(PD_ERR_INVALID, "pd_shard_groups called twice");
     rt::set_device(device);
     Shard& sh = *shard;
     const uint32_t S = info.S, G = info.G, W = shard_world;
@@ -766,16 +769,17 @@ void Index::shard_finish(const uint64_t* entries_of_rank, const uint64_t* multi_
     // ---- every entry's group, every group's first entry, from the head bits
     const uint64_t words = E / 32;
     const uint32_t htiles = (uint32_t)((words + ik::kHeadTileWords - 1) / ik::kHeadTileWords);
-    rt::DevBuf<uint32_t> tile_heads((size_t)htiles + 1), d_tot(4), scratch(prims::scan_tmp_words(std::max<uint64_t>(htiles, (uint64_t)S + 1)) + 16);
-    PD_LAUNCH(ik::head_count_kernel, htiles, 128, 0, st, (const uint32_t*)sh.heads_all.p, words, tile_heads.p);
+    sh.tile_heads.alloc((size_t)htiles + 1);
+    rt::DevBuf<uint32_t>& tile_heads = sh.tile_heads;
+    rt::DevBuf<uint32_t> d_tot(4), scratch(prims::scan_tmp_words(std::max<uint64_t>(htiles, (uint64_t)S + 1)) + 16);
+    PD_LAUNCH(ik::head_count_kernel, htiles, ik::kHeadTileWords, 0, st, (const uint32_t*)sh.heads_all.p, words, tile_heads.p);
     prims::exclusive_scan_u32(tile_heads.p, tile_heads.p, htiles, scratch.p, d_tot.p, st, &launches);
     uint32_t h_heads = 0;
     rt::d2h(&h_heads, d_tot.p, sizeof(uint32_t), st);
     rt::sync(st);
-    ent_gid.alloc((size_t)E);
     grp_head.alloc((size_t)h_heads + 1);
     rt::zero(d_tot.p, 4 * sizeof(uint32_t), st);
-    PD_LAUNCH(ik::head_apply_kernel, htiles, 128, 0, st, (const uint32_t*)sh.heads_all.p, words, E, (const uint32_t*)tile_heads.p, ent_gid.p, grp_head.p);
+    PD_LAUNCH(ik::head_apply_kernel, htiles, ik::kHeadTileWords, 0, st, (const uint32_t*)sh.heads_all.p, words, (const uint32_t*)tile_heads.p, grp_head.p);
     PD_LAUNCH(ik::group_tail_kernel, 1, 32, 0, st, grp_head.p, h_heads, (const uint32_t*)d_tot.p, (uint32_t)E);
     launches += 3;
 
@@ -820,6 +824,32 @@ void Index::shard_finish(const uint64_t* entries_of_rank, const uint64_t* multi_
     own_row0 = bounds[shard_rank];
     own_row1 = bounds[shard_rank + 1];
 
+    uint64_t pad = 0;
+    for (uint32_t r = 0; r < W; r++) pad += sh.seg - entries_of_rank[r];
+    t_fin.stop();
+    rt::sync(st);
+    info.U = U_all;
+    info.groups = (uint64_t)h_heads - pad;
+    info.lookups = h_cost[G];
+    sh.fin_ms = t_fin.ms();
+    sh.fin_launches = launches;
+    sh.grouped = true;
+    rt::stream_destroy(st);
+}
+
+// Step 3b: forward lists of this rank's rows from the gathered postings.
+void Index::shard_finish() {
+    if (!shard || !shard->grouped) throw Error(PD_ERR_INVALID, "pd_shard_groups has not been called");
+    rt::set_device(device);
+    Shard& sh = *shard;
+    const uint32_t S = info.S, G = info.G, W = shard_world;
+    const uint64_t E = sh.seg * W;
+    rt::stream_t st = rt::stream_create();
+    Timer t_fin(st);
+    t_fin.start();
+    uint64_t launches = sh.fin_launches;
+    rt::DevBuf<uint32_t>& tile_heads = sh.tile_heads;
+    rt::DevBuf<uint32_t> scratch(prims::scan_tmp_words((uint64_t)S + 1) + 16);
     // ---- forward lists of this rank's rows only (library.cpp:308-330)
     rt::DevBuf<uint32_t> gene_tot((size_t)S + 1), cur3(std::max<size_t>((size_t)3 * S, 1));
     PD_LAUNCH(ik::fwd_totals_kernel, blocks_for((uint64_t)S + 1), 256, 0, st, (const unsigned long long*)cls.p, S, own_row0, own_row1, gene_tot.p);
@@ -836,8 +866,8 @@ void Index::shard_finish(const uint64_t* entries_of_rank, const uint64_t* multi_
         rt::DevBuf<uint32_t> bucket_cur(ik::kMaxBuckets);
         rt::zero(bucket_cur.p, sizeof(uint32_t) * ik::kMaxBuckets, st);
         PD_LAUNCH(ik::fwd_partition_kernel, blocks_for(E, ik::kPartTile), ik::kPartThreads, 0, st, (const uint32_t*)post.p, (const uint32_t*)post_cnt.p,
-                  (const uint32_t*)ent_gid.p, (const uint32_t*)grp_head.p, (uint32_t)E, S, sk::kShortList, sk::kHugeList, bshift, (const uint32_t*)fwd_ptr.p,
-                  bucket_cur.p, records.p, own_row0, own_row1);
+                  (const uint32_t*)nullptr, (const uint32_t*)grp_head.p, (uint32_t)E, S, sk::kShortList, sk::kHugeList, bshift, (const uint32_t*)fwd_ptr.p,
+                  bucket_cur.p, records.p, own_row0, own_row1, (const uint32_t*)sh.heads_all.p, (const uint32_t*)tile_heads.p);
         PD_LAUNCH(ik::fwd_cursor_init_kernel, blocks_for(S), 256, 0, st, (const unsigned long long*)cls.p, (const uint32_t*)fwd_ptr.p, S, cur3.p);
         PD_LAUNCH(ik::fwd_place_kernel, blocks_for(R, 256 * ik::kFwdItems), 256, 0, st, (const uint4*)records.p, R, cur3.p, fwd.p, fwd_cnt.p);
         launches += 3;
@@ -848,16 +878,10 @@ void Index::shard_finish(const uint64_t* entries_of_rank, const uint64_t* multi_
     launches += 3;
     t_fin.stop();
     rt::sync(st);
-    uint64_t pad = 0;
-    for (uint32_t r = 0; r < W; r++) pad += sh.seg - entries_of_rank[r];
-    info.U = U_all;
-    info.groups = (uint64_t)h_heads - pad;
     info.R = R;
-    info.lookups = h_cost[G];
-    info.build_ms[4] = t_fin.ms();
-    info.build_ms[5] += t_fin.ms();
+    info.build_ms[4] = t_fin.ms() + sh.fin_ms;
+    info.build_ms[5] += t_fin.ms() + sh.fin_ms;
     info.build_ms[7] += (double)launches;
-    ent_gid.release();
     grp_head.release();
     rt::stream_destroy(st);
     delete shard;

@@ -72,13 +72,15 @@ struct Index {
         uint64_t seg = 0, mseg = 0;                    // segment sizes of the gathered arrays
         rt::DevBuf<uint32_t> post_slice, heads_slice, multi_slice;
         rt::DevBuf<unsigned long long> gene_counts;    // [S] list-class counts, [S] total_visited: this slice's part, all-reduced in place by the caller
-        rt::DevBuf<uint32_t> heads_all, multi_all;
-        double ms = 0;
-        uint64_t launches = 0;
+        rt::DevBuf<uint32_t> heads_all, multi_all, tile_heads;
+        double ms = 0, fin_ms = 0;
+        uint64_t launches = 0, fin_launches = 0;
+        bool grouped = false;
     };
     Shard* shard = nullptr;
     void shard_buffers(uint64_t max_entries, uint64_t max_multi, pd_shard_arrays* out);
-    void shard_finish(const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds);
+    void shard_groups(const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds);
+    void shard_finish();
 
     ~Index();
     void build(const uint8_t* residues, bool residues_on_device, const uint64_t* offsets, const uint32_t* genome_ids, uint32_t S,

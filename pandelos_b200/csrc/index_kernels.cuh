@@ -335,25 +335,59 @@ __global__ void __launch_bounds__(kPartThreads) fwd_partition_kernel(const uint3
                                                                       const uint32_t* __restrict__ grp_head, uint32_t U, uint32_t S,
                                                                       uint32_t short_max, uint32_t huge_min, uint32_t bshift,
                                                                       const uint32_t* __restrict__ fwd_ptr, uint32_t* __restrict__ bucket_cur,
-                                                                      uint4* __restrict__ records, uint32_t row0, uint32_t row1) {
+                                                                      uint4* __restrict__ records, uint32_t row0, uint32_t row1,
+                                                                      const uint32_t* __restrict__ head_bits, const uint32_t* __restrict__ tile_head_off) {
     __shared__ uint32_t cnt[kMaxBuckets];
     __shared__ uint32_t base[kMaxBuckets];
+    __shared__ uint32_t wpre[kPartTile / 32 + 1];  // head bits given instead of ent_gid: group heads before every word of this tile
+    __shared__ uint32_t wbits[kPartTile / 32];
     const unsigned tid = threadIdx.x;
     for (unsigned i = tid; i < kMaxBuckets; i += kPartThreads) cnt[i] = 0;
-    __syncthreads();
     const uint32_t e0 = blockIdx.x * (uint32_t)kPartTile;
+    if (head_bits) {
+        // sharded build: an entry's group = number of group heads at or before it, minus one (the tile = kPartTile entries =
+        // kPartTile / 32 words of head bits; tile_head_off = heads before the tile)
+        if (tid < kPartTile / 32) {
+            const uint64_t w = (uint64_t)blockIdx.x * (kPartTile / 32) + tid;
+            const uint32_t b = (w * 32 < U) ? head_bits[w] : 0u;
+            wbits[tid] = b;
+            uint32_t incl = (uint32_t)__popc(b);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((tid & 31u) >= (unsigned)d) incl += o;
+            }
+            wpre[tid + 1] = incl;  // inclusive inside the warp; the second warp adds the first one's total below
+        }
+        __syncthreads();
+        if (tid >= 32 && tid < kPartTile / 32) wpre[tid + 1] += wpre[32];
+        if (tid == 0) wpre[0] = 0;
+    }
+    __syncthreads();
     FwdRecord rec[kPartItems];
     uint32_t pos[kPartItems];
     unsigned have = 0;
     // the gathers level by level over all items (entry -> group -> group bounds), then the ranking atomics: the chains
-    // of the items overlap instead of running one after the other
+    // of the items overlap instead of running one after the other.  Entries of genes outside [row0, row1) drop out first.
 #pragma unroll
     for (int j = 0; j < kPartItems; j++) {
-        const uint32_t e = e0 + j * kPartThreads + tid;
+        const uint32_t l = j * kPartThreads + tid;
+        const uint32_t e = e0 + l;
         const bool in = e < U;
-        rec[j].gs = in ? ent_gid[e] : 0u;  // the group id for now
         rec[j].gene = in ? post[e] : 0u;   // gene | bit 31
-        if (in) have |= 1u << j;
+        const uint32_t gene = rec[j].gene & 0x7FFFFFFFu;
+        const bool want = in && gene >= row0 && gene < row1;
+        uint32_t g = 0;
+        if (want) {
+            if (head_bits) {
+                const uint32_t wi = l >> 5, b = l & 31u;
+                g = tile_head_off[blockIdx.x] + wpre[wi] + (uint32_t)__popc(wbits[wi] & (0xFFFFFFFFu >> (31u - b))) - 1u;
+            } else {
+                g = ent_gid[e];
+            }
+            have |= 1u << j;
+        }
+        rec[j].gs = g;  // the group id for now
     }
 #pragma unroll
     for (int j = 0; j < kPartItems; j++) {
@@ -362,8 +396,7 @@ __global__ void __launch_bounds__(kPartThreads) fwd_partition_kernel(const uint3
         const uint32_t gl = (have >> j & 1u) ? grp_head[g + 1] - gs : 0u;
         rec[j].gs = gs;
         rec[j].gl_multi = gl;
-        const uint32_t gene = rec[j].gene & 0x7FFFFFFFu;
-        if (gl < 2 || gene < row0 || gene >= row1) have &= ~(1u << j);
+        if (gl < 2) have &= ~(1u << j);
     }
 #pragma unroll
     for (int j = 0; j < kPartItems; j++) {
@@ -479,9 +512,9 @@ __global__ void __launch_bounds__(256) shard_pad_kernel(uint32_t* __restrict__ p
     post[e] = 0x7FFFFFFFu;
     atomicOr(&head_bits[e >> 5], 1u << (e & 31u));
 }
-// group heads per 4096-entry tile, then (after a scan) every entry's group and every group's first entry
-static const int kHeadTileWords = 128;
-__global__ void __launch_bounds__(128) head_count_kernel(const uint32_t* __restrict__ head_bits, uint64_t words, uint32_t* __restrict__ tile_heads) {
+// group heads per tile of kPartTile entries (the tiles of fwd_partition_kernel), then (after a scan) every group's first entry
+static const int kHeadTileWords = kPartTile / 32;
+__global__ void __launch_bounds__(kHeadTileWords) head_count_kernel(const uint32_t* __restrict__ head_bits, uint64_t words, uint32_t* __restrict__ tile_heads) {
     __shared__ uint32_t s_n;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
@@ -493,22 +526,17 @@ __global__ void __launch_bounds__(128) head_count_kernel(const uint32_t* __restr
     __syncthreads();
     if (threadIdx.x == 0) tile_heads[blockIdx.x] = s_n;
 }
-__global__ void __launch_bounds__(128) head_apply_kernel(const uint32_t* __restrict__ head_bits, uint64_t words, uint64_t E,
-                                                          const uint32_t* __restrict__ tile_head_off, uint32_t* __restrict__ ent_gid,
-                                                          uint32_t* __restrict__ grp_head) {
+__global__ void __launch_bounds__(kHeadTileWords) head_apply_kernel(const uint32_t* __restrict__ head_bits, uint64_t words,
+                                                                     const uint32_t* __restrict__ tile_head_off, uint32_t* __restrict__ grp_head) {
     __shared__ uint32_t scratch[33];
     const uint64_t w = (uint64_t)blockIdx.x * kHeadTileWords + threadIdx.x;
-    const uint32_t bits = w < words ? head_bits[w] : 0u;
+    uint32_t bits = w < words ? head_bits[w] : 0u;
     uint32_t tot;
-    uint32_t g = tile_head_off[blockIdx.x] + prims::block_excl_scan<128>((uint32_t)__popc(bits), scratch, &tot);  // heads before this word
-    for (uint32_t b = 0; b < 32; b++) {
-        const uint64_t e = w * 32 + b;
-        if (e >= E) break;
-        if ((bits >> b) & 1u) {
-            grp_head[g] = (uint32_t)e;
-            g++;
-        }
-        ent_gid[e] = g - 1;
+    uint32_t g = tile_head_off[blockIdx.x] + prims::block_excl_scan<kHeadTileWords>((uint32_t)__popc(bits), scratch, &tot);  // heads before this word
+    while (bits) {
+        const uint32_t b = (uint32_t)__ffs((int)bits) - 1u;
+        bits &= bits - 1u;
+        grp_head[g++] = (uint32_t)(w * 32 + b);
     }
 }
 // post_cnt at the positions of the gathered multi lists (segment r: pairs (entry inside rank r's slice, count))

@@ -163,10 +163,18 @@ def build_sharded(dist, native, k, data, device=None, device_index=-1, residues_
     dist.all_reduce(_as_tensor(si.d_gene_counts, 2 * S, 64, device))
     arr = pn.shard_buffers(int(counts[:, 0].max()), int(counts[:, 1].max()))
     seg, mseg = int(arr.seg), int(arr.mseg)
-    for ptr, per in ((arr.d_post, seg), (arr.d_heads, seg // 32), (arr.d_multi, 2 * mseg)):
+    works = []
+    for ptr, per, wait in ((arr.d_heads, seg // 32, True), (arr.d_multi, 2 * mseg, True), (arr.d_post, seg, False)):
         whole = _as_tensor(ptr, per * world, 32, device)
-        dist.all_gather_into_tensor(whole, whole[rank * per:(rank + 1) * per])   # in place: segment r is rank r's
+        work = dist.all_gather_into_tensor(whole, whole[rank * per:(rank + 1) * per], async_op=not wait)   # in place: segment r is rank r's
+        if not wait:
+            works.append((work, whole))
     if not cpu:
         torch.cuda.current_stream().synchronize()   # the engine works on its own streams
-    bounds = pn.shard_finish(counts[:, 0], counts[:, 1])
+    bounds = pn.shard_groups(counts[:, 0], counts[:, 1])   # while the postings (4 B each, the bulk) are still travelling
+    for work, _ in works:
+        work.wait()
+    if not cpu:
+        torch.cuda.current_stream().synchronize()
+    pn.shard_finish()
     return pn, bounds.astype(np.int64)

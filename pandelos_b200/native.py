@@ -102,7 +102,8 @@ def load(path=None):
     L.pd_build_shard.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(Options), C.c_uint32, C.c_uint32,
                                  C.POINTER(C.c_void_p), C.POINTER(ShardInfo)]
     L.pd_shard_buffers.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(ShardArrays)]
-    L.pd_shard_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pd_shard_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pd_shard_finish.argtypes = [C.c_void_p]
     _lib, _lib_path = L, path
     return L
 
@@ -260,13 +261,16 @@ class PangeneNative:
         _check(self._L.pd_shard_buffers(self._h, int(max_entries), int(max_multi), C.byref(a)))
         return a
 
-    def shard_finish(self, entries_of_rank, multi_of_rank):
+    def shard_groups(self, entries_of_rank, multi_of_rank):
         e = np.ascontiguousarray(entries_of_rank, dtype=np.uint64)
         m = np.ascontiguousarray(multi_of_rank, dtype=np.uint64)
         b = np.zeros(len(e) + 1, np.uint32)
-        _check(self._L.pd_shard_finish(self._h, e.ctypes.data, m.ctypes.data, b.ctypes.data))
-        _check(self._L.pd_info(self._h, C.byref(self.info)))
+        _check(self._L.pd_shard_groups(self._h, e.ctypes.data, m.ctypes.data, b.ctypes.data))
         return b
+
+    def shard_finish(self):
+        _check(self._L.pd_shard_finish(self._h))
+        _check(self._L.pd_info(self._h, C.byref(self.info)))
 
     # ---- diagnostics / partitions
     def gene_stats(self):
