@@ -146,10 +146,13 @@ int pd_score_partition_device(pd_index* ix, uint32_t row_begin, uint32_t row_end
                               float* d_best_hit, pd_score_stats* stats);
 
 /* ---- One index built by several GPUs (one process per GPU; the reference has no counterpart: its preprocessSequences is
- * single-threaded, library.cpp:189-371).  The rank space of the k-mers is cut into `world` slices; rank r makes, sorts,
- * count-dedups and groups the k-mers of slice r (every rank reads all residues, 1 B per k-mer).  The caller then
- *   1. all-gathers (entries, multi) of pd_shard_info over the ranks,
- *   2. all-reduces (sum, uint64) pd_shard_info.d_gene_counts [2 x S] in place,
+ * single-threaded, library.cpp:189-371).  The rank space of the k-mers is cut into `world` slices.  Every rank
+ *   1. pd_build_shard: makes the k-mers of ITS SHARE of the genes (about 1 / world of the residues) and groups them by the
+ *      slice they fall in (one stable pass).  The caller all-gathers pd_shard_keys.send_counts, gets room for its slice with
+ *      pd_shard_recv(sum of what the others hold for it) and moves the keys with one all-to-all (8 B per k-mer; blocks
+ *      arrive in source-rank order = gene order),
+ *   2. pd_shard_sort: sorts, count-dedups and groups the k-mers of its slice.  The caller all-gathers (entries, multi) of
+ *      pd_shard_info over the ranks and all-reduces (sum, uint64) pd_shard_info.d_gene_counts [2 x S] in place,
  *   3. calls pd_shard_buffers(max entries, max multi) and all-gathers each of the three arrays IN PLACE (segment r of each
  *      array is rank r's, already filled on that rank); the postings — by far the largest — may still be in flight during 4a,
  *   4a. calls pd_shard_groups: multiplicities, group structure of the whole entry list from the head bits, genome-aligned
@@ -158,7 +161,12 @@ int pd_score_partition_device(pd_index* ix, uint32_t row_begin, uint32_t row_end
  *      bounds[rank + 1]).
  * Afterwards pd_compute_scores / pd_genome_edges / pd_score_partition_device serve this rank's genomes / rows only
  * (PD_ERR_INVALID for others), with results bit-identical to a single-GPU index.  Needs the genes of a genome to be
- * contiguous and genomes in ascending order (as in every .faa PanDelos reads); pd_entries is not available. */
+ * contiguous and genomes in ascending order (as in every .faa PanDelos reads), at most 32 ranks; pd_entries is not
+ * available.  pandelos_b200/multigpu.py (build_sharded) drives these calls over torch.distributed. */
+typedef struct pd_shard_keys {
+    uint64_t* d_send;           /* device: this rank's keys grouped by destination rank */
+    uint64_t send_counts[32];   /* keys per destination rank */
+} pd_shard_keys;
 typedef struct pd_shard_info {
     uint64_t entries;         /* entries of this rank's slice */
     uint64_t multi;           /* ... of which held more than once by their gene */
@@ -172,7 +180,9 @@ typedef struct pd_shard_arrays {
     uint64_t seg, mseg;
 } pd_shard_arrays;
 int pd_build_shard(const uint8_t* residues, int32_t residues_on_device, const uint64_t* offsets, const uint32_t* genome_of, uint32_t S,
-                   int32_t k, const pd_options* opt, uint32_t rank, uint32_t world, pd_index** out, pd_shard_info* info);
+                   int32_t k, const pd_options* opt, uint32_t rank, uint32_t world, pd_index** out, pd_shard_keys* keys);
+int pd_shard_recv(pd_index* ix, uint64_t n_recv, uint64_t** d_recv);
+int pd_shard_sort(pd_index* ix, pd_shard_info* info);
 int pd_shard_buffers(pd_index* ix, uint64_t max_entries, uint64_t max_multi, pd_shard_arrays* out);
 int pd_shard_groups(pd_index* ix, const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds);
 int pd_shard_finish(pd_index* ix);

@@ -72,19 +72,28 @@ int pd_build_device(const uint8_t* d_residues, const uint64_t* offsets, const ui
 }
 
 int pd_build_shard(const uint8_t* residues, int32_t residues_on_device, const uint64_t* offsets, const uint32_t* genome_of, uint32_t S, int32_t k,
-                   const pd_options* opt, uint32_t rank, uint32_t world, pd_index** out, pd_shard_info* info) {
-    if (!info || world < 2 || rank >= world) {
-        pd::set_last_error("pd_build_shard: needs world >= 2, rank < world, info");
+                   const pd_options* opt, uint32_t rank, uint32_t world, pd_index** out, pd_shard_keys* keys) {
+    if (!keys || world < 2 || rank >= world) {
+        pd::set_last_error("pd_build_shard: needs world >= 2, rank < world, keys");
         return PD_ERR_INVALID;
     }
     const int rc = build_common(residues, residues_on_device != 0, offsets, genome_of, S, k, opt, out, rank, world);
     if (rc != PD_OK) return rc;
     pd::Index& x = (*out)->ix;
-    info->entries = x.shard->U_r;
-    info->multi = x.shard->M_r;
-    info->kmers = 0;
-    info->d_gene_counts = reinterpret_cast<uint64_t*>(x.shard->gene_counts.p);
+    memset(keys, 0, sizeof(*keys));
+    keys->d_send = x.shard->keys_a.p;
+    for (uint32_t r = 0; r < world; r++) keys->send_counts[r] = x.shard->send_counts[r];
     return PD_OK;
+}
+
+int pd_shard_recv(pd_index* ix, uint64_t n_recv, uint64_t** d_recv) {
+    if (!ix || !d_recv) return PD_ERR_INVALID;
+    return guarded([&] { *d_recv = ix->ix.shard_recv(n_recv); });
+}
+
+int pd_shard_sort(pd_index* ix, pd_shard_info* info) {
+    if (!ix || !info) return PD_ERR_INVALID;
+    return guarded([&] { ix->ix.shard_sort(info); });
 }
 
 int pd_shard_buffers(pd_index* ix, uint64_t max_entries, uint64_t max_multi, pd_shard_arrays* out) {

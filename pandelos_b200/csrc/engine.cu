@@ -382,12 +382,13 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         // ================================================================ sharded build: this rank's slice of the rank space
         if (opt.keep_sorted) throw Error(PD_ERR_INVALID, "keep_sorted is not available in a sharded build");
         if (N == 0 || S == 0) throw Error(PD_ERR_UNSUPPORTED, "sharded build of an empty input");
+        if (shard_world > (uint32_t)sortk::kMaxSlices) throw Error(PD_ERR_UNSUPPORTED, "sharded build: more than 32 ranks");
         shard = new Shard;
         Shard& sh = *shard;
         // Slice bounds in the rank space, identical on every rank: cut at multiples of base^(k-2) (a pair of leading
         // letters) so that every slice holds about 1 / world of the k-mers if letters were independent — balance of the
         // sort only, any cut is correct.  Counts of leading pairs are estimated from the alphabet histogram.
-        uint64_t lo = 0, hi = (uint64_t)pw;
+        uint64_t cuts[sortk::kMaxSlices + 1];
         {
             const int lead = k >= 2 ? 2 : 1;
             std::vector<double> f(base);
@@ -398,126 +399,87 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
             }
             const uint64_t unit = (uint64_t)pw / (lead == 2 ? (uint64_t)base * base : (uint64_t)base);
             const uint64_t bins = lead == 2 ? (uint64_t)base * base : base;
-            auto cut = [&](uint32_t r) -> uint64_t {   // first bin of slice r
-                if (r == 0) return 0;
-                if (r >= shard_world) return bins;
+            uint64_t b = 0;
+            double cum = 0;
+            cuts[0] = 0;
+            for (uint32_t r = 1; r < shard_world; r++) {   // first bin of slice r
                 const double want = (double)r / (double)shard_world;
-                double cum = 0;
-                for (uint64_t b = 0; b < bins; b++) {
+                while (b < bins) {
                     const double p = lead == 2 ? f[b / base] * f[b % base] : f[b];
-                    if (cum + p / 2 >= want) return b;
+                    if (cum + p / 2 >= want) break;
                     cum += p;
+                    b++;
                 }
-                return bins;
-            };
-            lo = cut(shard_rank) * unit;
-            hi = shard_rank + 1 == shard_world ? (uint64_t)pw : cut(shard_rank + 1) * unit;
-        }
-        Timer t_sh(st);
-        t_sh.start();
-        rt::DevBuf<uint64_t> keys_a(N), keys_b(N);
-        const uint32_t stiles = sortk::tiles_of(N);
-        const int passes = sortk::passes_of(rank_bits);
-        rt::DevBuf<uint32_t> tile_gene((size_t)stiles + 1), sort_ctl((size_t)2 * passes * sortk::kRadix + 32), slice_status((size_t)stiles + 1);
-        uint32_t* d_hist = sort_ctl.p;
-        uint32_t* d_bins = d_hist + passes * sortk::kRadix;
-        uint32_t* d_tot = d_bins + passes * sortk::kRadix;  // [0] keys kept, [4] slice ticket, [8 + p] tile tickets
-        rt::zero(sort_ctl.p, sort_ctl.bytes(), st);
-        rt::zero(slice_status.p, slice_status.bytes(), st);
-        t_enc.start();
-        PD_LAUNCH(sortk::tile_gene_kernel, blocks_for(std::max<uint32_t>(S, 1)), 256, 0, st, (const uint32_t*)d_key_off.p, S, stiles, tile_gene.p);
-        sortk::EncodeSrc es;
-        memset(&es, 0, sizeof(es));
-        es.res = d_res; es.gene_off = d_gene_off.p; es.key_off = d_key_off.p; es.tile_gene = tile_gene.p;
-        es.S = S; es.k = (int)k; es.base = base; es.mult = (uint64_t)(pw / (base ? base : 1)); es.seq_bits = seq_bits;
-        es.lo = lo; es.hi = hi; es.N = N; es.vt = vt;
-        const bool r32 = rank_bits <= 32;
-        const unsigned sgrid = std::min<uint32_t>(stiles, (uint32_t)sms * 8);
-        if (r32) PD_LAUNCH(sortk::kmer_slice_kernel<uint32_t>, sgrid, sortk::kThreads, 0, st, es, stiles, passes, d_hist, d_tot + 4, slice_status.p, keys_a.p);
-        else PD_LAUNCH(sortk::kmer_slice_kernel<uint64_t>, sgrid, sortk::kThreads, 0, st, es, stiles, passes, d_hist, d_tot + 4, slice_status.p, keys_a.p);
-        PD_LAUNCH(sortk::digit_bins_kernel, 1, sortk::kRadix, 0, st, (const uint32_t*)d_hist, passes, d_bins, d_tot);
-        uint32_t h_Nr = 0;
-        rt::d2h(&h_Nr, d_tot, sizeof(uint32_t), st);
-        t_enc.stop();
-        rt::sync(st);
-        launches += 3;
-        const uint64_t Nr = h_Nr;
-        if (Nr < 2) throw Error(PD_ERR_UNSUPPORTED, "sharded build: a rank's slice of the k-mer ranks is (nearly) empty — use fewer ranks for this input");
-        t_sort.start();
-        const uint32_t rtiles = sortk::tiles_of(Nr);
-        rt::DevBuf<uint32_t> sort_status((size_t)passes * rtiles * sortk::kRadix);
-        rt::zero(sort_status.p, sort_status.bytes(), st);
-        uint64_t* src = keys_a.p;
-        uint64_t* dst = keys_b.p;
-        {
-            const size_t smem = sortk::sweep_smem_bytes();
-            void (*kfn)(sortk::SweepArgs, sortk::EncodeSrc) = sortk::onesweep_kernel<0, uint32_t>;
-            rt::allow_smem(kfn, smem);
-            for (int p = 0; p < passes; p++) {
-                sortk::SweepArgs sa;
-                sa.keys = src; sa.out = dst; sa.n = Nr; sa.shift = seq_bits + 8 * p;
-                sa.bins = d_bins + p * sortk::kRadix;
-                sa.status = sort_status.p + (size_t)p * rtiles * sortk::kRadix;
-                sa.counter = d_tot + 8 + p;
-                PD_LAUNCH(kfn, rtiles, sortk::kThreads, smem, st, sa, es);
-                launches++;
-                std::swap(src, dst);
+                cuts[r] = b * unit;
             }
+            cuts[shard_world] = (uint64_t)pw;
         }
-        const uint64_t* sorted = src;
-        t_sort.stop();
-
-        // count dedup + rank groups of the slice (group boundaries are rank boundaries: no group straddles two slices)
-        t_grp.start();
-        const uint32_t tiles = (uint32_t)((Nr + ik::kEntTile - 1) / ik::kEntTile);
-        rt::DevBuf<uint32_t> tile_h((size_t)tiles + 1), tile_g((size_t)tiles + 1), d_spur(4);
-        rt::zero(d_spur.p, 4 * sizeof(uint32_t), st);
-        PD_LAUNCH(ik::entry_count_kernel, tiles, ik::kEntThreads, 0, st, sorted, Nr, seq_bits, tile_h.p, tile_g.p);
-        scratch.ensure(prims::scan_tmp_words(tiles) + 16);
-        prims::exclusive_scan_u32(tile_h.p, tile_h.p, tiles, scratch.p, d_total.p, st, &launches);
-        prims::exclusive_scan_u32(tile_g.p, tile_g.p, tiles, scratch.p, d_total.p + 1, st, &launches);
-        uint32_t h_tot[2] = {0, 0};
-        rt::d2h(h_tot, d_total.p, sizeof(h_tot), st);
+        // ---- this rank's SHARE of the genes (about 1 / world of the residues): its k-mers are made once, grouped by
+        // destination slice in one stable pass, and handed to the caller for the all-to-all
+        uint32_t ga, gb;
+        {
+            const uint64_t t0 = total / shard_world * shard_rank + (total % shard_world) * shard_rank / shard_world;
+            const uint64_t t1 = shard_rank + 1 == shard_world ? total : total / shard_world * (shard_rank + 1) + (total % shard_world) * (shard_rank + 1) / shard_world;
+            ga = shard_rank == 0 ? 0u : (uint32_t)(std::lower_bound(offsets, offsets + S, t0) - offsets);
+            gb = shard_rank + 1 == shard_world ? S : (uint32_t)(std::lower_bound(offsets, offsets + S, t1) - offsets);
+        }
+        uint32_t h_pos[2] = {0, 0};
+        rt::d2h(&h_pos[0], d_key_off.p + ga, sizeof(uint32_t), st);
+        rt::d2h(&h_pos[1], d_key_off.p + gb, sizeof(uint32_t), st);
         rt::sync(st);
-        const uint32_t Ur = h_tot[0], g_counted = h_tot[1];
-        sh.U_r = Ur;
-        sh.post_slice.alloc(Ur);
-        sh.heads_slice.alloc((size_t)Ur / 32 + 2);
-        const uint32_t multi_cap = (uint32_t)std::min<uint64_t>((uint64_t)Ur, (uint64_t)(Nr - Ur) + 16);  // every repeated entry merged at least one key
-        sh.multi_slice.alloc((size_t)2 * multi_cap + 2);
-        rt::DevBuf<uint32_t> cnt_tmp(Ur), gid_tmp(Ur), head_tmp((size_t)g_counted + 1);
-        rt::zero(sh.heads_slice.p, sh.heads_slice.bytes(), st);
-        ik::ShardOut so;
-        memset(&so, 0, sizeof(so));
-        so.head_bits = sh.heads_slice.p;
-        so.multi = sh.multi_slice.p;
-        so.n_multi = d_spur.p + 1;
-        so.multi_cap = multi_cap;
-        so.tail_merge = shard_rank + 1 == shard_world ? 1u : 0u;
-        PD_LAUNCH(ik::entry_apply_kernel, tiles, ik::kEntThreads, 0, st, sorted, Nr, seq_bits, (const uint32_t*)tile_h.p, (const uint32_t*)tile_g.p, Ur,
-                  sh.post_slice.p, cnt_tmp.p, gid_tmp.p, head_tmp.p, (uint64_t*)nullptr, d_spur.p, so);
-        PD_LAUNCH(ik::group_tail_kernel, 1, 32, 0, st, head_tmp.p, g_counted, (const uint32_t*)d_spur.p, Ur);
-        // this slice's part of the per-gene list-class counts and of total_visited (library.cpp:327)
-        sh.gene_counts.alloc((size_t)2 * S);
-        rt::zero(sh.gene_counts.p, sh.gene_counts.bytes(), st);
-        PD_LAUNCH(ik::fwd_count_kernel, blocks_for(Ur, 256 * ik::kFwdItems), 256, 0, st, (const uint32_t*)sh.post_slice.p, (const uint32_t*)gid_tmp.p,
-                  (const uint32_t*)head_tmp.p, Ur, sk::kShortList, sk::kHugeList, sh.gene_counts.p, sh.gene_counts.p + S);
-        uint32_t h_sp[2] = {0, 0};
-        rt::d2h(h_sp, d_spur.p, sizeof(h_sp), st);
-        launches += 4;
-        t_grp.stop();
-        t_sh.stop();
-        t_all.stop();
-        rt::sync(st);
-        if (h_sp[1] > multi_cap) throw Error(PD_ERR_CUDA, "sharded build: repeated-entry list overflow");
-        sh.M_r = h_sp[1];
+        const uint64_t pos_lo = h_pos[0], pos_hi = h_pos[1], n_share = pos_hi - pos_lo;
+        t_enc.start();
+        const uint32_t stiles = sortk::tiles_of(N);
+        sh.keys_a.alloc(std::max<uint64_t>(n_share, 1));
+        rt::DevBuf<uint32_t> tile_gene((size_t)stiles + 1), sort_ctl((size_t)2 * sortk::kRadix + 32);
+        uint32_t* d_hist = sort_ctl.p;
+        uint32_t* d_bins = d_hist + sortk::kRadix;
+        uint32_t* d_tot = d_bins + sortk::kRadix;
+        rt::zero(sort_ctl.p, sort_ctl.bytes(), st);
+        PD_LAUNCH(sortk::tile_gene_kernel, blocks_for(std::max<uint32_t>(S, 1)), 256, 0, st, (const uint32_t*)d_key_off.p, S, stiles, tile_gene.p);
+        launches++;
+        memset(sh.send_counts, 0, sizeof(sh.send_counts));
+        if (n_share) {
+            sortk::EncodeSrc es;
+            memset(&es, 0, sizeof(es));
+            es.res = d_res; es.gene_off = d_gene_off.p; es.key_off = d_key_off.p; es.tile_gene = tile_gene.p;
+            es.S = S; es.k = (int)k; es.base = base; es.mult = (uint64_t)(pw / (base ? base : 1)); es.seq_bits = seq_bits;
+            es.lo = 0; es.hi = 1ull << 63; es.N = N; es.pos_lo = pos_lo; es.pos_hi = pos_hi; es.vt = vt;
+            es.n_slices = shard_world;
+            for (uint32_t r = 0; r <= shard_world; r++) es.cuts[r] = cuts[r];
+            const bool r32 = rank_bits <= 32;
+            const uint32_t tile0 = (uint32_t)(pos_lo / sortk::kTile), tile1 = (uint32_t)((pos_hi + sortk::kTile - 1) / sortk::kTile);
+            const uint32_t ntiles = tile1 - tile0;
+            rt::DevBuf<uint32_t> status((size_t)ntiles * sortk::kRadix);
+            rt::zero(status.p, status.bytes(), st);
+            const unsigned hgrid = std::min<uint32_t>(ntiles, (uint32_t)sms * 8);
+            if (r32) PD_LAUNCH((sortk::kmer_hist_kernel<uint32_t, true>), hgrid, sortk::kThreads, 0, st, es, tile0, ntiles, 1, d_hist);
+            else PD_LAUNCH((sortk::kmer_hist_kernel<uint64_t, true>), hgrid, sortk::kThreads, 0, st, es, tile0, ntiles, 1, d_hist);
+            PD_LAUNCH(sortk::digit_bins_kernel, 1, sortk::kRadix, 0, st, (const uint32_t*)d_hist, 1, d_bins, d_tot);
+            sortk::SweepArgs sa;
+            sa.keys = nullptr; sa.out = sh.keys_a.p; sa.n = N; sa.shift = 0; sa.bins = d_bins; sa.status = status.p; sa.counter = d_tot + 8; sa.tile0 = tile0;
+            const size_t smem = sortk::sweep_smem_bytes();
+            void (*kfn)(sortk::SweepArgs, sortk::EncodeSrc) = r32 ? sortk::onesweep_kernel<2, uint32_t> : sortk::onesweep_kernel<2, uint64_t>;
+            rt::allow_smem(kfn, smem);
+            PD_LAUNCH(kfn, ntiles, sortk::kThreads, smem, st, sa, es);
+            launches += 3;
+            uint32_t h_cnt[sortk::kMaxSlices];
+            rt::d2h(h_cnt, d_hist, sizeof(uint32_t) * shard_world, st);
+            t_enc.stop();
+            t_all.stop();
+            rt::sync(st);   // (also: status, sort_ctl, tile_gene die here)
+            for (uint32_t r = 0; r < shard_world; r++) sh.send_counts[r] = h_cnt[r];
+        } else {
+            t_enc.stop();
+            t_all.stop();
+            rt::sync(st);
+        }
+        sh.n_share = n_share;
+        sh.rank_bits = rank_bits;
         sh.launches = launches;
         sh.ms = t_all.ms();
-        info.U = Ur;   // until pd_shard_finish: this slice only
         info.build_ms[0] = total ? t_hist.ms() : 0;
         info.build_ms[1] = t_enc.ms();
-        info.build_ms[2] = t_sort.ms();
-        info.build_ms[3] = t_grp.ms();
         info.build_ms[5] = sh.ms;
         info.build_ms[6] = t_h2d.ms();
         info.build_ms[7] = (double)launches;
@@ -558,11 +520,14 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
             es.lo = 0;
             es.hi = 1ull << 63;
             es.N = N;
+            es.pos_lo = 0;
+            es.pos_hi = N;
+            es.n_slices = 1;
             es.vt = vt;
             const bool r32 = rank_bits <= 32;
             const unsigned hgrid = std::min<uint32_t>(stiles, (uint32_t)sms * 8);
-            if (r32) PD_LAUNCH(sortk::kmer_hist_kernel<uint32_t>, hgrid, sortk::kThreads, 0, st, es, stiles, passes, d_hist);
-            else PD_LAUNCH(sortk::kmer_hist_kernel<uint64_t>, hgrid, sortk::kThreads, 0, st, es, stiles, passes, d_hist);
+            if (r32) PD_LAUNCH((sortk::kmer_hist_kernel<uint32_t, false>), hgrid, sortk::kThreads, 0, st, es, 0u, stiles, passes, d_hist);
+            else PD_LAUNCH((sortk::kmer_hist_kernel<uint64_t, false>), hgrid, sortk::kThreads, 0, st, es, 0u, stiles, passes, d_hist);
             PD_LAUNCH(sortk::digit_bins_kernel, 1, sortk::kRadix, 0, st, (const uint32_t*)d_hist, passes, d_bins, d_tot);
             launches += 3;
             t_enc.stop();
@@ -580,6 +545,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
                 sa.bins = d_bins + p * sortk::kRadix;
                 sa.status = sort_status.p + (size_t)p * stiles * sortk::kRadix;
                 sa.counter = d_tot + 8 + p;
+                sa.tile0 = 0;
                 void (*kfn)(sortk::SweepArgs, sortk::EncodeSrc) = sortk::onesweep_kernel<0, uint32_t>;
                 if (p == 0) kfn = r32 ? sortk::onesweep_kernel<1, uint32_t> : sortk::onesweep_kernel<1, uint64_t>;
                 rt::allow_smem(kfn, smem);
@@ -653,7 +619,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
             PD_LAUNCH(ik::fwd_place_kernel, blocks_for(R, 256 * ik::kFwdItems), 256, 0, st, (const uint4*)records.p, R, cur3.p, fwd.p, fwd_cnt.p);
             launches += 3;
         }
-        PD_LAUNCH(ik::gene_visited_kernel, blocks_for((uint64_t)S * 32), 256, 0, st, (const uint2*)fwd.p, (const uint32_t*)fwd_ptr.p, S,
+        PD_LAUNCH(ik::gene_visited_kernel, blocks_for((uint64_t)S * 32), 256, 0, st, (const uint2*)fwd.p, (const uint32_t*)fwd_ptr.p, 0u, S,
                   sk::kShortList, d_visited.p, fam_key.p, d_lookups.p);
         launches += 1;
         uint32_t h_spur = 0;
@@ -702,7 +668,125 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     }
 }
 
-// ------------------------------------------------------------------------------------------------ sharded build, steps 2 and 3
+// ------------------------------------------------------------------------------------------------ sharded build, later steps
+
+// Step 1b: room for the keys of this rank's slice, which the caller's all-to-all delivers in source-rank order (= gene order).
+uint64_t* Index::shard_recv(uint64_t n_recv) {
+    if (!shard) throw Error(PD_ERR_INVALID, "not a sharded build in progress");
+    rt::set_device(device);
+    if (n_recv >= (1ull << 31)) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more k-mers in one slice");
+    shard->n_recv = n_recv;
+    shard->keys_b.alloc(std::max<uint64_t>(n_recv, 1));
+    return shard->keys_b.p;
+}
+
+// Step 2: sort the slice by rank (stable: genes stay ascending inside a rank), count-dedup, rank groups, this slice's part
+// of the per-gene counts.
+void Index::shard_sort(pd_shard_info* out) {
+    if (!shard || !shard->keys_b.p) throw Error(PD_ERR_INVALID, "pd_shard_recv has not been called");
+    rt::set_device(device);
+    Shard& sh = *shard;
+    const uint32_t S = info.S;
+    const int seq_bits = (int)info.seq_bits;
+    const uint64_t Nr = sh.n_recv;
+    if (Nr < 2) throw Error(PD_ERR_UNSUPPORTED, "sharded build: a rank's slice of the k-mer ranks is (nearly) empty — use fewer ranks for this input");
+    rt::stream_t st = rt::stream_create();
+    uint64_t launches = 0;
+    Timer t_all(st), t_sort(st), t_grp(st);
+    t_all.start();
+    t_sort.start();
+    sh.keys_a.alloc(Nr);   // the send buffer has done its job: the second buffer of the ping-pong
+    const int passes = sortk::passes_of(sh.rank_bits);
+    const uint32_t rtiles = sortk::tiles_of(Nr);
+    rt::DevBuf<uint32_t> sort_ctl((size_t)2 * passes * sortk::kRadix + 32), sort_status((size_t)passes * rtiles * sortk::kRadix);
+    uint32_t* d_hist = sort_ctl.p;
+    uint32_t* d_bins = d_hist + passes * sortk::kRadix;
+    uint32_t* d_tot = d_bins + passes * sortk::kRadix;
+    rt::zero(sort_ctl.p, sort_ctl.bytes(), st);
+    rt::zero(sort_status.p, sort_status.bytes(), st);
+    PD_LAUNCH(sortk::keys_hist_kernel, std::min<uint32_t>(rtiles, (uint32_t)sms * 8), sortk::kThreads, 0, st, (const uint64_t*)sh.keys_b.p, Nr, seq_bits, passes,
+              d_hist);
+    PD_LAUNCH(sortk::digit_bins_kernel, 1, sortk::kRadix, 0, st, (const uint32_t*)d_hist, passes, d_bins, d_tot);
+    launches += 2;
+    uint64_t* src = sh.keys_b.p;
+    uint64_t* dst = sh.keys_a.p;
+    {
+        sortk::EncodeSrc es;
+        memset(&es, 0, sizeof(es));
+        const size_t smem = sortk::sweep_smem_bytes();
+        void (*kfn)(sortk::SweepArgs, sortk::EncodeSrc) = sortk::onesweep_kernel<0, uint32_t>;
+        rt::allow_smem(kfn, smem);
+        for (int p = 0; p < passes; p++) {
+            sortk::SweepArgs sa;
+            sa.keys = src; sa.out = dst; sa.n = Nr; sa.shift = seq_bits + 8 * p;
+            sa.bins = d_bins + p * sortk::kRadix;
+            sa.status = sort_status.p + (size_t)p * rtiles * sortk::kRadix;
+            sa.counter = d_tot + 8 + p;
+            sa.tile0 = 0;
+            PD_LAUNCH(kfn, rtiles, sortk::kThreads, smem, st, sa, es);
+            launches++;
+            std::swap(src, dst);
+        }
+    }
+    const uint64_t* sorted = src;
+    t_sort.stop();
+
+    // count dedup + rank groups of the slice (group boundaries are rank boundaries: no group straddles two slices)
+    t_grp.start();
+    const uint32_t tiles = (uint32_t)((Nr + ik::kEntTile - 1) / ik::kEntTile);
+    rt::DevBuf<uint32_t> tile_h((size_t)tiles + 1), tile_g((size_t)tiles + 1), d_spur(4), d_total(4), scratch(prims::scan_tmp_words(tiles) + 16);
+    rt::zero(d_spur.p, 4 * sizeof(uint32_t), st);
+    PD_LAUNCH(ik::entry_count_kernel, tiles, ik::kEntThreads, 0, st, sorted, Nr, seq_bits, tile_h.p, tile_g.p);
+    prims::exclusive_scan_u32(tile_h.p, tile_h.p, tiles, scratch.p, d_total.p, st, &launches);
+    prims::exclusive_scan_u32(tile_g.p, tile_g.p, tiles, scratch.p, d_total.p + 1, st, &launches);
+    uint32_t h_tot[2] = {0, 0};
+    rt::d2h(h_tot, d_total.p, sizeof(h_tot), st);
+    rt::sync(st);
+    const uint32_t Ur = h_tot[0], g_counted = h_tot[1];
+    sh.U_r = Ur;
+    sh.post_slice.alloc(Ur);
+    sh.heads_slice.alloc((size_t)Ur / 32 + 2);
+    const uint32_t multi_cap = (uint32_t)std::min<uint64_t>((uint64_t)Ur, (uint64_t)(Nr - Ur) + 16);  // every repeated entry merged at least one key
+    sh.multi_slice.alloc((size_t)2 * multi_cap + 2);
+    rt::DevBuf<uint32_t> cnt_tmp(Ur), gid_tmp(Ur), head_tmp((size_t)g_counted + 1);
+    rt::zero(sh.heads_slice.p, sh.heads_slice.bytes(), st);
+    ik::ShardOut so;
+    memset(&so, 0, sizeof(so));
+    so.head_bits = sh.heads_slice.p;
+    so.multi = sh.multi_slice.p;
+    so.n_multi = d_spur.p + 1;
+    so.multi_cap = multi_cap;
+    so.tail_merge = shard_rank + 1 == shard_world ? 1u : 0u;
+    PD_LAUNCH(ik::entry_apply_kernel, tiles, ik::kEntThreads, 0, st, sorted, Nr, seq_bits, (const uint32_t*)tile_h.p, (const uint32_t*)tile_g.p, Ur,
+              sh.post_slice.p, cnt_tmp.p, gid_tmp.p, head_tmp.p, (uint64_t*)nullptr, d_spur.p, so);
+    PD_LAUNCH(ik::group_tail_kernel, 1, 32, 0, st, head_tmp.p, g_counted, (const uint32_t*)d_spur.p, Ur);
+    // this slice's part of the per-gene list-class counts and of total_visited (library.cpp:327)
+    sh.gene_counts.alloc((size_t)2 * S);
+    rt::zero(sh.gene_counts.p, sh.gene_counts.bytes(), st);
+    PD_LAUNCH(ik::fwd_count_kernel, blocks_for(Ur, 256 * ik::kFwdItems), 256, 0, st, (const uint32_t*)sh.post_slice.p, (const uint32_t*)gid_tmp.p,
+              (const uint32_t*)head_tmp.p, Ur, sk::kShortList, sk::kHugeList, sh.gene_counts.p, sh.gene_counts.p + S);
+    uint32_t h_sp[2] = {0, 0};
+    rt::d2h(h_sp, d_spur.p, sizeof(h_sp), st);
+    launches += 4;
+    t_grp.stop();
+    t_all.stop();
+    rt::sync(st);
+    if (h_sp[1] > multi_cap) throw Error(PD_ERR_CUDA, "sharded build: repeated-entry list overflow");
+    sh.M_r = h_sp[1];
+    sh.keys_a.release();
+    sh.keys_b.release();
+    info.U = Ur;   // until pd_shard_finish: this slice only
+    info.build_ms[2] = t_sort.ms();
+    info.build_ms[3] = t_grp.ms();
+    info.build_ms[5] += t_all.ms();
+    info.build_ms[7] += (double)launches;
+    rt::stream_destroy(st);
+    out->entries = sh.U_r;
+    out->multi = sh.M_r;
+    out->kmers = Nr;
+    out->d_gene_counts = reinterpret_cast<uint64_t*>(sh.gene_counts.p);
+}
+
 
 void Index::shard_buffers(uint64_t max_entries, uint64_t max_multi, pd_shard_arrays* out) {
     if (!shard) throw Error(PD_ERR_INVALID, "not a sharded build in progress");
@@ -787,23 +871,30 @@ void Index::shard_groups(const uint64_t* entries_of_rank, const uint64_t* multi_
     rt::d2d(cls.p, sh.gene_counts.p, sizeof(unsigned long long) * S, st);
     rt::d2d(d_visited.p, sh.gene_counts.p + S, sizeof(unsigned long long) * S, st);
     rt::DevBuf<unsigned long long> d_cost((size_t)G + 2);
+    rt::DevBuf<uint32_t> d_first((size_t)2 * G + 2);   // first gene, gene count per genome
     rt::zero(d_cost.p, d_cost.bytes(), st);
-    PD_LAUNCH(ik::genome_cost_kernel, blocks_for(S), 256, 0, st, (const unsigned long long*)d_visited.p, (const uint2*)meta.p, S, d_cost.p, d_cost.p + G);
+    rt::fill_byte(d_first.p, 0xFF, sizeof(uint32_t) * G, st);
+    rt::zero(d_first.p + G, sizeof(uint32_t) * ((size_t)G + 2), st);
+    PD_LAUNCH(ik::genome_cost_kernel, blocks_for(S), 256, 0, st, (const unsigned long long*)d_visited.p, (const uint2*)meta.p, S, d_cost.p, d_cost.p + G,
+              d_first.p, d_first.p + G);
     launches++;
     std::vector<unsigned long long> h_cost((size_t)G + 2);
+    std::vector<uint32_t> h_first((size_t)2 * G + 2);
     rt::d2h(h_cost.data(), d_cost.p, sizeof(unsigned long long) * ((size_t)G + 1), st);
+    rt::d2h(h_first.data(), d_first.p, sizeof(uint32_t) * 2 * G, st);
     rt::sync(st);
-    genome_lists();   // genome_ptr: genes per genome
+    std::vector<uint32_t> gstart((size_t)G + 1, 0);   // genes of a genome contiguous and genomes ascending  <=>  first = prefix sum of count
     {
-        // genes of a genome contiguous and genomes ascending  <=>  genome_rows is the identity
         bool ok = true;
-        for (uint32_t s = 0; s < S && ok; s += 1 + S / 65536) ok = genome_rows[s] == s;
-        for (uint32_t g = 0; g <= G && ok; g++) ok = genome_ptr[g] <= S && (g == 0 || genome_ptr[g] >= genome_ptr[g - 1]);
-        if (ok) {   // exact check on the device-made list boundaries: first and last gene of every genome
-            for (uint32_t g = 0; g < G && ok; g++)
-                if (genome_ptr[g + 1] > genome_ptr[g]) ok = genome_rows[genome_ptr[g]] == genome_ptr[g] && genome_rows[genome_ptr[g + 1] - 1] == genome_ptr[g + 1] - 1;
+        uint32_t at = 0;
+        for (uint32_t g = 0; g < G && ok; g++) {
+            const uint32_t n = h_first[G + g];
+            ok = n == 0 || h_first[g] == at;
+            gstart[g] = at;
+            at += n;
         }
-        if (!ok) throw Error(PD_ERR_UNSUPPORTED, "sharded build: genes of a genome must be contiguous and genomes ascending");
+        gstart[G] = at;
+        if (!ok || at != S) throw Error(PD_ERR_UNSUPPORTED, "sharded build: genes of a genome must be contiguous and genomes ascending");
     }
     unsigned long long all_cost = 0;
     for (uint32_t g = 0; g < G; g++) all_cost += h_cost[g];
@@ -818,7 +909,7 @@ void Index::shard_groups(const uint64_t* entries_of_rank, const uint64_t* multi_
             gcut[p] = std::max(g, gcut[p - 1]);
         }
     }
-    for (uint32_t p = 0; p <= W; p++) bounds[p] = genome_ptr[gcut[p]];
+    for (uint32_t p = 0; p <= W; p++) bounds[p] = gstart[gcut[p]];
     own_g0 = gcut[shard_rank];
     own_g1 = gcut[shard_rank + 1];
     own_row0 = bounds[shard_rank];
@@ -873,8 +964,9 @@ void Index::shard_finish() {
         launches += 3;
         rt::sync(st);  // records, bucket_cur
     }
-    PD_LAUNCH(ik::gene_visited_kernel, blocks_for((uint64_t)S * 32), 256, 0, st, (const uint2*)fwd.p, (const uint32_t*)fwd_ptr.p, S, sk::kShortList,
-              (unsigned long long*)nullptr, fam_key.p, (unsigned long long*)nullptr);
+    if (own_row1 > own_row0)
+        PD_LAUNCH(ik::gene_visited_kernel, blocks_for((uint64_t)(own_row1 - own_row0) * 32), 256, 0, st, (const uint2*)fwd.p, (const uint32_t*)fwd_ptr.p,
+                  own_row0, own_row1, sk::kShortList, (unsigned long long*)nullptr, fam_key.p, (unsigned long long*)nullptr);
     launches += 3;
     t_fin.stop();
     rt::sync(st);

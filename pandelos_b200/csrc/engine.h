@@ -70,6 +70,10 @@ struct Index {
     struct Shard {
         uint32_t U_r = 0, M_r = 0;                     // entries / repeated entries of this rank's slice
         uint64_t seg = 0, mseg = 0;                    // segment sizes of the gathered arrays
+        rt::DevBuf<uint64_t> keys_a, keys_b;           // this rank's share grouped by destination slice (send); the keys of its slice (receive)
+        uint64_t send_counts[32] = {0};                // keys of the share per destination rank
+        uint64_t n_share = 0, n_recv = 0;
+        int rank_bits = 0;
         rt::DevBuf<uint32_t> post_slice, heads_slice, multi_slice;
         rt::DevBuf<unsigned long long> gene_counts;    // [S] list-class counts, [S] total_visited: this slice's part, all-reduced in place by the caller
         rt::DevBuf<uint32_t> heads_all, multi_all, tile_heads;
@@ -78,6 +82,8 @@ struct Index {
         bool grouped = false;
     };
     Shard* shard = nullptr;
+    uint64_t* shard_recv(uint64_t n_recv);
+    void shard_sort(pd_shard_info* out);
     void shard_buffers(uint64_t max_entries, uint64_t max_multi, pd_shard_arrays* out);
     void shard_groups(const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds);
     void shard_finish();

@@ -467,14 +467,14 @@ __global__ void __launch_bounds__(256) fwd_place_kernel(const uint4* __restrict_
 // of one family share their conserved k-mers, hence mostly this key; scoring calls process their rows in fam_key
 // order so that rows running at the same time read the same posting lists (L2 hits instead of HBM reads).
 // One warp per gene.
-__global__ void __launch_bounds__(256) gene_visited_kernel(const uint2* __restrict__ fwd, const uint32_t* __restrict__ fwd_ptr, uint32_t S,
+__global__ void __launch_bounds__(256) gene_visited_kernel(const uint2* __restrict__ fwd, const uint32_t* __restrict__ fwd_ptr, uint32_t s0, uint32_t S,
                                                             uint32_t short_max, unsigned long long* __restrict__ visited,
                                                             uint32_t* __restrict__ fam_key, unsigned long long* __restrict__ total) {
     __shared__ unsigned long long s_sum;
     if (threadIdx.x == 0) s_sum = 0;
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
-    const uint32_t s = (blockIdx.x * 256u + threadIdx.x) >> 5;
+    const uint32_t s = s0 + ((blockIdx.x * 256u + threadIdx.x) >> 5);   // genes [s0, S)
     if (s < S) {
         const uint32_t f0 = fwd_ptr[s], f1 = fwd_ptr[s + 1];
         unsigned long long v = 0;
@@ -549,16 +549,25 @@ __global__ void __launch_bounds__(256) shard_multi_kernel(const uint32_t* __rest
     post_cnt[(size_t)r * seg + m[0]] = m[1];
 }
 // cost[genome] += total_visited + 1 of its genes (query partitioning by posting-list volume, library.cpp:327)
+// first[genome] = its smallest gene, count[genome] = its genes (the caller checks that genomes are contiguous gene ranges)
 __global__ void __launch_bounds__(256) genome_cost_kernel(const unsigned long long* __restrict__ visited, const uint2* __restrict__ meta, uint32_t S,
-                                                           unsigned long long* __restrict__ cost, unsigned long long* __restrict__ total) {
+                                                           unsigned long long* __restrict__ cost, unsigned long long* __restrict__ total,
+                                                           uint32_t* __restrict__ first, uint32_t* __restrict__ count) {
     const uint32_t s = blockIdx.x * 256u + threadIdx.x;
     const bool in = s < S;
     const uint32_t g = in ? meta[s].y : 0xFFFFFFFFu;
+    if (in) {
+        const uint32_t gp = s ? meta[s - 1].y : 0xFFFFFFFFu;
+        if (gp != g) atomicMin(&first[g], s);   // one atomic per run of equal genomes
+    }
     unsigned long long v = in ? visited[s] : 0ull;
     // genes of a genome sit together: a warp whose lanes all belong to one genome adds once
     const uint32_t g0 = __shfl_sync(0xffffffffu, g, 0);
     const bool uniform = __all_sync(0xffffffffu, g == g0);
-    if (!uniform && in) atomicAdd(&cost[g], v + 1ull);
+    if (!uniform && in) {
+        atomicAdd(&cost[g], v + 1ull);
+        atomicAdd(&count[g], 1u);
+    }
     unsigned long long c = in ? v + 1ull : 0ull;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -566,7 +575,10 @@ __global__ void __launch_bounds__(256) genome_cost_kernel(const unsigned long lo
         c += __shfl_xor_sync(0xffffffffu, c, d);
     }
     if ((threadIdx.x & 31) == 0) {
-        if (uniform && g0 != 0xFFFFFFFFu) atomicAdd(&cost[g0], c);
+        if (uniform && g0 != 0xFFFFFFFFu) {
+            atomicAdd(&cost[g0], c);
+            atomicAdd(&count[g0], 32u);
+        }
         if (v) atomicAdd(total, v);
     }
 }

@@ -34,6 +34,7 @@ static const int kTile = kThreads * kItems;  // 4096 keys per tile
 static const int kWarps = kThreads / 32;
 static const int kRadix = 256;
 static const int kMaxPasses = 8;   // 63 rank bits at most
+static const int kMaxSlices = 32;  // ranks of a sharded build
 static const uint64_t kNoKey = ~0ull;  // never a key: rank_bits + seq_bits <= 63
 static const uint32_t kInclusive = 0x80000000u;  // status word: 0 = not ready; bit 31 = inclusive prefix; else aggregate + 1
 
@@ -49,8 +50,18 @@ struct EncodeSrc {
     int seq_bits;
     uint64_t lo, hi;  // ranks kept: [lo, hi)
     uint64_t N;       // key positions
+    uint64_t pos_lo, pos_hi;  // key positions kept: [pos_lo, pos_hi) (a rank's share of the genes in a sharded build)
+    uint32_t n_slices;        // sharded build: the rank space is cut into n_slices slices at cuts[1 .. n_slices - 1]
+    uint64_t cuts[kMaxSlices + 1];
     ik::ValTable vt;
 };
+
+// the slice (= destination rank of a sharded build) of a k-mer rank
+__device__ __forceinline__ unsigned slice_of(const EncodeSrc& s, uint64_t r) {
+    unsigned d = 0;
+    for (uint32_t i = 1; i < s.n_slices; i++) d += r >= s.cuts[i] ? 1u : 0u;
+    return d;
+}
 
 // tile_gene[t] = the gene whose k-mers include key t * kTile, for t < tiles; tile_gene[tiles] = S - 1
 __global__ void __launch_bounds__(256) tile_gene_kernel(const uint32_t* __restrict__ key_off, uint32_t S, uint32_t tiles,
@@ -105,15 +116,16 @@ __device__ __forceinline__ void encode_keys(const EncodeSrc& s, const uint8_t* v
                 r = (r - (RankT)val[p[-1]] * mult) * base + (RankT)val[p[s.k - 1]];  // library.cpp:75-79
             }
             p++;
-            if ((uint64_t)r >= s.lo && (uint64_t)r < s.hi) key = ((uint64_t)r << s.seq_bits) | g;
+            if ((uint64_t)r >= s.lo && (uint64_t)r < s.hi && i >= s.pos_lo && i < s.pos_hi) key = ((uint64_t)r << s.seq_bits) | g;
         }
         out(j, key);
     }
 }
 
-// hist[p * 256 + d] += keys (of the slice) whose digit p is d, for all passes at once
-template <typename RankT>
-__global__ void __launch_bounds__(kThreads) kmer_hist_kernel(EncodeSrc s, uint32_t tiles, int passes, uint32_t* __restrict__ hist) {
+// hist[p * 256 + d] += kept keys whose digit p is d, for all passes at once (SLICES: hist[d] += kept keys of slice d).
+// Tiles [tile0, tile0 + tiles).
+template <typename RankT, bool SLICES>
+__global__ void __launch_bounds__(kThreads) kmer_hist_kernel(EncodeSrc s, uint32_t tile0, uint32_t tiles, int passes, uint32_t* __restrict__ hist) {
     __shared__ uint32_t h[2][kMaxPasses * kRadix];
     __shared__ uint8_t val[256];
     const unsigned tid = threadIdx.x;
@@ -121,14 +133,16 @@ __global__ void __launch_bounds__(kThreads) kmer_hist_kernel(EncodeSrc s, uint32
     val[tid] = s.vt.v[tid];
     __syncthreads();
     uint32_t* mine = h[(tid >> 5) & 1];
-    for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (uint32_t tile = tile0 + blockIdx.x; tile < tile0 + tiles; tile += gridDim.x) {
         const uint64_t i0 = (uint64_t)tile * kTile + (uint64_t)tid * kItems;
         const uint32_t n = i0 >= s.N ? 0u : (uint32_t)(s.N - i0 < (uint64_t)kItems ? s.N - i0 : (uint64_t)kItems);
         const int seq_bits = s.seq_bits;
         encode_keys<RankT>(s, val, i0, n, s.tile_gene[tile], s.tile_gene[tile + 1], [&](int, uint64_t key) {
             if (key != kNoKey) {
                 const uint64_t r = key >> seq_bits;
-                for (int p = 0; p < passes; p++) atomicAdd(&mine[p * kRadix + ((unsigned)(r >> (8 * p)) & 0xFFu)], 1u);
+                if (SLICES) atomicAdd(&mine[slice_of(s, r)], 1u);
+                else
+                    for (int p = 0; p < passes; p++) atomicAdd(&mine[p * kRadix + ((unsigned)(r >> (8 * p)) & 0xFFu)], 1u);
             }
         });
     }
@@ -139,88 +153,22 @@ __global__ void __launch_bounds__(kThreads) kmer_hist_kernel(EncodeSrc s, uint32
     }
 }
 
-// Rank-range sharding of the build (several GPUs build one index): the keys of THIS rank's slice [lo, hi), compacted in
-// gene order into `out`, and their digit counts for all passes.  Persistent CTAs take 4096-position tiles by ticket; a
-// tile's kept keys follow those of all tiles before it (one status word per tile, look-back by a whole warp: 32 tiles
-// per step).  Every rank reads all residues (1 B per k-mer) and keeps about 1 / world of the keys.
-template <typename RankT>
-__global__ void __launch_bounds__(kThreads) kmer_slice_kernel(EncodeSrc s, uint32_t tiles, int passes, uint32_t* __restrict__ hist,
-                                                               uint32_t* __restrict__ counter, uint32_t* status, uint64_t* __restrict__ out) {
-    __shared__ uint32_t h[kMaxPasses * kRadix];
-    __shared__ uint64_t stage[kTile];   // the tile's kept keys, packed: they leave in coalesced runs
-    __shared__ uint8_t val[256];
-    __shared__ uint32_t scratch[33];
-    __shared__ uint32_t s_tile, s_before;
-    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (unsigned i = tid; i < kMaxPasses * kRadix; i += kThreads) h[i] = 0;
-    val[tid] = s.vt.v[tid];
-    uint32_t* mine = h;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(counter, 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= tiles) break;
-        const uint64_t i0 = (uint64_t)tile * kTile + (uint64_t)tid * kItems;
-        const uint32_t n = i0 >= s.N ? 0u : (uint32_t)(s.N - i0 < (uint64_t)kItems ? s.N - i0 : (uint64_t)kItems);
-        uint64_t key[kItems];
-        uint32_t kept = 0;
-        const int seq_bits = s.seq_bits;
-        encode_keys<RankT>(s, val, i0, n, s.tile_gene[tile], s.tile_gene[tile + 1], [&](int j, uint64_t kv) {
-            key[j] = kv;
-            if (kv != kNoKey) {
-                kept++;
-                const uint64_t r = kv >> seq_bits;
-                for (int p = 0; p < passes; p++) atomicAdd(&mine[p * kRadix + ((unsigned)(r >> (8 * p)) & 0xFFu)], 1u);
-            }
-        });
-        uint32_t total;
-        const uint32_t off = prims::block_excl_scan<kThreads>(kept, scratch, &total);
-        {
-            uint32_t q = off;
-#pragma unroll
-            for (int j = 0; j < kItems; j++)
-                if (key[j] != kNoKey) stage[q++] = key[j];
-        }
-        if (warp == 0) {
-            uint32_t before = 0;
-            volatile uint32_t* st = status;
-            if (tile == 0) {
-                if (lane == 0) st[0] = kInclusive | total;
-            } else {
-                if (lane == 0) st[tile] = total + 1u;
-                for (long long hi = tile;; hi -= 32) {
-                    const long long idx = hi - 1 - (long long)lane;
-                    uint32_t v = 0;
-                    if (idx >= 0) {
-                        while ((v = st[idx]) == 0u) {
-                        }
-                    }
-                    const unsigned inc = __ballot_sync(0xffffffffu, idx >= 0 && (v & kInclusive) != 0u);
-                    uint32_t c = 0;
-                    if (idx >= 0) {
-                        if (!inc) c = v - 1u;
-                        else {
-                            const unsigned first = __ffs(inc) - 1;  // the nearest tile that knows its inclusive prefix
-                            c = lane < first ? v - 1u : (lane == first ? (v & ~kInclusive) : 0u);
-                        }
-                    }
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-                    before += c;
-                    if (inc) break;
-                }
-                if (lane == 0) st[tile] = kInclusive | (before + total);
-            }
-            if (lane == 0) s_before = before;
-        }
-        __syncthreads();
-        const uint64_t before = s_before;
-        for (uint32_t i = tid; i < total; i += kThreads) out[before + i] = stage[i];
+// the same from keys that exist already (the keys a rank of a sharded build received): 16-byte loads
+__global__ void __launch_bounds__(kThreads) keys_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n, int shift0, int passes,
+                                                              uint32_t* __restrict__ hist) {
+    __shared__ uint32_t h[2][kMaxPasses * kRadix];
+    const unsigned tid = threadIdx.x;
+    for (unsigned i = tid; i < 2 * kMaxPasses * kRadix; i += kThreads) (&h[0][0])[i] = 0;
+    __syncthreads();
+    uint32_t* mine = h[(tid >> 5) & 1];
+    const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+    for (uint64_t i = (uint64_t)blockIdx.x * kThreads + tid; i < n; i += stride) {
+        const uint64_t r = keys[i] >> shift0;
+        for (int p = 0; p < passes; p++) atomicAdd(&mine[p * kRadix + ((unsigned)(r >> (8 * p)) & 0xFFu)], 1u);
     }
     __syncthreads();
     for (unsigned i = tid; i < (unsigned)passes * kRadix; i += kThreads) {
-        const uint32_t v = h[i];
+        const uint32_t v = h[0][i] + h[1][i];
         if (v) atomicAdd(&hist[i], v);
     }
 }
@@ -246,6 +194,7 @@ struct SweepArgs {
     const uint32_t* bins;  // this pass: [256]
     uint32_t* status;      // this pass: tiles x 256 words, zero at launch
     uint32_t* counter;     // this pass: tile ticket, zero at launch
+    uint32_t tile0;        // MODE 1 / 2: first tile of key positions this launch covers (tile = tile0 + ticket)
 };
 
 inline size_t sweep_smem_bytes() {
@@ -268,7 +217,8 @@ __device__ __forceinline__ unsigned match_digit(unsigned dig, unsigned vm) {
     return r;
 }
 
-// MODE 0: keys from `a.keys`.  MODE 1: keys made from the residues (EncodeSrc).
+// MODE 0: keys from `a.keys`.  MODE 1: keys made from the residues (EncodeSrc).  MODE 2: as MODE 1, but the "digit" is the
+// key's slice of the rank space: one stable pass that groups a rank's share of the keys by destination rank (sharded build).
 // Order of work in a tile: load -> per-warp digit counts (shared-memory atomics) -> offsets, tile counts PUBLISHED ->
 // rank (ballots) -> keys to their place in the tile buffer -> look-back (by now the tiles before have published) -> out.
 template <int MODE, typename RankT>
@@ -285,19 +235,20 @@ __global__ void __launch_bounds__(kThreads, 4) onesweep_kernel(SweepArgs a, Enco
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) *ticket = atomicAdd(a.counter, 1u);  // tiles in the order the CTAs start: every tile before mine is running or done
     for (unsigned i = tid; i < kWarps * kRadix; i += kThreads) wc[i] = 0;
-    if (MODE == 1) val[tid] = s.vt.v[tid];
+    if (MODE != 0) val[tid] = s.vt.v[tid];
     __syncthreads();
-    const uint32_t tile = *ticket;
-    const uint64_t tile_base = (uint64_t)tile * kTile;
+    const uint32_t tile = *ticket;                      // status / look-back order
+    const uint32_t ptile = tile + (MODE != 0 ? a.tile0 : 0u);  // tile of key positions
+    const uint64_t tile_base = (uint64_t)ptile * kTile;
     const uint32_t tile_n = (uint32_t)((a.n - tile_base < (uint64_t)kTile) ? (a.n - tile_base) : (uint64_t)kTile);
 
     uint64_t key[kItems];
-    if (MODE == 1) {
+    if (MODE != 0) {
         // blocked encode (a thread rolls over kItems consecutive k-mers), transposed through shared memory to the striped
         // order the ranking wants; one pad word per 16 keeps both sides at the two wavefronts an 8-byte access needs
         const uint32_t l0 = tid * kItems;
         const uint32_t n = l0 >= tile_n ? 0u : (tile_n - l0 < (uint32_t)kItems ? tile_n - l0 : (uint32_t)kItems);
-        encode_keys<RankT>(s, val, tile_base + l0, n, s.tile_gene[tile], s.tile_gene[tile + 1],
+        encode_keys<RankT>(s, val, tile_base + l0, n, s.tile_gene[ptile], s.tile_gene[ptile + 1],
                            [&](int j, uint64_t kv) { stage[l0 + j + ((l0 + j) >> 4)] = kv; });
         __syncthreads();
 #pragma unroll
@@ -318,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 4) onesweep_kernel(SweepArgs a, Enco
     uint32_t* my_wc = wc + warp * kRadix;
 #pragma unroll
     for (int j = 0; j < kItems; j++)
-        if (key[j] != kNoKey) atomicAdd(&my_wc[(unsigned)(key[j] >> a.shift) & 0xFFu], 1u);
+        if (key[j] != kNoKey) atomicAdd(&my_wc[MODE == 2 ? slice_of(s, key[j] >> s.seq_bits) : ((unsigned)(key[j] >> a.shift) & 0xFFu)], 1u);
     __syncthreads();  // (also: the buffer of the first pass's transpose is free again)
 
     // ---- per digit (thread = digit): exclusive scan over the warps, tile total, exclusive scan over the digits;
@@ -347,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 4) onesweep_kernel(SweepArgs a, Enco
 #pragma unroll
     for (int j = 0; j < kItems; j++) {
         const bool has = key[j] != kNoKey;
-        const unsigned d = (unsigned)(key[j] >> a.shift) & 0xFFu;
+        const unsigned d = MODE == 2 ? (has ? slice_of(s, key[j] >> s.seq_bits) : 0u) : ((unsigned)(key[j] >> a.shift) & 0xFFu);
         const unsigned vm = full ? 0xffffffffu : __ballot_sync(0xffffffffu, has);
         const unsigned peers = match_digit(d, vm);
         const unsigned leader = __ffs(peers) - 1;
@@ -388,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 4) onesweep_kernel(SweepArgs a, Enco
         const uint32_t idx = i * kThreads + tid;
         if (idx < tile_kept) {
             const uint64_t kv = stage[idx];
-            const unsigned d = (unsigned)(kv >> a.shift) & 0xFFu;
+            const unsigned d = MODE == 2 ? slice_of(s, kv >> s.seq_bits) : ((unsigned)(kv >> a.shift) & 0xFFu);
             a.out[(uint64_t)gdelta[d] + idx] = kv;
         }
     }

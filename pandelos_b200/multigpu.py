@@ -144,19 +144,36 @@ def _as_tensor(ptr, count, bits, device):
 
 
 def build_sharded(dist, native, k, data, device=None, device_index=-1, residues_device_ptr=None, **engine_kw):
-    """ONE index built by all ranks of `dist` together (include/pandelos_b200.h, pd_build_shard): every rank sorts and groups
-    the k-mers of its slice of the rank space, the slices' postings / group-head bits / repeated-entry lists are
+    """ONE index built by all ranks of `dist` together (include/pandelos_b200.h, pd_build_shard ...): every rank makes the
+    k-mers of its share of the genes, an all-to-all moves every k-mer to the rank that owns its slice of the rank space,
+    every rank sorts / dedups / groups its slice, the slices' postings / group-head bits / repeated-entry lists are
     all-gathered in place, the per-gene partial counts all-reduced, and every rank makes the forward lists of its own,
     genome-aligned, posting-list-volume-balanced share of the query rows.  Returns (PangeneNative, bounds[world + 1]):
-    rank r serves genes [bounds[r], bounds[r + 1]).  The only collectives of the multi-GPU path (NCCL over NVLink on
-    GPUs; gloo in the CPU tests): 1 tiny all-gather, 1 all-reduce of 16 S bytes, 3 all-gathers (4 B per posting in all)."""
+    rank r serves genes [bounds[r], bounds[r + 1]).  The collectives of the multi-GPU path (NCCL over NVLink on GPUs;
+    gloo in the CPU tests): 2 tiny all-gathers, 1 all-to-all (8 B per k-mer), 1 all-reduce (16 B per gene), 3 all-gathers
+    (4 B per posting in all)."""
     import torch
     rank, world = dist.get_rank(), dist.get_world_size()
-    pn = native.PangeneNative(k, data, device=device_index, residues_device_ptr=residues_device_ptr, shard=(rank, world), **engine_kw)
-    si = pn.shard_info
     cpu = device is None or getattr(device, "type", "cpu") != "cuda"
-    mine = torch.tensor([int(si.entries), int(si.multi)], dtype=torch.int64, device=None if cpu else device)
-    counts = torch.zeros(2 * world, dtype=torch.int64, device=None if cpu else device)
+    tdev = None if cpu else device
+    pn = native.PangeneNative(k, data, device=device_index, residues_device_ptr=residues_device_ptr, shard=(rank, world), **engine_kw)
+    # ---- k-mers to the rank that sorts them
+    send_counts = torch.tensor([int(pn.shard_keys.send_counts[r]) for r in range(world)], dtype=torch.int64, device=tdev)
+    all_counts = torch.zeros(world * world, dtype=torch.int64, device=tdev)
+    dist.all_gather_into_tensor(all_counts, send_counts)
+    all_counts = all_counts.cpu().numpy().reshape(world, world)      # [source, destination]
+    in_splits = [int(v) for v in all_counts[:, rank]]
+    out_splits = [int(v) for v in all_counts[rank, :]]
+    n_recv, n_send = sum(in_splits), sum(out_splits)
+    recv = _as_tensor(pn.shard_recv(n_recv), max(n_recv, 1), 64, device)[:n_recv]
+    send = _as_tensor(pn.shard_keys.d_send, max(n_send, 1), 64, device)[:n_send]
+    dist.all_to_all_single(recv, send, in_splits, out_splits)
+    if not cpu:
+        torch.cuda.current_stream().synchronize()   # the engine works on its own streams
+    si = pn.shard_sort()
+    # ---- the slices' results to every rank
+    mine = torch.tensor([int(si.entries), int(si.multi)], dtype=torch.int64, device=tdev)
+    counts = torch.zeros(2 * world, dtype=torch.int64, device=tdev)
     dist.all_gather_into_tensor(counts, mine)
     counts = counts.cpu().numpy().reshape(world, 2)
     S = data.sequences_count
@@ -170,7 +187,7 @@ def build_sharded(dist, native, k, data, device=None, device_index=-1, residues_
         if not wait:
             works.append((work, whole))
     if not cpu:
-        torch.cuda.current_stream().synchronize()   # the engine works on its own streams
+        torch.cuda.current_stream().synchronize()
     bounds = pn.shard_groups(counts[:, 0], counts[:, 1])   # while the postings (4 B each, the bulk) are still travelling
     for work, _ in works:
         work.wait()

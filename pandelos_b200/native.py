@@ -58,6 +58,10 @@ class EdgesStruct(C.Structure):
                 ("cells", C.c_uint64), ("owner", C.c_void_p)]
 
 
+class ShardKeys(C.Structure):
+    _fields_ = [("d_send", C.c_void_p), ("send_counts", C.c_uint64 * 32)]
+
+
 class ShardInfo(C.Structure):
     _fields_ = [("entries", C.c_uint64), ("multi", C.c_uint64), ("kmers", C.c_uint64), ("d_gene_counts", C.c_void_p)]
 
@@ -100,7 +104,9 @@ def load(path=None):
     L.pd_partition_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p]
     L.pd_build_shard.restype = C.c_int
     L.pd_build_shard.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(Options), C.c_uint32, C.c_uint32,
-                                 C.POINTER(C.c_void_p), C.POINTER(ShardInfo)]
+                                 C.POINTER(C.c_void_p), C.POINTER(ShardKeys)]
+    L.pd_shard_recv.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.pd_shard_sort.argtypes = [C.c_void_p, C.POINTER(ShardInfo)]
     L.pd_shard_buffers.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(ShardArrays)]
     L.pd_shard_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pd_shard_finish.argtypes = [C.c_void_p]
@@ -178,14 +184,14 @@ class PangeneNative:
         opt = Options(int(device), int(verbose), int(contexts), int(hash_log2), int(cell_capacity), int(keep_sorted), 0)
         h = C.c_void_p()
         S = data.sequences_count
-        self.shard_info = None
+        self.shard_keys = None
         if shard is not None:
             rank, world = shard
-            self.shard_info = ShardInfo()
+            self.shard_keys = ShardKeys()
             on_dev = residues_device_ptr is not None
             rc = L.pd_build_shard(C.c_void_p(int(residues_device_ptr)) if on_dev else data.residues.ctypes.data, int(on_dev),
                                   data.offsets.ctypes.data, data.sequenceGenome.ctypes.data, S, self.k, C.byref(opt), int(rank), int(world),
-                                  C.byref(h), C.byref(self.shard_info))
+                                  C.byref(h), C.byref(self.shard_keys))
         elif residues_device_ptr is not None:
             rc = L.pd_build_device(C.c_void_p(int(residues_device_ptr)), data.offsets.ctypes.data, data.sequenceGenome.ctypes.data, S,
                                    self.k, C.byref(opt), C.byref(h))
@@ -256,6 +262,16 @@ class PangeneNative:
         return e, (lambda: self._L.pd_edges_release(self._h, C.byref(e)))
 
     # ---- sharded build, steps 2 and 3 (include/pandelos_b200.h)
+    def shard_recv(self, n_recv):
+        p = C.c_void_p()
+        _check(self._L.pd_shard_recv(self._h, int(n_recv), C.byref(p)))
+        return p.value
+
+    def shard_sort(self):
+        si = ShardInfo()
+        _check(self._L.pd_shard_sort(self._h, C.byref(si)))
+        return si
+
     def shard_buffers(self, max_entries, max_multi):
         a = ShardArrays()
         _check(self._L.pd_shard_buffers(self._h, int(max_entries), int(max_multi), C.byref(a)))
