@@ -88,6 +88,8 @@ class ClockSampler:
         self.samples = []    # (sm_mhz, reasons bitmask) from NVML
         self.max_mhz = None
         self.source = None
+        self.first = 0
+        self.first_nvml = 0
 
     def _nvml_loop(self, nv, handle):
         while not self.stop_flag.is_set():
@@ -130,6 +132,14 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def mark_timed_region(self):
+        """Waits for the sampler's first sample (so that its start-up is over) and drops what was sampled so far."""
+        t0 = time.time()
+        while self.source == "nvidia-smi" and not self.lines and time.time() - t0 < 5.0:
+            time.sleep(0.02)
+        self.first = len(self.lines)
+        self.first_nvml = len(self.samples)
+
     def stop(self):
         if self.source == "nvml":
             self.stop_flag.set()
@@ -137,8 +147,9 @@ class ClockSampler:
             nv = self._nv
             bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
-            reasons = sorted(n for n, b in bits.items() if any(r & b for _, r in self.samples))
-            sm = [m for m, _ in self.samples]
+            samples = self.samples[self.first_nvml:]
+            reasons = sorted(n for n, b in bits.items() if any(r & b for _, r in samples))
+            sm = [m for m, _ in samples]
             return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
                     "samples": len(sm), "source": "nvml"}
         if not self.proc:
@@ -149,7 +160,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -525,12 +536,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        pn, st = step()
-        pn.close()
+    # The clock sampler (an `nvidia-smi -lms` loop) is started BEFORE the warm-up steps: its start-up initialises NVML on every
+    # GPU of the box, which holds a driver lock for ~0.1 s and showed up as a 10 - 120 ms host stall inside one of the first
+    # timed steps (max over ranks: one stalled rank stalls the collectives of all).  Only samples taken during the timed
+    # steps are used.
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        pn, st = step()
+        pn.close()
+    if rank == 0:
+        sampler.mark_timed_region()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = build_ms = 0.0
     launches = 0
