@@ -295,7 +295,7 @@ def run_reference(args):
            "extrapolated": len(sample) < w.G, "same_index": not fallback, "preprocess_s": pre_s, "scores_s_per_step": t_sc,
            "sample_genomes": sample if len(sample) <= 32 else len(sample), "sample_pairs": int(pairs),
            "pairs_source": "tests/golden/digests (oracle restatement), not the engine",
-           "reference_cells_match_golden": cells_ok,
+           "reference_cells_match_golden": cells_ok, "host_max_rss_gb": __import__("resource").getrusage(__import__("resource").RUSAGE_SELF).ru_maxrss / 1048576.0,
            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "reference", "sample": desc},
            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))

@@ -43,7 +43,9 @@ typedef struct pd_options {
     int32_t hash_log2;       /* log2 slots of the per-row shared-memory accumulator (0 = default 12) */
     uint64_t cell_capacity;  /* initial per-call cell buffer, in cells (0 = automatic) */
     int32_t keep_sorted;     /* 1 = keep the sorted k-mer keys so pd_entries can return ranks (tests) */
-    int32_t reserved;
+    int32_t devices;         /* > 1: one replica of the index on each of that many devices (starting at `device`), genomes dealt
+                                out in posting-list-volume-balanced blocks; pd_compute_scores / pd_genome_edges go to the owner's
+                                device, calls for different devices run side by side.  0 / 1 = one device.  Host residues only. */
 } pd_options;
 
 typedef struct pd_index_info {
@@ -186,6 +188,11 @@ int pd_shard_sort(pd_index* ix, pd_shard_info* info);
 int pd_shard_buffers(pd_index* ix, uint64_t max_entries, uint64_t max_multi, pd_shard_arrays* out);
 int pd_shard_groups(pd_index* ix, const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds);
 int pd_shard_finish(pd_index* ix);
+
+/* pd_options.devices > 1: number of replicas, and which of them (0 .. pd_devices - 1) serves a genome; a host that issues its
+ * per-genome calls device by device keeps all devices busy. */
+int pd_devices(const pd_index* ix);
+int pd_genome_device(const pd_index* ix, uint32_t genome);
 
 /* Splits [0, S) into `parts` contiguous gene ranges of near-equal total_visited (query partitioning by
  * posting-list volume); bounds[parts+1].  snap_to_genomes != 0 moves boundaries to genome boundaries. */

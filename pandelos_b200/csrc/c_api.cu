@@ -1,6 +1,10 @@
 // The plain C ABI of include/pandelos_b200.h: argument checks, error-code mapping, nothing else.
 #include <cstring>
 #include <new>
+#include <thread>
+#include <algorithm>
+#include <string>
+#include <vector>
 
 #include "engine.h"
 
@@ -8,8 +12,22 @@ namespace pd {
 const std::string& last_error();
 }  // namespace pd
 
+// The handle: one index, or (pd_options.devices > 1) one replica of it per device with the genomes dealt out to the
+// devices in contiguous, posting-list-volume-balanced blocks.  Every per-genome call goes to the replica that owns the genome;
+// calls for genomes of different devices run in parallel (the Java host calls computeScores from a thread pool,
+// Pangenes.java:54-66).  The per-index calls (pd_info, pd_gene_stats, ...) are answered by the first replica.
 struct pd_index {
     pd::Index ix;
+    std::vector<pd::Index*> more;           // replicas on further devices
+    std::vector<uint32_t> genome_owner;     // genome -> 0 (ix) or 1 + position in `more`
+    std::vector<uint32_t> bounds;           // row bounds of the devices' blocks (devices + 1)
+    ~pd_index() {
+        for (pd::Index* x : more) delete x;
+    }
+    pd::Index& of_genome(uint32_t g) {
+        const uint32_t o = g < genome_owner.size() ? genome_owner[g] : 0u;
+        return o == 0 ? ix : *more[o - 1];
+    }
 };
 
 namespace {
@@ -43,7 +61,52 @@ int build_common(const uint8_t* residues, bool on_device, const uint64_t* offset
         h = new pd_index;
         h->ix.shard_rank = rank;
         h->ix.shard_world = world;
-        h->ix.build(residues, on_device, offsets, genome_of, S, k, opt);
+        int devices = opt ? opt->devices : 0;
+        const int have = pd::rt::device_count();
+        if (devices > have) devices = have;
+        if (devices <= 1 || world > 1) {
+            h->ix.build(residues, on_device, offsets, genome_of, S, k, opt);
+            return;
+        }
+        if (on_device) throw pd::Error(PD_ERR_INVALID, "pd_options.devices > 1 needs host residues (every device gets its own copy)");
+        // one replica per device, built at the same time by one host thread each
+        const int first = opt->device >= 0 ? opt->device : pd::rt::current_device();
+        std::vector<std::string> errs((size_t)devices);
+        std::vector<int> codes((size_t)devices, PD_OK);
+        std::vector<std::thread> th;
+        h->more.assign((size_t)devices - 1, nullptr);
+        for (int d = 0; d < devices; d++) {
+            th.emplace_back([&, d]() {
+                try {
+                    pd_options o = *opt;
+                    o.device = (first + d) % have;
+                    o.devices = 1;
+                    if (d) o.verbose = 0;   // one cost report
+                    pd::Index* x = d ? new pd::Index : &h->ix;
+                    if (d) h->more[(size_t)d - 1] = x;
+                    x->build(residues, false, offsets, genome_of, S, k, &o);
+                } catch (const pd::Error& e) {
+                    errs[(size_t)d] = e.what();
+                    codes[(size_t)d] = e.code;
+                } catch (const std::exception& e) {
+                    errs[(size_t)d] = e.what();
+                    codes[(size_t)d] = PD_ERR_CUDA;
+                }
+            });
+        }
+        for (std::thread& t : th) t.join();
+        for (int d = 0; d < devices; d++)
+            if (codes[(size_t)d] != PD_OK) throw pd::Error(codes[(size_t)d], errs[(size_t)d]);
+        // genomes to devices: contiguous row blocks of equal posting-list volume, cut at genome boundaries
+        h->bounds.assign((size_t)devices + 1, 0);
+        h->ix.partition_rows((uint32_t)devices, true, h->bounds.data());
+        h->ix.host_mirrors();
+        h->genome_owner.assign(h->ix.info.G, 0);
+        for (uint32_t s = 0; s < S; s++) {
+            uint32_t d = 0;
+            while (d + 1 < (uint32_t)devices && s >= h->bounds[d + 1]) d++;
+            h->genome_owner[h->ix.genome_of[s]] = d;   // (genomes that are not contiguous gene ranges: the device of their last gene)
+        }
     });
     if (rc != PD_OK) {
         delete h;
@@ -141,12 +204,12 @@ int pd_compute_scores(pd_index* ix, uint32_t genome, pd_scores* out) {
         return PD_ERR_INVALID;
     }
     memset(out, 0, sizeof(*out));
-    return guarded([&] { ix->ix.compute_scores(genome, out); });
+    return guarded([&] { ix->of_genome(genome).compute_scores(genome, out); });
 }
 
 void pd_scores_release(pd_index* ix, pd_scores* s) {
     if (!ix || !s || !s->owner) return;
-    ix->ix.release(static_cast<pd::ScoreContext*>(s->owner));
+    pd::Index::release_context(static_cast<pd::ScoreContext*>(s->owner));
     memset(s, 0, sizeof(*s));
 }
 
@@ -156,12 +219,12 @@ int pd_genome_edges(pd_index* ix, uint32_t genome, pd_edges* out) {
         return PD_ERR_INVALID;
     }
     memset(out, 0, sizeof(*out));
-    return guarded([&] { ix->ix.genome_edges(genome, out); });
+    return guarded([&] { ix->of_genome(genome).genome_edges(genome, out); });
 }
 
 void pd_edges_release(pd_index* ix, pd_edges* e) {
     if (!ix || !e || !e->owner) return;
-    ix->ix.release(static_cast<pd::ScoreContext*>(e->owner));
+    pd::Index::release_context(static_cast<pd::ScoreContext*>(e->owner));
     memset(e, 0, sizeof(*e));
 }
 
@@ -174,7 +237,52 @@ int pd_last_score_stats(const pd_scores* s, pd_score_stats* out) {
 int pd_score_partition_device(pd_index* ix, uint32_t row_begin, uint32_t row_end, uint32_t rows_per_launch, float* d_best_hit,
                               pd_score_stats* stats) {
     if (!ix) return PD_ERR_INVALID;
-    return guarded([&] { ix->ix.score_partition(row_begin, row_end, rows_per_launch, d_best_hit, stats); });
+    if (ix->more.empty()) return guarded([&] { ix->ix.score_partition(row_begin, row_end, rows_per_launch, d_best_hit, stats); });
+    // several devices: every device scores the part of the range that lies in its block, all at the same time
+    return guarded([&] {
+        if (d_best_hit) throw pd::Error(PD_ERR_INVALID, "pd_score_partition_device: no caller-side best-hit table with pd_options.devices > 1");
+        const size_t D = ix->more.size() + 1;
+        std::vector<pd_score_stats> st(D);
+        std::vector<std::string> errs(D);
+        std::vector<int> codes(D, PD_OK);
+        std::vector<std::thread> th;
+        for (size_t d = 0; d < D; d++) {
+            memset(&st[d], 0, sizeof(pd_score_stats));
+            const uint32_t b = std::max(row_begin, ix->bounds[d]), e = std::min(row_end, ix->bounds[d + 1]);
+            if (b >= e) continue;
+            th.emplace_back([&, d, b, e]() {
+                try {
+                    (d ? *ix->more[d - 1] : ix->ix).score_partition(b, e, rows_per_launch, nullptr, &st[d]);
+                } catch (const pd::Error& x) {
+                    errs[d] = x.what();
+                    codes[d] = x.code;
+                } catch (const std::exception& x) {
+                    errs[d] = x.what();
+                    codes[d] = PD_ERR_CUDA;
+                }
+            });
+        }
+        for (std::thread& t : th) t.join();
+        for (size_t d = 0; d < D; d++)
+            if (codes[d] != PD_OK) throw pd::Error(codes[d], errs[d]);
+        if (stats) {
+            memset(stats, 0, sizeof(*stats));
+            for (size_t d = 0; d < D; d++) {
+                stats->rows += st[d].rows; stats->lookups += st[d].lookups; stats->pairs += st[d].pairs; stats->cells += st[d].cells;
+                stats->fallback_rows += st[d].fallback_rows; stats->launches += st[d].launches; stats->fwd_entries += st[d].fwd_entries;
+                stats->retry_rows += st[d].retry_rows;
+                stats->kernel_ms = std::max(stats->kernel_ms, st[d].kernel_ms);   // the devices run side by side
+                stats->total_ms = std::max(stats->total_ms, st[d].total_ms);
+            }
+        }
+    });
+}
+
+int pd_devices(const pd_index* ix) { return ix ? (int)ix->more.size() + 1 : 0; }
+
+int pd_genome_device(const pd_index* ix, uint32_t genome) {
+    if (!ix || genome >= ix->ix.info.G) return -1;
+    return genome < ix->genome_owner.size() ? (int)ix->genome_owner[genome] : 0;
 }
 
 int pd_partition_rows(const pd_index* ix, uint32_t parts, int32_t snap_to_genomes, uint32_t* bounds) {

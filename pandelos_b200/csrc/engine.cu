@@ -254,6 +254,10 @@ ScoreContext* Index::acquire() {
     }
 }
 
+void Index::release_context(ScoreContext* c) {
+    if (c && c->ix) c->ix->release(c);
+}
+
 void Index::release(ScoreContext* c) {
     for (uint32_t i = 0; i < c->map_rows; i++) c->h_map.p[genome_rows[c->map_r0 + i]] = INT32_MAX;
     c->map_rows = 0;

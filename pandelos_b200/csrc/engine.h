@@ -93,6 +93,7 @@ struct Index {
                int32_t k, const pd_options* o);
     ScoreContext* acquire();
     void release(ScoreContext* c);
+    static void release_context(ScoreContext* c);   // to the index the context belongs to
     void compute_scores(uint32_t genome, pd_scores* out);
     void genome_edges(uint32_t genome, pd_edges* out);
     void score_partition(uint32_t row_begin, uint32_t row_end, uint32_t rows_per_launch, float* d_best_hit, pd_score_stats* st);

@@ -200,6 +200,9 @@ int main(int argc, char** argv) {
     memset(&opt, 0, sizeof(opt));
     opt.device = -1;
     opt.verbose = 1;
+    // every visible GPU gets a replica of the index and a share of the genomes (PD_DEVICES caps it)
+    opt.devices = pd_device_count();
+    if (const char* e = getenv("PD_DEVICES")) opt.devices = std::max(1, std::min(opt.devices, atoi(e)));
     pd_index* ix = nullptr;
     if (pd_build(residues.data(), offsets.data(), genome_of.data(), S, k, &opt, &ix) != PD_OK) {
         if (k <= 0) {  // library.cpp:90-93
@@ -232,14 +235,19 @@ int main(int argc, char** argv) {
     // its own edge list; lists are joined in genome order, which is the order the sequential host would report them in.
     std::vector<std::vector<Edge>> per_genome(info.G);
     std::vector<unsigned long long> filtered(info.G, 0);
-    std::atomic<uint32_t> next(0);
+    const int n_dev = std::max(1, pd_devices(ix));
+    std::vector<std::vector<uint32_t>> queue((size_t)n_dev);   // genomes by the device that serves them
+    for (uint32_t g = 0; g < info.G; g++) queue[(size_t)std::max(0, pd_genome_device(ix, g))].push_back(g);
+    std::vector<std::atomic<uint32_t>> next((size_t)n_dev);
+    for (auto& n : next) n.store(0);
     std::atomic<bool> failed(false);
     std::string failure;
     std::mutex failure_mu;
-    auto worker = [&]() {
+    auto worker = [&](int dev) {
         for (;;) {
-            const uint32_t g = next.fetch_add(1);
-            if (g >= info.G || failed.load()) return;
+            const uint32_t qi = next[(size_t)dev].fetch_add(1);
+            if (qi >= queue[(size_t)dev].size() || failed.load()) return;
+            const uint32_t g = queue[(size_t)dev][qi];
             pd_edges e;
             if (pd_genome_edges(ix, g, &e) != PD_OK) {
                 std::lock_guard<std::mutex> lk(failure_mu);
@@ -261,10 +269,12 @@ int main(int argc, char** argv) {
         // every extra worker is an extra score context to warm up (pinned and device result buffers, ~0.1 s): worth it
         // only on inputs with hundreds of genomes
         const int wanted = info.G >= 400 ? 4 : (info.G >= 100 ? 2 : 1);
-        const unsigned n_workers = (unsigned)std::max(1, std::min(threads > 0 ? std::min(threads, wanted) : wanted, 4));
+        const unsigned per_dev = (unsigned)std::max(1, std::min(threads > 0 ? std::min(threads, wanted) : wanted, 4));
         std::vector<std::thread> pool;
-        for (unsigned t = 1; t < n_workers; t++) pool.emplace_back(worker);
-        worker();
+        for (int d = 0; d < n_dev; d++)
+            for (unsigned t = 0; t < per_dev; t++)
+                if (d || t) pool.emplace_back(worker, d);
+        worker(0);
         for (std::thread& t : pool) t.join();
     }
     if (failed.load()) {

@@ -106,6 +106,10 @@ JNIEXPORT void JNICALL Java_infoasys_cli_pangenes_PangeneNative_preprocessSequen
     opt.device = -1;
     opt.verbose = 1;  // the reference always prints its cost report (library.cpp:337-370)
     if (const char* e = getenv("PANDELOS_B200_CONTEXTS")) opt.contexts = atoi(e);
+    // every visible GPU gets a replica of the index and a share of the genomes: the Java pool's computeScores(g) calls
+    // (Pangenes.java:60-66) then run on all of them with no change on the Java side (PD_DEVICES caps it)
+    opt.devices = pd_device_count();
+    if (const char* e = getenv("PD_DEVICES")) opt.devices = atoi(e) < 1 ? 1 : (atoi(e) < opt.devices ? atoi(e) : opt.devices);
     pd_index* ix = nullptr;
     const int rc = pd_build(residues.data(), offsets.data(), genome_of.data(), (uint32_t)S, (int32_t)kvalue, &opt, &ix);
     if (rc != PD_OK) fatal(env, "preprocessSequences");

@@ -27,7 +27,7 @@ class PdError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("verbose", C.c_int32), ("contexts", C.c_int32), ("hash_log2", C.c_int32),
-                ("cell_capacity", C.c_uint64), ("keep_sorted", C.c_int32), ("reserved", C.c_int32)]
+                ("cell_capacity", C.c_uint64), ("keep_sorted", C.c_int32), ("devices", C.c_int32)]
 
 
 class IndexInfo(C.Structure):
@@ -102,6 +102,8 @@ def load(path=None):
     L.pd_edges_release.argtypes = [C.c_void_p, C.POINTER(EdgesStruct)]
     L.pd_score_partition_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(ScoreStats)]
     L.pd_partition_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p]
+    L.pd_devices.argtypes = [C.c_void_p]
+    L.pd_genome_device.argtypes = [C.c_void_p, C.c_uint32]
     L.pd_build_shard.restype = C.c_int
     L.pd_build_shard.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(Options), C.c_uint32, C.c_uint32,
                                  C.POINTER(C.c_void_p), C.POINTER(ShardKeys)]
@@ -173,7 +175,7 @@ class PangeneNative:
     """Device-resident index + scoring calls: `new PangeneNative(k, pid)` / `generateScoresPart(g)`."""
 
     def __init__(self, k, data, device=-1, verbose=False, contexts=0, hash_log2=0, cell_capacity=0, keep_sorted=False,
-                 residues_device_ptr=None, shard=None):
+                 residues_device_ptr=None, shard=None, devices=0):
         """shard = (rank, world): this process builds slice `rank` of an index that `world` processes build together
         (pd_build_shard); the caller exchanges the slices and calls shard_buffers / shard_finish
         (pandelos_b200.multigpu.build_sharded does all of it over torch.distributed)."""
@@ -181,7 +183,7 @@ class PangeneNative:
         self._L = L
         self._data = data
         self.k = int(k)
-        opt = Options(int(device), int(verbose), int(contexts), int(hash_log2), int(cell_capacity), int(keep_sorted), 0)
+        opt = Options(int(device), int(verbose), int(contexts), int(hash_log2), int(cell_capacity), int(keep_sorted), int(devices))
         h = C.c_void_p()
         S = data.sequences_count
         self.shard_keys = None
@@ -287,6 +289,12 @@ class PangeneNative:
     def shard_finish(self):
         _check(self._L.pd_shard_finish(self._h))
         _check(self._L.pd_info(self._h, C.byref(self.info)))
+
+    def devices(self):
+        return int(self._L.pd_devices(self._h))
+
+    def genome_device(self, genome):
+        return int(self._L.pd_genome_device(self._h, int(genome)))
 
     # ---- diagnostics / partitions
     def gene_stats(self):
