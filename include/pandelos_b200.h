@@ -110,6 +110,10 @@ int pd_build(const uint8_t* residues, const uint64_t* offsets, const uint32_t* g
 int pd_build_device(const uint8_t* d_residues, const uint64_t* offsets, const uint32_t* genome_of, uint32_t S, int32_t k,
                     const pd_options* opt, pd_index** out);
 void pd_free(pd_index* ix);
+/* pd_free keeps the index's score contexts (streams, device and pinned result buffers) and its device blocks in per-device
+ * caches for the next index (a new index per request is the expected use; PD_CACHE_KEEP_MB caps the idle device bytes).
+ * pd_trim gives all of it back to the driver; call it when no index will be built for a while. */
+void pd_trim(void);
 
 int pd_info(const pd_index* ix, pd_index_info* out);
 /* per gene: kseq_lengths (library.cpp:250-262) and computation_costs[].total_visited (library.cpp:327); either may be NULL */

@@ -57,6 +57,11 @@ int build_common(const uint8_t* residues, bool on_device, const uint64_t* offset
     }
     *out = nullptr;
     pd_index* h = nullptr;
+    struct DeviceRestore {   // pd_options.device selects the index's device; the caller's current device is left as it was
+        int dev = -1;
+        DeviceRestore() { if (pd::rt::device_count() > 0) { try { dev = pd::rt::current_device(); } catch (...) { dev = -1; } } }
+        ~DeviceRestore() { if (dev >= 0) { try { pd::rt::set_device(dev); } catch (...) {} } }
+    } restore;
     int rc = guarded([&] {
         h = new pd_index;
         h->ix.shard_rank = rank;
@@ -175,6 +180,13 @@ int pd_shard_finish(pd_index* ix) {
 }
 
 void pd_free(pd_index* ix) { delete ix; }
+
+void pd_trim(void) {
+    try {
+        pd::trim_memory();
+    } catch (...) {
+    }
+}
 
 int pd_info(const pd_index* ix, pd_index_info* out) {
     if (!ix || !out) return PD_ERR_INVALID;

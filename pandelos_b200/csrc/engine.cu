@@ -214,6 +214,9 @@ Index::~Index() {
     ContextPool& pool = context_pool();
     for (ScoreContext* c : all_ctx) {
         c->ix = nullptr;
+        // a context the caller still holds (pd_scores / pd_edges not released) is not parked: its buffers are in use and
+        // its flat_map rows are still set; it is deleted when the caller releases it (release_context)
+        if (std::find(free_ctx.begin(), free_ctx.end(), c) == free_ctx.end()) continue;
         std::unique_lock<std::mutex> lk(pool.mu);
         std::vector<ScoreContext*>& v = pool.parked[device & 15];
         if (v.size() < kParkedPerDevice) {
@@ -223,6 +226,21 @@ Index::~Index() {
             delete c;
         }
     }
+}
+
+// drops everything the library keeps between indices: parked score contexts, cached device and pinned host blocks
+void trim_memory() {
+    std::vector<ScoreContext*> drop;
+    {
+        ContextPool& pool = context_pool();
+        std::lock_guard<std::mutex> lk(pool.mu);
+        for (auto& v : pool.parked) {
+            drop.insert(drop.end(), v.begin(), v.end());
+            v.clear();
+        }
+    }
+    for (ScoreContext* c : drop) delete c;
+    rt::trim_all();
 }
 
 ScoreContext* Index::acquire() {
@@ -255,7 +273,9 @@ ScoreContext* Index::acquire() {
 }
 
 void Index::release_context(ScoreContext* c) {
-    if (c && c->ix) c->ix->release(c);
+    if (!c) return;
+    if (c->ix) c->ix->release(c);
+    else delete c;   // its index is gone (pd_free before pd_scores_release): nothing to hand it back to
 }
 
 void Index::release(ScoreContext* c) {
@@ -293,7 +313,12 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     info.k = k;
     thr = 1.0f / (2.0f * (float)k);
 
-    rt::stream_t st = rt::stream_create();
+    struct StreamGuard {   // every exit path, the throwing ones too, gives the stream back
+        rt::stream_t s;
+        StreamGuard() : s(rt::stream_create()) {}
+        ~StreamGuard() { rt::stream_destroy(s); }
+    } st_guard;
+    rt::stream_t st = st_guard.s;
     uint64_t launches = 0;
     Timer t_all(st), t_h2d(st), t_hist(st), t_enc(st), t_sort(st), t_grp(st), t_fwd(st);
     t_all.start();
@@ -309,28 +334,22 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     }
     rt::DevBuf<uint64_t> d_gene_off((size_t)S + 1);
     rt::DevBuf<uint32_t> d_gid(std::max<size_t>(S, 1)), d_kseq((size_t)S + 1), d_key_off((size_t)S + 1), d_flags(4), d_total(4);
+    rt::DevBuf<unsigned long long> d_n64(2);
+    rt::zero(d_n64.p, 2 * sizeof(unsigned long long), st);
     rt::h2d(d_gene_off.p, offsets, sizeof(uint64_t) * ((size_t)S + 1), st);
     rt::h2d(d_gid.p, genome_ids, sizeof(uint32_t) * S, st);
     rt::zero(d_flags.p, 4 * sizeof(uint32_t), st);
     meta.alloc(std::max<size_t>(S, 1));
     PD_LAUNCH(ik::gene_meta_kernel, blocks_for((uint64_t)S + 1), 256, 0, st, (const uint64_t*)d_gene_off.p, (const uint32_t*)d_gid.p, S, (int)k,
-              d_kseq.p, meta.p, d_flags.p);
+              d_kseq.p, meta.p, d_flags.p, d_n64.p);
     launches++;
     rt::DevBuf<uint32_t> scratch(prims::scan_tmp_words((uint64_t)S + 1) + 16);
     prims::exclusive_scan_u32(d_kseq.p, d_key_off.p, (uint64_t)S + 1, scratch.p, nullptr, st, &launches);
     uint32_t h_flags[4] = {0, 0, 0, 0}, h_N = 0;
     rt::d2h(h_flags, d_flags.p, sizeof(h_flags), st);
     rt::d2h(&h_N, d_key_off.p + S, sizeof(uint32_t), st);
-    // a k-mer total of 2^31 or more would wrap the 32-bit scan: bound it on the host from the residue total
-    if (total >= (1ull << 31) + (uint64_t)S * (uint64_t)(k - 1)) {
-        uint64_t Nh = 0;
-        for (uint32_t s = 0; s < S && Nh < (1ull << 31); s++) {
-            if (offsets[s + 1] < offsets[s]) throw Error(PD_ERR_INVALID, "offsets must be ascending");
-            const uint64_t len = offsets[s + 1] - offsets[s];
-            if (len >= (uint64_t)k) Nh += len - k + 1;
-        }
-        if (Nh >= (1ull << 31)) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more k-mers (the reference's own int index limit)");
-    }
+    unsigned long long h_n64 = 0;   // the exact k-mer total: the 32-bit scan above wraps at 2^32
+    rt::d2h(&h_n64, d_n64.p, sizeof(h_n64), st);
     t_h2d.stop();
 
     // ---- alphabet (library.cpp:216-230, 96-100)
@@ -348,6 +367,7 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     t_hist.stop();
     if (h_flags[0] & 1u) throw Error(PD_ERR_INVALID, "offsets must be ascending");
     if (h_flags[0] & 2u) throw Error(PD_ERR_UNSUPPORTED, "a gene of 2^20 or more residues");
+    if (h_n64 >= (1ull << 31)) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more k-mers (the reference's own int index limit)");
     const uint64_t N = h_N;
     const uint32_t G = S ? h_flags[1] + 1 : 0;  // library.cpp:242
     info.G = G;
@@ -488,7 +508,6 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         info.build_ms[6] = t_h2d.ms();
         info.build_ms[7] = (double)launches;
         info.max_kseq = h_flags[2];
-        rt::stream_destroy(st);
         return;
     }
 
@@ -659,7 +678,6 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     info.build_ms[5] = t_all.ms();
     info.build_ms[6] = t_h2d.ms();
     info.build_ms[7] = (double)launches;
-    rt::stream_destroy(st);
 
     if (opt.verbose) {
         // the reference's cost report (library.cpp:347-370); "Total cost" is the work-unit ground truth

@@ -103,5 +103,6 @@ struct Index {
 };
 
 void set_last_error(const std::string& s);
+void trim_memory();
 
 }  // namespace pd

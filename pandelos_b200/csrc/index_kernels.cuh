@@ -39,7 +39,7 @@ static const unsigned long long kClsMask = (1ull << kClsBits) - 1ull;
 // its exclusive scan ends in N.
 __global__ void __launch_bounds__(256) gene_meta_kernel(const uint64_t* __restrict__ off, const uint32_t* __restrict__ genome_ids,
                                                          uint32_t S, int k, uint32_t* __restrict__ kseq, uint2* __restrict__ meta,
-                                                         uint32_t* __restrict__ flags) {
+                                                         uint32_t* __restrict__ flags, unsigned long long* __restrict__ n_kmers) {
     const uint32_t s = blockIdx.x * 256u + threadIdx.x;
     uint32_t err = 0, gid = 0, kl = 0;
     if (s < S) {
@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(256) gene_meta_kernel(const uint64_t* __restri
     } else if (s == S) {
         kseq[S] = 0;
     }
+    uint32_t ksum = kl;   // per warp < 32 * 2^20: no overflow
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         err |= __shfl_xor_sync(0xffffffffu, err, d);
@@ -64,11 +65,13 @@ __global__ void __launch_bounds__(256) gene_meta_kernel(const uint64_t* __restri
         gid = o > gid ? o : gid;
         const uint32_t ok = __shfl_xor_sync(0xffffffffu, kl, d);
         kl = ok > kl ? ok : kl;
+        ksum += __shfl_xor_sync(0xffffffffu, ksum, d);
     }
     if ((threadIdx.x & 31) == 0) {
         if (err) atomicOr(&flags[0], err);
         atomicMax(&flags[1], gid);
         atomicMax(&flags[2], kl);
+        if (ksum) atomicAdd(n_kmers, (unsigned long long)ksum);   // the exact k-mer total in 64 bits (the 32-bit scan may wrap)
     }
 }
 

@@ -103,18 +103,21 @@ inline void collect() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return;
     BlockCache& c = block_cache(dev);
+    // only the blocks queued BEFORE the synchronisation are known to be idle after it: a block another thread frees
+    // while this one waits may still be read by kernels queued after the wait began
+    std::vector<void*> idle;
     {
         std::lock_guard<std::mutex> lk(c.mu);
         if (c.pending.empty()) return;
+        idle.swap(c.pending);
     }
     cudaDeviceSynchronize();
     std::lock_guard<std::mutex> lk(c.mu);
-    for (void* p : c.pending) {
+    for (void* p : idle) {
         const size_t sz = c.live[p].first;
         c.free_blocks.emplace(sz, p);
         c.cached += sz;
     }
-    c.pending.clear();
     // Give memory back only when the idle blocks exceed three quarters of the device (asked once: cudaMemGetInfo and
     // cudaFree cost milliseconds to tens of milliseconds, and a trimmed block is the next build's cudaMalloc);
     // an allocation that fails empties the cache anyway (dmalloc).
@@ -175,6 +178,8 @@ inline void dfree(void* p) {
     }
     cudaFree(p);
 }
+// gives every idle cached block of every device (and the idle pinned host blocks) back to the driver
+inline void trim_all();
 // allocator statistics since the last call (PD_TRACE): cache hits, cudaMalloc calls, their bytes and host time
 inline void cache_stats(int dev, uint64_t* hits, uint64_t* misses, uint64_t* miss_bytes, uint64_t* miss_ns) {
     BlockCache& c = block_cache(dev);
@@ -228,6 +233,32 @@ inline void hfree(void* p) {
     }
     c.free_blocks.emplace(it->second, p);
     c.cached += it->second;
+}
+inline void trim_all() {
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) return;
+    for (int d = 0; d < 16; d++) {
+        BlockCache& c = block_cache(d);
+        bool any;
+        {
+            std::lock_guard<std::mutex> lk(c.mu);
+            any = !c.pending.empty() || !c.free_blocks.empty();
+        }
+        if (!any) continue;
+        if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); continue; }
+        collect();
+        std::lock_guard<std::mutex> lk(c.mu);
+        trim_cache(c, 0);
+    }
+    cudaSetDevice(cur);
+    HostCache& h = host_cache();
+    std::lock_guard<std::mutex> lk(h.mu);
+    for (auto& kv : h.free_blocks) {
+        cudaFreeHost(kv.second);
+        h.live.erase(kv.second);
+    }
+    h.free_blocks.clear();
+    h.cached = 0;
 }
 inline stream_t stream_create() { stream_t s; PD_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return s; }
 inline void stream_destroy(stream_t s) { cudaStreamDestroy(s); }
@@ -298,6 +329,7 @@ inline void* dmalloc(size_t n) {
 }
 inline void dfree(void* p) { free(p); }
 inline void collect() {}
+inline void trim_all() {}
 inline void* hmalloc(size_t n) { return malloc(n ? n : 1); }
 inline void hfree(void* p) { free(p); }
 inline stream_t stream_create() { return 0; }

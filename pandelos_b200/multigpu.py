@@ -114,6 +114,12 @@ def score_and_gather(pn, gather, rank, row_begin):
     """Scores this rank's genes [row_begin, row_begin + rows) chunk by chunk with `pn.score_partition_device`, queueing
     each chunk's all-gather behind it; returns the summed pd_score_stats fields as a dict.  `gather.local` must be zero
     where rows are padding (it is after construction; the engine zeroes the rows it scores)."""
+    try:   # gather.local was made (zero-filled) on torch's stream; the engine writes it from its own streams
+        import torch
+        if gather.local.is_cuda:
+            torch.cuda.current_stream(gather.local.device).synchronize()
+    except ImportError:
+        pass
     total = None
     for c in range(gather.chunks):
         lo, hi = gather.local_range(rank, c)

@@ -92,6 +92,7 @@ def load(path=None):
         f.restype = C.c_int
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(Options), C.POINTER(C.c_void_p)]
     L.pd_free.argtypes = [C.c_void_p]
+    L.pd_trim.argtypes = []
     L.pd_info.argtypes = [C.c_void_p, C.POINTER(IndexInfo)]
     L.pd_gene_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.pd_entries.argtypes = [C.c_void_p] * 6

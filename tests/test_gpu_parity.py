@@ -255,3 +255,48 @@ def test_jni_dropin_against_unmodified_reference_library():
         check_scores(a, b, "jni genome %d" % g)
         cells += a.scoresCount
     assert cells > 0
+
+
+def test_several_devices_serve_the_same_results():
+    """pd_options.devices = 2: one replica per device, genomes dealt out by posting-list volume; every per-genome result
+    must be what a single-device index returns, and the partition call must see the same job."""
+    import ctypes as C
+    if native.load().pd_device_count() < 2:
+        pytest.skip("one device visible")
+    w = synth.shape("mycoplasma64", scale=0.3)
+    k = 4
+    data = native.PangeneIData(w.residues, w.offsets, w.genome_of)
+    one = native.PangeneNative(k, data)
+    two = native.PangeneNative(k, data, devices=2)
+    try:
+        assert two.devices() == 2 and one.devices() == 1
+        owners = [two.genome_device(g) for g in range(one.info.G)]
+        assert set(owners) == {0, 1} and owners == sorted(owners)
+        for g in range(one.info.G):
+            assert _scores_digest(two.generateScoresPart(g)) == _scores_digest(one.generateScoresPart(g)), g
+            a, b = two.genomeEdges(g), one.genomeEdges(g)
+            assert sorted(zip(a[0].tolist(), a[1].tolist(), a[2].view(np.uint32).tolist())) == sorted(zip(b[0].tolist(), b[1].tolist(), b[2].view(np.uint32).tolist()))
+        s2, s1 = two.score_partition_device(0, one.info.S), one.score_partition_device(0, one.info.S)
+        assert (s2.pairs, s2.cells, s2.lookups, s2.rows) == (s1.pairs, s1.cells, s1.lookups, s1.rows)
+    finally:
+        one.close()
+        two.close()
+    native.load().pd_trim()
+
+
+def test_release_after_free_and_trim():
+    """A Scores object released after its index was freed (a host that tears down in the wrong order) and pd_trim between
+    indices: no crash, the next index works and returns the same result."""
+    import ctypes as C
+    w = synth.generate(4, 80, 90.0, 0.1, 81)
+    data = native.PangeneIData(w.residues, w.offsets, w.genome_of)
+    L = native.load()
+    pn = native.PangeneNative(4, data)
+    want = _scores_digest(pn.generateScoresPart(1))
+    st, rel = pn.compute_scores_raw(2)
+    pn.close()
+    rel()
+    L.pd_trim()
+    pn = native.PangeneNative(4, data)
+    assert _scores_digest(pn.generateScoresPart(1)) == want
+    pn.close()
