@@ -41,6 +41,7 @@ static const uint32_t kFlag = 0x80000000u;      // counter word: "this column ha
 static const uint32_t kMulti = 0x80000000u;     // posting / forward length: multiplicity > 1 (then *_cnt is read)
 static const uint32_t kShortList = 64;          // lists up to this length are flattened
 static const uint32_t kHugeList = 2048;         // lists longer than this are walked by the whole CTA
+static const uint32_t kLongFirst = 256;         // long lists above this length are handed out before the shorter ones
 static const uint32_t kXSlots = 2048;           // side-table slots per CTA (global memory)
 static const uint32_t kXCap = kXSlots * 3 / 4;
 static const uint32_t kProbeLimit = 160;        // probes after which a row is declared too big for its table
@@ -496,6 +497,31 @@ struct WarpScratch {
 __device__ __forceinline__ void round_step(const ScoreArgs& a, const Tab& t, LaneQueue& lq, uint32_t (&e)[kItems], uint32_t cnt,
                                            uint32_t pos, uint32_t mj, const uint32_t* __restrict__ nq, int nrem, uint32_t self) {
     const unsigned lane = threadIdx.x & 31;
+    if (kItems % 4 == 0 && cnt >= 32u * kItems && mj == 1) {
+        // a full round of a k-mer the row holds once (nearly all rounds of the conserved lists): four postings per lane at
+        // a time, no per-pair checks; a repeated posting (bit 31) is a per-lane side step
+#pragma unroll
+        for (int u = 0; u < kItems; u += 4) {
+            uint32_t c[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                c[i] = e[u + i];
+                e[u + i] = nrem > 32 * (u + i) ? nq[32 * (u + i)] : self;
+            }
+            if ((c[0] | c[1] | c[2] | c[3]) & kMulti) {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (c[i] & kMulti) {
+                        add_general(gen_args(a, t), c[i] & ~kMulti, a.post_cnt[pos + 32u * (u + i) + lane], 1u);
+                        c[i] = self;
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) item_add(a, t, lq, c[i]);
+            queue_check(a, t, lq, kLaneDrain);
+        }
+        return;
+    }
 #pragma unroll
     for (int u = 0; u < kItems; u += 2) {
         uint32_t c0 = e[u], c1 = e[u + 1];
@@ -545,16 +571,25 @@ __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t_in, 
     {
         uint32_t e[kItems];
         uint32_t gs = 0, gl = 0, mj = 1, p0 = 0;
+        // The lists are handed out in two rounds over the same counter: the longer ones (> kLongFirst postings) first, the
+        // rest after them, so that the last lists in flight when the row ends are short and the warps reach the row's
+        // barrier within one round of each other instead of up to a whole 2048-posting list apart.
+        const uint32_t n_long = nl - ns;
         auto claim = [&](uint32_t& cgs, uint32_t& cgl, uint32_t& cmj) -> bool {
-            uint32_t li = 0;
-            if (lane == 0) li = *t.over() ? 0x7FFFFFFFu : atomicAdd(ctr + 1, 1u);  // one lane polls the stop flag
-            li = __shfl_sync(0xffffffffu, li, 0);
-            if (li >= nl - ns) return false;
-            const uint2 fw = fbuf[ns + li];
-            cmj = (fw.y & kMulti) ? a.fwd_cnt[f0 + ns + li] : 1u;
-            cgl = fw.y & ~kMulti;
-            cgs = fw.x;
-            return true;
+            for (;;) {
+                uint32_t li = 0;
+                if (lane == 0) li = *t.over() ? 0x7FFFFFFFu : atomicAdd(ctr + 1, 1u);  // one lane polls the stop flag
+                li = __shfl_sync(0xffffffffu, li, 0);
+                if (li >= 2u * n_long) return false;
+                const uint32_t idx = li < n_long ? li : li - n_long;
+                const uint2 fw = fbuf[ns + idx];
+                const uint32_t gl = fw.y & ~kMulti;
+                if ((li < n_long) != (gl > kLongFirst)) continue;  // the other round's
+                cmj = (fw.y & kMulti) ? a.fwd_cnt[f0 + ns + idx] : 1u;
+                cgl = gl;
+                cgs = fw.x;
+                return true;
+            }
         };
         bool have = claim(gs, gl, mj);
         if (have) {
@@ -887,7 +922,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) score_rows_kernel(Sco
                             pairs++;
                             uint32_t inter, pc, tc;
                             slot_sums(xt, c, cnt[s], &inter, &pc, &tc);
-                            valid = gate(a.k2, pc, tc, rc.kr, a.meta[c].x);
+                            // the row-side test needs no gather: homologs pass it, and only what fails it looks up the column's length
+                            valid = (a.k2 * pc >= rc.kr) || gate(a.k2, pc, tc, rc.kr, a.meta[c].x);
                         }
                         if (!valid) {
                             keys[s] = kEmpty;
