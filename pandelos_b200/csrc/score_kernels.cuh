@@ -41,6 +41,7 @@ static const uint32_t kFlag = 0x80000000u;      // counter word: "this column ha
 static const uint32_t kMulti = 0x80000000u;     // posting / forward length: multiplicity > 1 (then *_cnt is read)
 static const uint32_t kShortList = 64;          // lists up to this length are flattened
 static const uint32_t kHugeList = 2048;         // lists longer than this are walked by the whole CTA
+static const uint32_t kLongFirst = 256;         // long lists above this length are handed out before the shorter ones
 static const uint32_t kXSlots = 2048;           // side-table slots per CTA (global memory)
 static const uint32_t kXCap = kXSlots * 3 / 4;
 static const uint32_t kProbeLimit = 160;        // probes after which a row is declared too big for its table
@@ -566,50 +567,44 @@ __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t_in, 
     lq.base = smem_addr(ws.queue + lane);
     lq.wr = lq.base;
     const unsigned le = 0xffffffffu >> (31 - lane);  // lanes <= mine
-    // ---- long lists: the work unit is one ROUND (kItems x 32 postings) of one list, handed out through a shared word
-    // (list << 8 | round) by compare-and-swap.  Whole lists as units left the warps up to a list (three rounds for the
-    // conserved k-mers of this workload) apart at the end of the row: 11 % of all stall samples were warps waiting at the
-    // row's closing barrier.
+    // ---- long lists: one warp per list
     {
         uint32_t e[kItems];
         uint32_t gs = 0, gl = 0, mj = 1, p0 = 0;
+        // The lists are handed out in two rounds over the same counter: the longer ones (> kLongFirst postings) first, the
+        // rest after them, so that the last lists in flight when the row ends are short and the warps reach the row's
+        // barrier within one round of each other instead of up to a whole 2048-posting list apart.
         const uint32_t n_long = nl - ns;
-        auto claim = [&](uint32_t& cgs, uint32_t& cgl, uint32_t& cmj, uint32_t& cp0) -> bool {
-            uint32_t li = 0x7FFFFFFFu, r = 0;
-            if (lane == 0 && !*t.over()) {   // one lane polls the stop flag and takes the unit
-                uint32_t old = *(volatile uint32_t*)(ctr + 1);
-                for (;;) {
-                    li = old >> 8;
-                    r = old & 0xFFu;
-                    if (li >= n_long) break;
-                    const uint32_t l = fbuf[ns + li].y & ~kMulti;
-                    const uint32_t next = (r + 1) * (32u * kItems) < l ? old + 1u : ((li + 1u) << 8);
-                    const uint32_t seen = atomicCAS(ctr + 1, old, next);
-                    if (seen == old) break;
-                    old = seen;
-                }
+        auto claim = [&](uint32_t& cgs, uint32_t& cgl, uint32_t& cmj) -> bool {
+            for (;;) {
+                uint32_t li = 0;
+                if (lane == 0) li = *t.over() ? 0x7FFFFFFFu : atomicAdd(ctr + 1, 1u);  // one lane polls the stop flag
+                li = __shfl_sync(0xffffffffu, li, 0);
+                if (li >= 2u * n_long) return false;
+                const uint32_t idx = li < n_long ? li : li - n_long;
+                const uint2 fw = fbuf[ns + idx];
+                const uint32_t gl = fw.y & ~kMulti;
+                if ((li < n_long) != (gl > kLongFirst)) continue;  // the other round's
+                cmj = (fw.y & kMulti) ? a.fwd_cnt[f0 + ns + idx] : 1u;
+                cgl = gl;
+                cgs = fw.x;
+                return true;
             }
-            li = __shfl_sync(0xffffffffu, li, 0);
-            r = __shfl_sync(0xffffffffu, r, 0);
-            if (li >= n_long) return false;
-            const uint2 fw = fbuf[ns + li];
-            cmj = (fw.y & kMulti) ? a.fwd_cnt[f0 + ns + li] : 1u;
-            cgl = fw.y & ~kMulti;
-            cgs = fw.x;
-            cp0 = r * (32u * kItems);
-            return true;
         };
-        bool have = claim(gs, gl, mj, p0);
+        bool have = claim(gs, gl, mj);
         if (have) {
 #pragma unroll
-            for (int u = 0; u < kItems; u++) e[u] = p0 + 32u * u + lane < gl ? a.post[gs + p0 + 32u * u + lane] : self;
+            for (int u = 0; u < kItems; u++) e[u] = 32u * u + lane < gl ? a.post[gs + 32u * u + lane] : self;
         }
         while (have) {
-            uint32_t ngs = 0, ngl = 0, nmj = 1, np0 = 0;
-            const bool nhave = claim(ngs, ngl, nmj, np0);
+            uint32_t ngs = gs, ngl = gl, nmj = mj, np0 = p0 + 32 * kItems;
+            bool nhave = true;
+            if (np0 >= gl) {
+                nhave = claim(ngs, ngl, nmj);
+                np0 = 0;
+            }
             const int nrem = nhave ? (int)(ngl - np0) - (int)lane : 0;
-            const uint32_t left = gl - p0;
-            round_step(a, t, lq, e, left < 32u * kItems ? left : 32u * kItems, gs + p0, mj, a.post + ngs + np0 + lane, nrem, self);
+            round_step(a, t, lq, e, gl - p0, gs + p0, mj, a.post + ngs + np0 + lane, nrem, self);
             gs = ngs;
             gl = ngl;
             mj = nmj;
