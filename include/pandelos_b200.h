@@ -190,6 +190,10 @@ int pd_build_shard(const uint8_t* residues, int32_t residues_on_device, const ui
 int pd_shard_recv(pd_index* ix, uint64_t n_recv, uint64_t** d_recv);
 int pd_shard_sort(pd_index* ix, pd_shard_info* info);
 int pd_shard_buffers(pd_index* ix, uint64_t max_entries, uint64_t max_multi, pd_shard_arrays* out);
+/* pd_shard_buffers may be called with max_multi = 0 as soon as an upper bound of the slices' entries is known (a slice has at
+ * most as many entries as it received k-mers), so that the all-gather of the postings starts before the exact counts have been
+ * exchanged; pd_shard_multi then makes the third array (world x max_multi x 2) once the list sizes are known. */
+int pd_shard_multi(pd_index* ix, uint64_t max_multi, uint32_t** d_multi);
 int pd_shard_groups(pd_index* ix, const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds);
 int pd_shard_finish(pd_index* ix);
 

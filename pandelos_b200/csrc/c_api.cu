@@ -169,6 +169,11 @@ int pd_shard_buffers(pd_index* ix, uint64_t max_entries, uint64_t max_multi, pd_
     return guarded([&] { ix->ix.shard_buffers(max_entries, max_multi, out); });
 }
 
+int pd_shard_multi(pd_index* ix, uint64_t max_multi, uint32_t** d_multi) {
+    if (!ix || !d_multi) return PD_ERR_INVALID;
+    return guarded([&] { *d_multi = ix->ix.shard_multi(max_multi); });
+}
+
 int pd_shard_groups(pd_index* ix, const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds) {
     if (!ix || !entries_of_rank || !multi_of_rank || !bounds) return PD_ERR_INVALID;
     return guarded([&] { ix->ix.shard_groups(entries_of_rank, multi_of_rank, bounds); });

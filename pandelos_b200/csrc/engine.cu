@@ -814,14 +814,14 @@ void Index::shard_buffers(uint64_t max_entries, uint64_t max_multi, pd_shard_arr
     if (!shard) throw Error(PD_ERR_INVALID, "not a sharded build in progress");
     rt::set_device(device);
     Shard& sh = *shard;
-    if (max_entries < sh.U_r || max_multi < sh.M_r) throw Error(PD_ERR_INVALID, "segment smaller than this rank's slice");
+    if (max_entries < sh.U_r || (max_multi && max_multi < sh.M_r)) throw Error(PD_ERR_INVALID, "segment smaller than this rank's slice");
     sh.seg = (max_entries + 4095) / 4096 * 4096;
-    sh.mseg = std::max<uint64_t>(max_multi, 1);
+    sh.mseg = max_multi;   // 0: the repeated-entry lists get their array later (shard_multi), once their sizes are known
     if (sh.seg * shard_world >= 0x7FFFFFFFull) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more (padded) entries");
     rt::stream_t st = rt::stream_create();
     post.alloc((size_t)sh.seg * shard_world);
     sh.heads_all.alloc((size_t)sh.seg / 32 * shard_world);
-    sh.multi_all.alloc((size_t)2 * sh.mseg * shard_world);
+    if (sh.mseg) sh.multi_all.alloc((size_t)2 * sh.mseg * shard_world);
     uint32_t* my_post = post.p + (size_t)sh.seg * shard_rank;
     uint32_t* my_heads = sh.heads_all.p + (size_t)sh.seg / 32 * shard_rank;
     rt::zero(my_heads, sizeof(uint32_t) * (sh.seg / 32), st);
@@ -829,17 +829,33 @@ void Index::shard_buffers(uint64_t max_entries, uint64_t max_multi, pd_shard_arr
     rt::d2d(my_heads, sh.heads_slice.p, sizeof(uint32_t) * (((size_t)sh.U_r + 31) / 32), st);
     if (sh.seg > sh.U_r)
         PD_LAUNCH(ik::shard_pad_kernel, blocks_for(sh.seg - sh.U_r), 256, 0, st, my_post, my_heads, sh.U_r, (uint32_t)sh.seg);
-    rt::d2d(sh.multi_all.p + (size_t)2 * sh.mseg * shard_rank, sh.multi_slice.p, sizeof(uint32_t) * 2 * sh.M_r, st);
+    if (sh.mseg) rt::d2d(sh.multi_all.p + (size_t)2 * sh.mseg * shard_rank, sh.multi_slice.p, sizeof(uint32_t) * 2 * sh.M_r, st);
     rt::sync(st);
     rt::stream_destroy(st);
     sh.post_slice.release();
     sh.heads_slice.release();
-    sh.multi_slice.release();
+    if (sh.mseg) sh.multi_slice.release();
     out->d_post = post.p;
     out->d_heads = sh.heads_all.p;
-    out->d_multi = sh.multi_all.p;
+    out->d_multi = sh.mseg ? sh.multi_all.p : nullptr;
     out->seg = sh.seg;
     out->mseg = sh.mseg;
+}
+
+// The array of the repeated-entry lists when pd_shard_buffers was called before their sizes were known (max_multi = 0).
+uint32_t* Index::shard_multi(uint64_t max_multi) {
+    if (!shard || !shard->seg) throw Error(PD_ERR_INVALID, "pd_shard_buffers has not been called");
+    rt::set_device(device);
+    Shard& sh = *shard;
+    if (max_multi < sh.M_r) throw Error(PD_ERR_INVALID, "segment smaller than this rank's list");
+    sh.mseg = std::max<uint64_t>(max_multi, 1);
+    sh.multi_all.alloc((size_t)2 * sh.mseg * shard_world);
+    rt::stream_t st = rt::stream_create();
+    rt::d2d(sh.multi_all.p + (size_t)2 * sh.mseg * shard_rank, sh.multi_slice.p, sizeof(uint32_t) * 2 * sh.M_r, st);
+    rt::sync(st);
+    rt::stream_destroy(st);
+    sh.multi_slice.release();
+    return sh.multi_all.p;
 }
 
 // Step 3a: everything that does not need the gathered postings — multiplicities, group structure from the head bits,
@@ -847,6 +863,7 @@ void Index::shard_buffers(uint64_t max_entries, uint64_t max_multi, pd_shard_arr
 void Index::shard_groups(const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds) {
     if (!shard || !shard->seg) throw Error(PD_ERR_INVALID, "pd_shard_buffers has not been called");
     if (shard->grouped) throw Error(PD_ERR_INVALID, "pd_shard_groups called twice");
+    if (!shard->mseg) throw Error(PD_ERR_INVALID, "pd_shard_multi has not been called");
     rt::set_device(device);
     Shard& sh = *shard;
     const uint32_t S = info.S, G = info.G, W = shard_world;

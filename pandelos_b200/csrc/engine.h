@@ -85,6 +85,7 @@ struct Index {
     uint64_t* shard_recv(uint64_t n_recv);
     void shard_sort(pd_shard_info* out);
     void shard_buffers(uint64_t max_entries, uint64_t max_multi, pd_shard_arrays* out);
+    uint32_t* shard_multi(uint64_t max_multi);
     void shard_groups(const uint64_t* entries_of_rank, const uint64_t* multi_of_rank, uint32_t* bounds);
     void shard_finish();
 

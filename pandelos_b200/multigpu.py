@@ -149,6 +149,18 @@ def _as_tensor(ptr, count, bits, device):
     return torch.from_numpy(np.ctypeslib.as_array((ct * int(count)).from_address(int(ptr))))
 
 
+_bulk_groups = {}
+
+
+def _bulk_group(dist):
+    """A second communicator for the one large transfer (the all-gather of the postings): collectives of one communicator
+    run in order, so on the default group the small exchanges that follow would queue behind it."""
+    key = (dist.get_backend(), dist.get_world_size())
+    if key not in _bulk_groups:
+        _bulk_groups[key] = dist.new_group(ranks=list(range(dist.get_world_size())))
+    return _bulk_groups[key]
+
+
 def build_sharded(dist, native, k, data, device=None, device_index=-1, residues_device_ptr=None, **engine_kw):
     """ONE index built by all ranks of `dist` together (include/pandelos_b200.h, pd_build_shard ...): every rank makes the
     k-mers of its share of the genes, an all-to-all moves every k-mer to the rank that owns its slice of the rank space,
@@ -162,6 +174,7 @@ def build_sharded(dist, native, k, data, device=None, device_index=-1, residues_
     rank, world = dist.get_rank(), dist.get_world_size()
     cpu = device is None or getattr(device, "type", "cpu") != "cuda"
     tdev = None if cpu else device
+    bulk = _bulk_group(dist)   # (made once; every rank must make it at the same point)
     pn = native.PangeneNative(k, data, device=device_index, residues_device_ptr=residues_device_ptr, shard=(rank, world), **engine_kw)
     # ---- k-mers to the rank that sorts them
     send_counts = torch.tensor([int(pn.shard_keys.send_counts[r]) for r in range(world)], dtype=torch.int64, device=tdev)
@@ -177,26 +190,28 @@ def build_sharded(dist, native, k, data, device=None, device_index=-1, residues_
     if not cpu:
         torch.cuda.current_stream().synchronize()   # the engine works on its own streams
     si = pn.shard_sort()
-    # ---- the slices' results to every rank
+    # ---- the slices' results to every rank.  A slice has at most as many entries as it received k-mers, so the segment size
+    # of the postings is known already: their all-gather (4 B per posting, the bulk) starts now and runs behind everything else
+    seg_bound = int(all_counts.sum(axis=0).max())
+    arr = pn.shard_buffers(seg_bound, 0)
+    seg = int(arr.seg)
+    post_all = _as_tensor(arr.d_post, seg * world, 32, device)
+    post_work = dist.all_gather_into_tensor(post_all, post_all[rank * seg:(rank + 1) * seg], group=bulk, async_op=True)   # in place: segment r is rank r's
+    heads_all = _as_tensor(arr.d_heads, seg // 32 * world, 32, device)
+    dist.all_gather_into_tensor(heads_all, heads_all[rank * (seg // 32):(rank + 1) * (seg // 32)])
     mine = torch.tensor([int(si.entries), int(si.multi)], dtype=torch.int64, device=tdev)
     counts = torch.zeros(2 * world, dtype=torch.int64, device=tdev)
     dist.all_gather_into_tensor(counts, mine)
-    counts = counts.cpu().numpy().reshape(world, 2)
     S = data.sequences_count
     dist.all_reduce(_as_tensor(si.d_gene_counts, 2 * S, 64, device))
-    arr = pn.shard_buffers(int(counts[:, 0].max()), int(counts[:, 1].max()))
-    seg, mseg = int(arr.seg), int(arr.mseg)
-    works = []
-    for ptr, per, wait in ((arr.d_heads, seg // 32, True), (arr.d_multi, 2 * mseg, True), (arr.d_post, seg, False)):
-        whole = _as_tensor(ptr, per * world, 32, device)
-        work = dist.all_gather_into_tensor(whole, whole[rank * per:(rank + 1) * per], async_op=not wait)   # in place: segment r is rank r's
-        if not wait:
-            works.append((work, whole))
+    counts = counts.cpu().numpy().reshape(world, 2)
+    mseg = max(int(counts[:, 1].max()), 1)
+    multi_all = _as_tensor(pn.shard_multi(mseg), 2 * mseg * world, 32, device)
+    dist.all_gather_into_tensor(multi_all, multi_all[rank * 2 * mseg:(rank + 1) * 2 * mseg])
     if not cpu:
-        torch.cuda.current_stream().synchronize()
-    bounds = pn.shard_groups(counts[:, 0], counts[:, 1])   # while the postings (4 B each, the bulk) are still travelling
-    for work, _ in works:
-        work.wait()
+        torch.cuda.current_stream().synchronize()   # the engine works on its own streams
+    bounds = pn.shard_groups(counts[:, 0], counts[:, 1])   # while the postings are still travelling
+    post_work.wait()
     if not cpu:
         torch.cuda.current_stream().synchronize()
     pn.shard_finish()

@@ -111,6 +111,7 @@ def load(path=None):
     L.pd_shard_recv.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
     L.pd_shard_sort.argtypes = [C.c_void_p, C.POINTER(ShardInfo)]
     L.pd_shard_buffers.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(ShardArrays)]
+    L.pd_shard_multi.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
     L.pd_shard_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pd_shard_finish.argtypes = [C.c_void_p]
     _lib, _lib_path = L, path
@@ -279,6 +280,11 @@ class PangeneNative:
         a = ShardArrays()
         _check(self._L.pd_shard_buffers(self._h, int(max_entries), int(max_multi), C.byref(a)))
         return a
+
+    def shard_multi(self, max_multi):
+        p = C.c_void_p()
+        _check(self._L.pd_shard_multi(self._h, int(max_multi), C.byref(p)))
+        return p.value
 
     def shard_groups(self, entries_of_rank, multi_of_rank):
         e = np.ascontiguousarray(entries_of_rank, dtype=np.uint64)
