@@ -41,7 +41,6 @@ static const uint32_t kFlag = 0x80000000u;      // counter word: "this column ha
 static const uint32_t kMulti = 0x80000000u;     // posting / forward length: multiplicity > 1 (then *_cnt is read)
 static const uint32_t kShortList = 64;          // lists up to this length are flattened
 static const uint32_t kHugeList = 2048;         // lists longer than this are walked by the whole CTA
-static const uint32_t kLongFirst = 256;         // long lists above this length are handed out before the shorter ones
 static const uint32_t kXSlots = 2048;           // side-table slots per CTA (global memory)
 static const uint32_t kXCap = kXSlots * 3 / 4;
 static const uint32_t kProbeLimit = 160;        // probes after which a row is declared too big for its table
@@ -571,25 +570,16 @@ __device__ __forceinline__ void accumulate(const ScoreArgs& a, const Tab& t_in, 
     {
         uint32_t e[kItems];
         uint32_t gs = 0, gl = 0, mj = 1, p0 = 0;
-        // The lists are handed out in two rounds over the same counter: the longer ones (> kLongFirst postings) first, the
-        // rest after them, so that the last lists in flight when the row ends are short and the warps reach the row's
-        // barrier within one round of each other instead of up to a whole 2048-posting list apart.
-        const uint32_t n_long = nl - ns;
         auto claim = [&](uint32_t& cgs, uint32_t& cgl, uint32_t& cmj) -> bool {
-            for (;;) {
-                uint32_t li = 0;
-                if (lane == 0) li = *t.over() ? 0x7FFFFFFFu : atomicAdd(ctr + 1, 1u);  // one lane polls the stop flag
-                li = __shfl_sync(0xffffffffu, li, 0);
-                if (li >= 2u * n_long) return false;
-                const uint32_t idx = li < n_long ? li : li - n_long;
-                const uint2 fw = fbuf[ns + idx];
-                const uint32_t gl = fw.y & ~kMulti;
-                if ((li < n_long) != (gl > kLongFirst)) continue;  // the other round's
-                cmj = (fw.y & kMulti) ? a.fwd_cnt[f0 + ns + idx] : 1u;
-                cgl = gl;
-                cgs = fw.x;
-                return true;
-            }
+            uint32_t li = 0;
+            if (lane == 0) li = *t.over() ? 0x7FFFFFFFu : atomicAdd(ctr + 1, 1u);  // one lane polls the stop flag
+            li = __shfl_sync(0xffffffffu, li, 0);
+            if (li >= nl - ns) return false;
+            const uint2 fw = fbuf[ns + li];
+            cmj = (fw.y & kMulti) ? a.fwd_cnt[f0 + ns + li] : 1u;
+            cgl = fw.y & ~kMulti;
+            cgs = fw.x;
+            return true;
         };
         bool have = claim(gs, gl, mj);
         if (have) {
