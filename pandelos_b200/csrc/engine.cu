@@ -1285,22 +1285,10 @@ void launch_rows(ScoreContext& c, sk::ScoreArgs a, const Level& lv, int cursor_i
     a.plimit = std::min<uint32_t>(1u << lv.hbits, sk::kProbeLimit);
     a.nslots = lv.t1 + (1u << lv.hbits);
     a.t1 = lv.t1;
-    {   // order-preserving slot functions: umulhi(c, mul) = floor(c * slots / S) < slots for every c < S.  Tier 1 uses it
-        // rotated (score_kernels.cuh, t1_slot_of): with many genomes the bank then follows the genome number
+    {   // order-preserving slot functions: umulhi(c, mul) = floor(c * slots / S) < slots for every c < S
         const uint64_t S = std::max<uint64_t>(c.ix->info.S, 1);
         a.hmul = (uint32_t)std::min<uint64_t>(((1ull << lv.hbits) << 32) / S, 0xFFFFFFFFull);
-        uint32_t rot = 0;
-        const uint32_t lg = log2_floor(lv.t1), G = c.ix->info.G;
-        if ((1u << lg) == lv.t1 && S >= lv.t1) {
-            uint32_t gbits = 0;
-            while ((1u << gbits) < G) gbits++;
-            rot = (G >= 512 && lg > gbits) ? lg - gbits : 0;
-            static const char* const e = getenv("PD_T1ROT");  // tuning
-            if (e) rot = std::min<uint32_t>((uint32_t)atoi(e), lg > 5 ? lg - 5 : 0);
-        }
-        a.t1rot = rot;
-        a.t1hi = rot ? lg - rot : 0;
-        a.t1mul = (uint32_t)std::min<uint64_t>(((uint64_t)(lv.t1 >> rot) << 32) / S, 0xFFFFFFFFull);
+        a.t1mul = (uint32_t)std::min<uint64_t>(((uint64_t)lv.t1 << 32) / S, 0xFFFFFFFFull);
     }
     a.fcap = lv.fcap;
     a.cursor = c.d_cursors.p + cursor_id;

@@ -80,9 +80,7 @@ struct ScoreArgs {
     uint32_t plimit;  // tier-2 probe limit
     uint32_t nslots;  // T1 + H
     uint32_t t1;      // tier-1 slots (a multiple of 32)
-    uint32_t t1mul;   // floor(2^32 * (T1 >> t1rot) / S): tier-1 slot of column c from the 64-bit product c * t1mul, see t1_slot_of
-    uint32_t t1rot;   // bits the order-preserving slot index is rotated by (0: not rotated)
-    uint32_t t1hi;    // log2(T1) - t1rot (with t1rot = 0: unused)
+    uint32_t t1mul;   // tier-1 slot of column c = floor(c * T1 / S) = umulhi(c, t1mul): ORDER PRESERVING on purpose, see Tab
     uint32_t fcap;    // forward entries staged per segment
     // outputs
     float* o_score;
@@ -226,23 +224,12 @@ __device__ __forceinline__ XTab xtab_of(const ScoreArgs& a, const Tab& t) {
     return x;
 }
 
-// Tier-1 slot of column c.  The order-preserving index floor(c * T1 / S) is used ROTATED right by `t1rot` bits inside its
-// log2(T1) bits (a bijection on the slots: nothing changes for collisions): slot = coarse | sub << t1hi with
-// coarse = floor(c * (T1 >> t1rot) / S) = the high word of c * t1mul, sub = the next t1rot bits of that product.  The
-// lanes of a warp hold consecutive postings of a list, for a conserved k-mer one homolog per genome: with T1 >> t1rot
-// ~ G the low bits of the slot — the bank — are the (approximate) genome number, consecutive across the lanes, instead
-// of the random low bits of c * T1 / S, so the 4-byte key loads and the counter atomics of a round spread over the banks.
-// c must be a gene (< S): the hot loop pads with the row's own gene, whose cell is dropped anyway.
-__device__ __forceinline__ uint32_t t1_slot_of(uint32_t c, uint32_t t1mul, uint32_t t1rot, uint32_t t1hi) {
-    const unsigned long long p = (unsigned long long)c * t1mul;
-#ifdef PD_EMU
-    const uint32_t sub = t1rot ? (uint32_t)p >> (32 - t1rot) : 0u;
-#else
-    const uint32_t sub = __funnelshift_l((uint32_t)p, 0u, t1rot);  // the top t1rot bits of the low word (0 for t1rot = 0)
-#endif
-    return (uint32_t)(p >> 32) | (sub << t1hi);
-}
-__device__ __forceinline__ uint32_t t1_slot(const ScoreArgs& a, uint32_t c) { return t1_slot_of(c, a.t1mul, a.t1rot, a.t1hi); }
+// Tier-1 slot of column c: the order-preserving index floor(c * T1 / S), one multiply.  c must be a gene (< S): the hot
+// loop pads with the row's own gene, whose cell is dropped anyway.  (Round 2 also tried the index rotated so that the bank
+// follows the genome number: no effect on the kernel time — shared-memory conflicts are not what bounds it — and three
+// more instructions per posting, so it is gone.)
+__device__ __forceinline__ uint32_t t1_slot_of(uint32_t c, uint32_t t1mul) { return __umulhi(c, t1mul); }
+__device__ __forceinline__ uint32_t t1_slot(const ScoreArgs& a, uint32_t c) { return t1_slot_of(c, a.t1mul); }
 __device__ __forceinline__ uint32_t t2_home(const ScoreArgs& a, uint32_t c) { return min(__umulhi(c, a.hmul), a.hmask); }
 
 __device__ __forceinline__ uint32_t x_find_or_insert(const XTab& x, uint32_t c) {
@@ -295,11 +282,11 @@ struct GenArgs {
     saddr_t keys_sa;
     RowCtl* ctl;
     uint32_t* xbase;
-    uint32_t t1, t1mul, t1rot, t1hi, hmask, hmul, plimit, nslots;
+    uint32_t t1, t1mul, hmask, hmul, plimit, nslots;
 };
 __device__ __noinline__ void add_general(const GenArgs g, uint32_t c, uint32_t n, uint32_t m) {
     // the slot of column c in either tier (claimed if new)
-    uint32_t h = t1_slot_of(c, g.t1mul, g.t1rot, g.t1hi);
+    uint32_t h = t1_slot_of(c, g.t1mul);
     {
         const saddr_t a1 = g.keys_sa + h * 4u;
         uint32_t k = lds_u32(a1);
@@ -351,8 +338,6 @@ __device__ __forceinline__ GenArgs gen_args(const ScoreArgs& a, const Tab& t) {
     g.xbase = a.xtab + (size_t)blockIdx.x * (5 * kXSlots);
     g.t1 = a.t1;
     g.t1mul = a.t1mul;
-    g.t1rot = a.t1rot;
-    g.t1hi = a.t1hi;
     g.hmask = a.hmask;
     g.hmul = a.hmul;
     g.plimit = a.plimit;
@@ -439,7 +424,7 @@ __device__ __noinline__ void queue_drain(const GenArgs g, saddr_t base, uint32_t
     __syncwarp();
     for (uint32_t j = lane; j < total; j += 32) {
         const uint32_t cur = lds_u32(base + (j - lane) * 4u);
-        const uint32_t s1 = t1_slot_of(cur, g.t1mul, g.t1rot, g.t1hi);
+        const uint32_t s1 = t1_slot_of(cur, g.t1mul);
         const saddr_t a1 = g.keys_sa + s1 * 4u;
         uint32_t k1 = lds_u32(a1);
         if (k1 == kEmpty) {
@@ -499,13 +484,22 @@ __device__ __forceinline__ void round_step(const ScoreArgs& a, const Tab& t, Lan
     if (kItems % 4 == 0 && cnt >= 32u * kItems && mj == 1) {
         // a full round of a k-mer the row holds once (nearly all rounds of the conserved lists): four postings per lane at
         // a time, no per-pair checks; a repeated posting (bit 31) is a per-lane side step
+        const bool next_full = __all_sync(0xffffffffu, nrem > 32 * (kItems - 1));  // the next round is full too: loads need no predicate
 #pragma unroll
         for (int u = 0; u < kItems; u += 4) {
             uint32_t c[4];
+            if (next_full) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                c[i] = e[u + i];
-                e[u + i] = nrem > 32 * (u + i) ? nq[32 * (u + i)] : self;
+                for (int i = 0; i < 4; i++) {
+                    c[i] = e[u + i];
+                    e[u + i] = nq[32 * (u + i)];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    c[i] = e[u + i];
+                    e[u + i] = nrem > 32 * (u + i) ? nq[32 * (u + i)] : self;
+                }
             }
             if ((c[0] | c[1] | c[2] | c[3]) & kMulti) {
 #pragma unroll
