@@ -488,8 +488,12 @@ def main():
     data_pinned = native.PangeneIData(res_host.numpy(), w.offsets, w.genome_of)
     # the job's query genes, split by posting-list volume at genome boundaries (the sharded build does it itself)
     if sharded:
-        pn0, bounds = make_index()
-        pn0.close()
+        # (three untimed builds: NCCL sets up its peer-to-peer connections and maps the exchange buffers of the other ranks
+        # lazily, per buffer address; until every address the block cache hands out has been seen — a few builds at N = 8 —
+        # a build call can stall by 10 - 100 ms.  Setup cost of the communicator, not of the step; the warm-up steps follow.)
+        for _ in range(3):
+            pn0, bounds = make_index()
+            pn0.close()
     elif world > 1:
         pn0 = native.PangeneNative(k, data, device=local)
         _, visited = pn0.gene_stats()
