@@ -70,7 +70,7 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled during the timed region (B200_PROFILING.md recipe): an `nvidia-smi -lms 100`
+    """SM clock and throttle reasons sampled during the timed region (B200_PROFILING.md recipe): an `nvidia-smi -lms 250`
     loop beside the bench (default).  PD_CLOCKS=nvml reads the same counters through NVML in this process (falls back to
     nvidia-smi when the binding is missing); PD_CLOCKS=off disables sampling."""
 
@@ -121,7 +121,7 @@ class ClockSampler:
                 self.source = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "250"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
