@@ -170,17 +170,28 @@ def build_sharded(dist, native, k, data, device=None, device_index=-1, residues_
     rank r serves genes [bounds[r], bounds[r + 1]).  The collectives of the multi-GPU path (NCCL over NVLink on GPUs;
     gloo in the CPU tests): 2 tiny all-gathers, 1 all-to-all (8 B per k-mer), 1 all-reduce (16 B per gene), 3 all-gathers
     (4 B per posting in all)."""
+    import os
+    import time
     import torch
     rank, world = dist.get_rank(), dist.get_world_size()
     cpu = device is None or getattr(device, "type", "cpu") != "cuda"
     tdev = None if cpu else device
     bulk = _bulk_group(dist)   # (made once; every rank must make it at the same point)
+    trace = os.environ.get("PD_SHARD_TRACE")   # host wall clock per stage, printed for calls slower than this many ms
+    marks = [("start", time.perf_counter())]
+
+    def mark(name):
+        if trace:
+            marks.append((name, time.perf_counter()))
+
     pn = native.PangeneNative(k, data, device=device_index, residues_device_ptr=residues_device_ptr, shard=(rank, world), **engine_kw)
+    mark("build_shard")
     # ---- k-mers to the rank that sorts them
     send_counts = torch.tensor([int(pn.shard_keys.send_counts[r]) for r in range(world)], dtype=torch.int64, device=tdev)
     all_counts = torch.zeros(world * world, dtype=torch.int64, device=tdev)
     dist.all_gather_into_tensor(all_counts, send_counts)
     all_counts = all_counts.cpu().numpy().reshape(world, world)      # [source, destination]
+    mark("counts")
     in_splits = [int(v) for v in all_counts[:, rank]]
     out_splits = [int(v) for v in all_counts[rank, :]]
     n_recv, n_send = sum(in_splits), sum(out_splits)
@@ -189,13 +200,16 @@ def build_sharded(dist, native, k, data, device=None, device_index=-1, residues_
     dist.all_to_all_single(recv, send, in_splits, out_splits)
     if not cpu:
         torch.cuda.current_stream().synchronize()   # the engine works on its own streams
+    mark("all_to_all")
     si = pn.shard_sort()
+    mark("shard_sort")
     # ---- the slices' results to every rank.  A slice has at most as many entries as it received k-mers, so the segment size
     # of the postings is known already: their all-gather (4 B per posting, the bulk) starts now and runs behind everything else
     seg_bound = int(all_counts.sum(axis=0).max())
     arr = pn.shard_buffers(seg_bound, 0)
     seg = int(arr.seg)
     post_all = _as_tensor(arr.d_post, seg * world, 32, device)
+    mark("buffers")
     post_work = dist.all_gather_into_tensor(post_all, post_all[rank * seg:(rank + 1) * seg], group=bulk, async_op=True)   # in place: segment r is rank r's
     heads_all = _as_tensor(arr.d_heads, seg // 32 * world, 32, device)
     dist.all_gather_into_tensor(heads_all, heads_all[rank * (seg // 32):(rank + 1) * (seg // 32)])
@@ -206,13 +220,21 @@ def build_sharded(dist, native, k, data, device=None, device_index=-1, residues_
     dist.all_reduce(_as_tensor(si.d_gene_counts, 2 * S, 64, device))
     counts = counts.cpu().numpy().reshape(world, 2)
     mseg = max(int(counts[:, 1].max()), 1)
+    mark("small_collectives")
     multi_all = _as_tensor(pn.shard_multi(mseg), 2 * mseg * world, 32, device)
     dist.all_gather_into_tensor(multi_all, multi_all[rank * 2 * mseg:(rank + 1) * 2 * mseg])
     if not cpu:
         torch.cuda.current_stream().synchronize()   # the engine works on its own streams
+    mark("multi")
     bounds = pn.shard_groups(counts[:, 0], counts[:, 1])   # while the postings are still travelling
+    mark("groups")
     post_work.wait()
     if not cpu:
         torch.cuda.current_stream().synchronize()
+    mark("post_wait")
     pn.shard_finish()
+    mark("finish")
+    if trace and (marks[-1][1] - marks[0][1]) * 1e3 > float(trace):
+        import sys
+        print("[shard trace] rank %d: " % rank + ", ".join("%s %.1f" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3) for i in range(1, len(marks))), file=sys.stderr, flush=True)
     return pn, bounds.astype(np.int64)
