@@ -260,8 +260,44 @@ inline void trim_all() {
     h.free_blocks.clear();
     h.cached = 0;
 }
-inline stream_t stream_create() { stream_t s; PD_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return s; }
-inline void stream_destroy(stream_t s) { cudaStreamDestroy(s); }
+// Streams and events are pooled per device and never given back to the driver: creating / destroying them goes through the
+// driver's resource manager, whose lock is shared by every process on the box — a monitoring poll (nvidia-smi, NVML) that
+// holds it for 25 ms stalls every such call of every rank for as long (measured at 8 ranks: whole build steps +25 .. +120 ms).
+// Kernel launches, async copies and stream waits do not take that lock.  A stream is idle when it is handed back (every
+// caller synchronises first).
+struct HandlePool {
+    std::mutex mu;
+    std::vector<cudaStream_t> streams[16];
+    std::vector<cudaEvent_t> events[16];
+    std::unordered_map<void*, int> home;   // handle -> the device it was made on (it goes back to that device's list)
+};
+inline HandlePool& handle_pool() {
+    static HandlePool* p = new HandlePool;   // (never destroyed: the CUDA runtime may be gone at exit)
+    return *p;
+}
+inline stream_t stream_create() {
+    const int d = current_device() & 15;
+    HandlePool& hp = handle_pool();
+    {
+        std::lock_guard<std::mutex> lk(hp.mu);
+        if (!hp.streams[d].empty()) {
+            stream_t s = hp.streams[d].back();
+            hp.streams[d].pop_back();
+            return s;
+        }
+    }
+    stream_t s;
+    PD_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    std::lock_guard<std::mutex> lk(hp.mu);
+    hp.home[reinterpret_cast<void*>(s)] = d;
+    return s;
+}
+inline void stream_destroy(stream_t s) {
+    HandlePool& hp = handle_pool();
+    std::lock_guard<std::mutex> lk(hp.mu);
+    auto it = hp.home.find(reinterpret_cast<void*>(s));
+    if (it != hp.home.end()) hp.streams[it->second].push_back(s);
+}
 inline void sync(stream_t s) { PD_CUDA(cudaStreamSynchronize(s)); }
 // non-blocking: true when everything queued on the stream has finished; throws on a failed stream
 inline bool stream_idle(stream_t s) {
@@ -275,8 +311,29 @@ inline void d2h(void* h, const void* d, size_t n, stream_t s) { if (n) PD_CUDA(c
 inline void d2d(void* dst, const void* src, size_t n, stream_t s) { if (n) PD_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s)); }
 inline void zero(void* d, size_t n, stream_t s) { if (n) PD_CUDA(cudaMemsetAsync(d, 0, n, s)); }
 inline void fill_byte(void* d, int v, size_t n, stream_t s) { if (n) PD_CUDA(cudaMemsetAsync(d, v, n, s)); }
-inline event_t event_create() { event_t e; PD_CUDA(cudaEventCreate(&e)); return e; }
-inline void event_destroy(event_t e) { cudaEventDestroy(e); }
+inline event_t event_create() {
+    const int d = current_device() & 15;
+    HandlePool& hp = handle_pool();
+    {
+        std::lock_guard<std::mutex> lk(hp.mu);
+        if (!hp.events[d].empty()) {
+            event_t e = hp.events[d].back();
+            hp.events[d].pop_back();
+            return e;
+        }
+    }
+    event_t e;
+    PD_CUDA(cudaEventCreate(&e));
+    std::lock_guard<std::mutex> lk(hp.mu);
+    hp.home[reinterpret_cast<void*>(e)] = d;
+    return e;
+}
+inline void event_destroy(event_t e) {
+    HandlePool& hp = handle_pool();
+    std::lock_guard<std::mutex> lk(hp.mu);
+    auto it = hp.home.find(reinterpret_cast<void*>(e));
+    if (it != hp.home.end()) hp.events[it->second].push_back(e);
+}
 inline void event_record(event_t e, stream_t s) { PD_CUDA(cudaEventRecord(e, s)); }
 inline float event_ms(event_t a, event_t b) { float ms = 0; PD_CUDA(cudaEventSynchronize(b)); PD_CUDA(cudaEventElapsedTime(&ms, a, b)); return ms; }
 inline void check_launch(const char* what) {
