@@ -711,7 +711,24 @@ void Index::shard_sort(pd_shard_info* out) {
     const uint32_t S = info.S;
     const int seq_bits = (int)info.seq_bits;
     const uint64_t Nr = sh.n_recv;
-    if (Nr < 2) throw Error(PD_ERR_UNSUPPORTED, "sharded build: a rank's slice of the k-mer ranks is (nearly) empty — use fewer ranks for this input");
+    if (Nr < 2) {
+        // A (nearly) empty slice — an input too small for this many ranks.  Throwing here would leave the other ranks waiting in
+        // their next collective: the slice is reported as unusable (multi = all ones) and every rank refuses together after
+        // the counts have been exchanged (multigpu.build_sharded; pd_shard_buffers refuses too).
+        sh.U_r = 0;
+        sh.M_r = 0;
+        sh.unusable = true;
+        sh.gene_counts.alloc((size_t)2 * std::max<uint32_t>(S, 1));
+        rt::stream_t st0 = rt::stream_create();
+        rt::zero(sh.gene_counts.p, sh.gene_counts.bytes(), st0);
+        rt::sync(st0);
+        rt::stream_destroy(st0);
+        out->entries = 0;
+        out->multi = ~0ull;
+        out->kmers = Nr;
+        out->d_gene_counts = reinterpret_cast<uint64_t*>(sh.gene_counts.p);
+        return;
+    }
     rt::stream_t st = rt::stream_create();
     uint64_t launches = 0;
     Timer t_all(st), t_sort(st), t_grp(st);
@@ -814,6 +831,7 @@ void Index::shard_buffers(uint64_t max_entries, uint64_t max_multi, pd_shard_arr
     if (!shard) throw Error(PD_ERR_INVALID, "not a sharded build in progress");
     rt::set_device(device);
     Shard& sh = *shard;
+    if (sh.unusable) throw Error(PD_ERR_UNSUPPORTED, "sharded build: a rank's slice of the k-mer ranks is (nearly) empty — use fewer ranks for this input");
     if (max_entries < sh.U_r || (max_multi && max_multi < sh.M_r)) throw Error(PD_ERR_INVALID, "segment smaller than this rank's slice");
     sh.seg = (max_entries + 4095) / 4096 * 4096;
     sh.mseg = max_multi;   // 0: the repeated-entry lists get their array later (shard_multi), once their sizes are known

@@ -79,7 +79,7 @@ struct Index {
         rt::DevBuf<uint32_t> heads_all, multi_all, tile_heads;
         double ms = 0, fin_ms = 0;
         uint64_t launches = 0, fin_launches = 0;
-        bool grouped = false;
+        bool grouped = false, unusable = false;
     };
     Shard* shard = nullptr;
     uint64_t* shard_recv(uint64_t n_recv);

@@ -192,6 +192,10 @@ def build_sharded(dist, native, k, data, device=None, device_index=-1, residues_
     dist.all_gather_into_tensor(all_counts, send_counts)
     all_counts = all_counts.cpu().numpy().reshape(world, world)      # [source, destination]
     mark("counts")
+    if int(all_counts.sum(axis=0).min()) < 2:   # known on every rank at the same point: all refuse together, nobody waits in a collective
+        pn.close()
+        raise native.PdError(native.PD_ERR_UNSUPPORTED, "sharded build: the input is too small for %d ranks (rank %d would get %d k-mers to sort)" % (
+            world, int(all_counts.sum(axis=0).argmin()), int(all_counts.sum(axis=0).min())))
     in_splits = [int(v) for v in all_counts[:, rank]]
     out_splits = [int(v) for v in all_counts[rank, :]]
     n_recv, n_send = sum(in_splits), sum(out_splits)

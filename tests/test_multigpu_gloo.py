@@ -142,3 +142,32 @@ def test_sharded_build_matches_the_single_process_index(tmp_path, world, low):
     res = [open(os.path.join(str(tmp_path), "result%d" % r)).read() for r in range(world)]
     assert all(r.startswith("ok") for r in res), res
     assert sum(int(r.split()[1]) for r in res) > 0
+
+
+def _tiny_worker(rank, world, port, emu_path, out_dir):
+    """An input too small for the rank count: every rank must refuse, at the same point, with an error — not hang."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(HERE))
+    from pandelos_b200 import multigpu, native, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    native.load(emu_path)
+    w = synth.from_sequences(["AAAAAA", "AAAAAA"], [0, 1])   # every k-mer is the same: one slice gets everything
+    try:
+        multigpu.build_sharded(dist, native, 3, native.PangeneIData(w.residues, w.offsets, w.genome_of))
+        res = "built"
+    except native.PdError as e:
+        res = "refused" if e.code == native.PD_ERR_UNSUPPORTED else "error %d" % e.code
+    open(os.path.join(out_dir, "tiny%d" % rank), "w").write(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_build_refuses_too_small_inputs_on_every_rank(tmp_path):
+    import build_emu
+    import torch.multiprocessing as mp
+    emu = build_emu.build()
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_tiny_worker, args=(2, port, emu, str(tmp_path)), nprocs=2, join=True)
+    assert [open(os.path.join(str(tmp_path), "tiny%d" % r)).read() for r in range(2)] == ["refused", "refused"]
