@@ -223,6 +223,10 @@ def build_sharded(dist, native, k, data, device=None, device_index=-1, residues_
     S = data.sequences_count
     dist.all_reduce(_as_tensor(si.d_gene_counts, 2 * S, 64, device))
     counts = counts.cpu().numpy().reshape(world, 2)
+    if int(counts[world - 1, 0]) < 2:   # the reference's tail merge (library.cpp:300-306) joins the LAST entry to the group before it:
+        post_work.wait()                # both must be in the last slice.  Known on every rank here: all refuse together.
+        pn.close()
+        raise native.PdError(native.PD_ERR_UNSUPPORTED, "sharded build: the last rank's slice holds fewer than two entries — use fewer ranks for this input")
     mseg = max(int(counts[:, 1].max()), 1)
     mark("small_collectives")
     multi_all = _as_tensor(pn.shard_multi(mseg), 2 * mseg * world, 32, device)
