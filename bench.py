@@ -474,6 +474,8 @@ def main():
     # residues resident in HBM before the timed region
     res_host = torch.from_numpy(w.residues).pin_memory()
     res_dev = res_host.to(dev, non_blocking=False)
+    off_dev = off_pin.to(dev)
+    gid_dev = gid_pin.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     sharded = world > 1 and strong and args.build == "sharded"
 
@@ -481,6 +483,8 @@ def main():
         """The index as this run builds it: one per rank (single GPU, replicated) or one for all ranks (sharded)."""
         d = data_pinned if host_residues else data
         ptr = None if host_residues else res_dev.data_ptr()
+        if not host_residues:   # the whole input is resident in HBM: residues and the gene table (offsets, genome ids)
+            kw = dict(kw, table_device_ptrs=(off_dev.data_ptr(), gid_dev.data_ptr()))
         if sharded:
             return multigpu.build_sharded(dist, native, k, d, device=dev, device_index=local, residues_device_ptr=ptr, **kw)
         return native.PangeneNative(k, d, device=local, residues_device_ptr=ptr, **kw), None
@@ -744,7 +748,7 @@ def main():
                 parity_ok = parity_ok and ok
 
     if rank == 0:
-        step_desc = "index build from HBM-resident residues + scoring of the rank's query rows (cells left in HBM)"
+        step_desc = "index build from the HBM-resident input (residues, gene offsets, genome ids) + scoring of the rank's query rows (cells left in HBM)"
         if gather is not None:
             step_desc += ", NCCL allgather of the best-hit slices chunk by chunk behind the scoring"
         out = {"metric": "gene-pair Jaccard scores/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,

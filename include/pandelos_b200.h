@@ -46,6 +46,8 @@ typedef struct pd_options {
     int32_t devices;         /* > 1: one replica of the index on each of that many devices (starting at `device`), genomes dealt
                                 out in posting-list-volume-balanced blocks; pd_compute_scores / pd_genome_edges go to the owner's
                                 device, calls for different devices run side by side.  0 / 1 = one device.  Host residues only. */
+    int32_t table_on_device; /* pd_build_device only: `offsets` and `genome_of` are device pointers as well */
+    int32_t reserved;
 } pd_options;
 
 typedef struct pd_index_info {
@@ -106,7 +108,8 @@ int pd_device_count(void);
  * offsets[S+1] ascending with offsets[0] == 0; genome_of[S].  Host pointers. */
 int pd_build(const uint8_t* residues, const uint64_t* offsets, const uint32_t* genome_of, uint32_t S, int32_t k,
              const pd_options* opt, pd_index** out);
-/* Same, with `residues` already in device memory (offsets / genome_of stay host pointers: O(S) metadata). */
+/* Same, with `residues` already in device memory (offsets / genome_of stay host pointers — O(S) metadata — unless
+ * pd_options.table_on_device says they are resident too). */
 int pd_build_device(const uint8_t* d_residues, const uint64_t* offsets, const uint32_t* genome_of, uint32_t S, int32_t k,
                     const pd_options* opt, pd_index** out);
 void pd_free(pd_index* ix);

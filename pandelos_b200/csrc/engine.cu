@@ -297,8 +297,10 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     opt.device = -1;
     if (o) opt = *o;
     if (k <= 0) throw Error(PD_ERR_INVALID, "K value must be greater than 0.");  // library.cpp:90-93
-    if (!offsets || (!genome_ids && S) || (!residues && S && offsets[S] != offsets[0]))
-        throw Error(PD_ERR_INVALID, "null input pointer");
+    // pd_options.table_on_device: `offsets` and `genome_ids` are device pointers too (with device residues): a host that keeps
+    // the whole input resident in HBM between builds pays no copy of the 12 S bytes of the gene table either
+    const bool tab_dev = opt.table_on_device != 0 && residues_on_device;
+    if (!offsets || (!genome_ids && S)) throw Error(PD_ERR_INVALID, "null input pointer");
     if (rt::device_count() <= 0) throw Error(PD_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU path");
     if (opt.device >= 0) rt::set_device(opt.device);
     device = rt::current_device();
@@ -306,9 +308,21 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
     sms = rt::sm_count();
     smem_optin = rt::max_optin_smem();
 
-    if (offsets[0] != 0) throw Error(PD_ERR_INVALID, "offsets[0] must be 0");
+    uint64_t off_ends[2] = {0, 0};   // offsets[0], offsets[S]
+    if (tab_dev) {
+        rt::stream_t s0 = rt::stream_create();
+        rt::d2h(&off_ends[0], offsets, sizeof(uint64_t), s0);
+        rt::d2h(&off_ends[1], offsets + S, sizeof(uint64_t), s0);
+        rt::sync(s0);
+        rt::stream_destroy(s0);
+    } else {
+        off_ends[0] = offsets[0];
+        off_ends[1] = offsets[S];
+    }
+    if (!residues && S && off_ends[1] != off_ends[0]) throw Error(PD_ERR_INVALID, "null input pointer");
+    if (off_ends[0] != 0) throw Error(PD_ERR_INVALID, "offsets[0] must be 0");
     if (S >= 0x7FFFFFFFu) throw Error(PD_ERR_UNSUPPORTED, "2^31 or more genes");
-    const uint64_t total = offsets[S];
+    const uint64_t total = off_ends[1];
     info.S = S;
     info.k = k;
     thr = 1.0f / (2.0f * (float)k);
@@ -332,15 +346,33 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         rt::h2d(d_res_own.p, residues, total, st);
         d_res = d_res_own.p;
     }
-    rt::DevBuf<uint64_t> d_gene_off((size_t)S + 1);
-    rt::DevBuf<uint32_t> d_gid(std::max<size_t>(S, 1)), d_kseq((size_t)S + 1), d_key_off((size_t)S + 1), d_flags(4), d_total(4);
+    struct TableRef {   // the gene table on the device: a copy made here, or the caller's own arrays
+        rt::DevBuf<uint64_t> off_own;
+        rt::DevBuf<uint32_t> gid_own;
+        const uint64_t* off = nullptr;
+        const uint32_t* gid = nullptr;
+    } tab;
+    struct { const uint64_t* p; } d_gene_off;
+    struct { const uint32_t* p; } d_gid;
+    if (tab_dev) {
+        d_gene_off.p = offsets;
+        d_gid.p = genome_ids;
+    } else {
+        tab.off_own.alloc((size_t)S + 1);
+        tab.gid_own.alloc(std::max<size_t>(S, 1));
+        d_gene_off.p = tab.off_own.p;
+        d_gid.p = tab.gid_own.p;
+    }
+    rt::DevBuf<uint32_t> d_kseq((size_t)S + 1), d_key_off((size_t)S + 1), d_flags(4), d_total(4);
     rt::DevBuf<unsigned long long> d_n64(2);
     rt::zero(d_n64.p, 2 * sizeof(unsigned long long), st);
-    rt::h2d(d_gene_off.p, offsets, sizeof(uint64_t) * ((size_t)S + 1), st);
-    rt::h2d(d_gid.p, genome_ids, sizeof(uint32_t) * S, st);
+    if (!tab_dev) {
+        rt::h2d(tab.off_own.p, offsets, sizeof(uint64_t) * ((size_t)S + 1), st);
+        rt::h2d(tab.gid_own.p, genome_ids, sizeof(uint32_t) * S, st);
+    }
     rt::zero(d_flags.p, 4 * sizeof(uint32_t), st);
     meta.alloc(std::max<size_t>(S, 1));
-    PD_LAUNCH(ik::gene_meta_kernel, blocks_for((uint64_t)S + 1), 256, 0, st, (const uint64_t*)d_gene_off.p, (const uint32_t*)d_gid.p, S, (int)k,
+    PD_LAUNCH(ik::gene_meta_kernel, blocks_for((uint64_t)S + 1), 256, 0, st, d_gene_off.p, d_gid.p, S, (int)k,
               d_kseq.p, meta.p, d_flags.p, d_n64.p);
     launches++;
     rt::DevBuf<uint32_t> scratch(prims::scan_tmp_words((uint64_t)S + 1) + 16);
@@ -440,17 +472,18 @@ void Index::build(const uint8_t* residues, bool residues_on_device, const uint64
         }
         // ---- this rank's SHARE of the genes (about 1 / world of the residues): its k-mers are made once, grouped by
         // destination slice in one stable pass, and handed to the caller for the all-to-all
-        uint32_t ga, gb;
+        uint32_t h_pos[2] = {0, 0};
         {
             const uint64_t t0 = total / shard_world * shard_rank + (total % shard_world) * shard_rank / shard_world;
             const uint64_t t1 = shard_rank + 1 == shard_world ? total : total / shard_world * (shard_rank + 1) + (total % shard_world) * (shard_rank + 1) / shard_world;
-            ga = shard_rank == 0 ? 0u : (uint32_t)(std::lower_bound(offsets, offsets + S, t0) - offsets);
-            gb = shard_rank + 1 == shard_world ? S : (uint32_t)(std::lower_bound(offsets, offsets + S, t1) - offsets);
+            // first genes at or after residues t0 / t1 (lower bound over the offsets), and the key positions they start at
+            rt::DevBuf<uint32_t> d_pos(4);
+            PD_LAUNCH(ik::share_bounds_kernel, 1, 32, 0, st, d_gene_off.p, (const uint32_t*)d_key_off.p, S, shard_rank == 0 ? 0ull : t0,
+                      shard_rank + 1 == shard_world ? ~0ull : t1, d_pos.p);
+            launches++;
+            rt::d2h(h_pos, d_pos.p, sizeof(h_pos), st);
+            rt::sync(st);
         }
-        uint32_t h_pos[2] = {0, 0};
-        rt::d2h(&h_pos[0], d_key_off.p + ga, sizeof(uint32_t), st);
-        rt::d2h(&h_pos[1], d_key_off.p + gb, sizeof(uint32_t), st);
-        rt::sync(st);
         const uint64_t pos_lo = h_pos[0], pos_hi = h_pos[1], n_share = pos_hi - pos_lo;
         t_enc.start();
         const uint32_t stiles = sortk::tiles_of(N);

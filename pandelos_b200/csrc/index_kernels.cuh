@@ -75,6 +75,22 @@ __global__ void __launch_bounds__(256) gene_meta_kernel(const uint64_t* __restri
     }
 }
 
+// ---- sharded build: key positions [pos[0], pos[1]) of the genes whose residues start in [t0, t1) (t1 = all ones: to the end)
+__global__ void share_bounds_kernel(const uint64_t* __restrict__ off, const uint32_t* __restrict__ key_off, uint32_t S, uint64_t t0, uint64_t t1,
+                                    uint32_t* __restrict__ pos) {
+    if (blockIdx.x != 0 || threadIdx.x > 1) return;
+    const uint64_t t = threadIdx.x == 0 ? t0 : t1;
+    uint32_t lo = 0, hi = S;   // first gene g in [0, S] with off[g] >= t (S when none)
+    if (t == ~0ull) lo = S;
+    else
+        while (lo < hi) {
+            const uint32_t m = lo + (hi - lo) / 2;
+            if (off[m] < t) lo = m + 1;
+            else hi = m;
+        }
+    pos[threadIdx.x] = key_off[lo];
+}
+
 // ---- alphabet histogram: 16-B loads, per-warp privatised shared histograms
 __global__ void __launch_bounds__(256) byte_hist_kernel(const uint8_t* __restrict__ res, uint64_t n,
                                                          unsigned long long* __restrict__ hist) {

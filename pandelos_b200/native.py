@@ -27,7 +27,8 @@ class PdError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("verbose", C.c_int32), ("contexts", C.c_int32), ("hash_log2", C.c_int32),
-                ("cell_capacity", C.c_uint64), ("keep_sorted", C.c_int32), ("devices", C.c_int32)]
+                ("cell_capacity", C.c_uint64), ("keep_sorted", C.c_int32), ("devices", C.c_int32),
+                ("table_on_device", C.c_int32), ("reserved", C.c_int32)]
 
 
 class IndexInfo(C.Structure):
@@ -177,7 +178,7 @@ class PangeneNative:
     """Device-resident index + scoring calls: `new PangeneNative(k, pid)` / `generateScoresPart(g)`."""
 
     def __init__(self, k, data, device=-1, verbose=False, contexts=0, hash_log2=0, cell_capacity=0, keep_sorted=False,
-                 residues_device_ptr=None, shard=None, devices=0):
+                 residues_device_ptr=None, shard=None, devices=0, table_device_ptrs=None):
         """shard = (rank, world): this process builds slice `rank` of an index that `world` processes build together
         (pd_build_shard); the caller exchanges the slices and calls shard_buffers / shard_finish
         (pandelos_b200.multigpu.build_sharded does all of it over torch.distributed)."""
@@ -185,7 +186,13 @@ class PangeneNative:
         self._L = L
         self._data = data
         self.k = int(k)
-        opt = Options(int(device), int(verbose), int(contexts), int(hash_log2), int(cell_capacity), int(keep_sorted), int(devices))
+        opt = Options(int(device), int(verbose), int(contexts), int(hash_log2), int(cell_capacity), int(keep_sorted), int(devices),
+                      1 if (table_device_ptrs is not None and residues_device_ptr is not None) else 0, 0)
+        # the gene table: host arrays, or (table_device_ptrs = (offsets, genome ids), with device residues) resident in HBM too
+        if opt.table_on_device:
+            off_arg, gid_arg = C.c_void_p(int(table_device_ptrs[0])), C.c_void_p(int(table_device_ptrs[1]))
+        else:
+            off_arg, gid_arg = data.offsets.ctypes.data, data.sequenceGenome.ctypes.data
         h = C.c_void_p()
         S = data.sequences_count
         self.shard_keys = None
@@ -194,11 +201,10 @@ class PangeneNative:
             self.shard_keys = ShardKeys()
             on_dev = residues_device_ptr is not None
             rc = L.pd_build_shard(C.c_void_p(int(residues_device_ptr)) if on_dev else data.residues.ctypes.data, int(on_dev),
-                                  data.offsets.ctypes.data, data.sequenceGenome.ctypes.data, S, self.k, C.byref(opt), int(rank), int(world),
+                                  off_arg, gid_arg, S, self.k, C.byref(opt), int(rank), int(world),
                                   C.byref(h), C.byref(self.shard_keys))
         elif residues_device_ptr is not None:
-            rc = L.pd_build_device(C.c_void_p(int(residues_device_ptr)), data.offsets.ctypes.data, data.sequenceGenome.ctypes.data, S,
-                                   self.k, C.byref(opt), C.byref(h))
+            rc = L.pd_build_device(C.c_void_p(int(residues_device_ptr)), off_arg, gid_arg, S, self.k, C.byref(opt), C.byref(h))
         else:
             rc = L.pd_build(data.residues.ctypes.data, data.offsets.ctypes.data, data.sequenceGenome.ctypes.data, S, self.k,
                             C.byref(opt), C.byref(h))

@@ -98,7 +98,11 @@ def _shard_worker(rank, world, port, emu_path, out_dir, low_complexity):
     w = synth.generate(6, 25, 60.0, 0.1, 93, low_complexity=low_complexity)
     k = 3
     data = native.PangeneIData(w.residues, w.offsets, w.genome_of)
-    pn, bounds = multigpu.build_sharded(dist, native, k, data)
+    if low_complexity > 0:   # the input "resident on the device" (host memory under the emulator): residues and the gene table by pointer
+        pn, bounds = multigpu.build_sharded(dist, native, k, data, residues_device_ptr=data.residues.ctypes.data,
+                                            table_device_ptrs=(data.offsets.ctypes.data, data.sequenceGenome.ctypes.data))
+    else:
+        pn, bounds = multigpu.build_sharded(dist, native, k, data)
     one = native.PangeneNative(k, data)
     ok = pn.info.U == one.info.U and pn.info.lookups == one.info.lookups and pn.info.groups == one.info.groups and pn.info.N == one.info.N
     gb = multigpu.genome_bounds(w.genome_of, one.info.G)
