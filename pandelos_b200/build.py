@@ -117,7 +117,8 @@ def build_host(force=False):
         _run([CXX, "-std=c++17", "-O2", "-Wall", "-I", hdir, "-o", CALCK_BIN, src])
     src = os.path.join(hdir, "netclu_cc_main.cpp")
     if force or _stale(NETCLU_BIN, [src] + headers):
-        _run([CXX, "-std=c++17", "-O2", "-Wall", "-I", hdir, "-o", NETCLU_BIN, src])
+        # -ffp-contract=off: girvan_newman.h repeats networkx' float sums operation by operation
+        _run([CXX, "-std=c++17", "-O2", "-Wall", "-ffp-contract=off", "-pthread", "-I", hdir, "-o", NETCLU_BIN, src])
     return CLI_BIN
 
 

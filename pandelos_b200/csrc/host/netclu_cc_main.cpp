@@ -1,6 +1,6 @@
 // netclu_cc: the connected-component half of the reference's netclu_ng.py, natively.
 //
-//   netclu_cc <in.faa> <in.net> [-r rest.net]
+//   netclu_cc <in.faa> <in.net> [-r rest.net | -g]
 //
 // netclu_ng.py:64-72,149-172 takes the connected components of the .net graph; a component in which no two genes of one
 // genome lack an edge (get_max_collision == 0, netclu_ng.py:79-96) IS a family and is printed as it stands; only the
@@ -14,6 +14,13 @@
 // is what it was in the full file, so networkx' tie-breaking is unchanged).  Of that run keep the `F{ ` lines that do
 // not end in " }" (its own remaining-singleton lines, which this tool already printed or which belong to families
 // printed here).  INTEGRATION.md shows the pipeline; tests/test_netclu_cc.py checks it against netclu_ng.py's stdout.
+// (A component split alone can fall differently from the same component split inside the full network: networkx orders
+// the nodes of a subgraph view one way when the component is less than half of the graph and another way otherwise, and
+// that order breaks ties between edges of equal betweenness.  The -r pipeline is exact up to such ties; -g is exact.)
+//
+// With -g the split is done here as well (girvan_newman.h: networkx' Girvan-Newman restated with its iteration orders
+// and float arithmetic, so that ties fall as they do in the script run on the FULL network), the families it makes are
+// printed as `F{ ` lines too, and the exit status is 0: no Python, no networkx, one pass.
 //
 // Readers follow the script: header = every even line of the .faa, `strip().split('\t')` -> genome, name
 // (netclu_ng.py:17-30); .net line -> int, int, weight; a line with src == dst only adds the node (:43-56).
@@ -31,6 +38,7 @@
 #include <vector>
 
 #include "faa.h"
+#include "girvan_newman.h"
 
 namespace {
 
@@ -82,15 +90,17 @@ int fail(const char* what, const std::string& arg) {
 
 int main(int argc, char** argv) {
     std::string faa_path, net_path, rest_path;
+    bool native_split = false;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         if (a == "-r" && i + 1 < argc) rest_path = argv[++i];
+        else if (a == "-g") native_split = true;
         else if (faa_path.empty()) faa_path = a;
         else if (net_path.empty()) net_path = a;
         else return fail("unexpected argument ", a);
     }
     if (net_path.empty()) {
-        fprintf(stderr, "usage: netclu_cc <in.faa> <in.net> [-r rest.net]\n");
+        fprintf(stderr, "usage: netclu_cc <in.faa> <in.net> [-r rest.net | -g]\n");
         return 1;
     }
 
@@ -142,10 +152,14 @@ int main(int argc, char** argv) {
     std::vector<uint8_t> in_net(S, 0);
     std::vector<uint64_t> edges;  // (min << 32 | max) of every edge line, sorted: has_edge by binary search
     edges.reserve(lines.size());
+    std::vector<uint32_t> node_pos(S, UINT32_MAX);  // position in pnet's node order (first appearance, netclu_ng.py:47-52)
+    uint32_t n_nodes = 0;
     for (const Line& l : lines) {
         in_net[l.a] = 1;
+        if (node_pos[l.a] == UINT32_MAX) node_pos[l.a] = n_nodes++;
         if (l.a == l.b) continue;
         in_net[l.b] = 1;
+        if (node_pos[l.b] == UINT32_MAX) node_pos[l.b] = n_nodes++;
         dsu.unite(l.a, l.b);
         edges.push_back(static_cast<uint64_t>(std::min(l.a, l.b)) << 32 | std::max(l.a, l.b));
     }
@@ -169,36 +183,74 @@ int main(int argc, char** argv) {
     std::string out;
     size_t n_comp = 0, n_split = 0;
     std::vector<std::pair<uint32_t, uint32_t>> by_genome;
+    auto has_collision = [&](const uint32_t* first, const uint32_t* last) {
+        by_genome.clear();
+        for (const uint32_t* m = first; m != last; m++) by_genome.emplace_back(genome[*m], *m);
+        std::sort(by_genome.begin(), by_genome.end());
+        for (size_t i = 0; i < by_genome.size();) {
+            size_t j = i;
+            while (j < by_genome.size() && by_genome[j].first == by_genome[i].first) j++;
+            for (size_t x = i; x < j; x++)
+                for (size_t y = x + 1; y < j; y++)
+                    if (!has_edge(by_genome[x].second, by_genome[y].second)) return true;
+            i = j;
+        }
+        return false;
+    };
+    auto print_family = [&](const uint32_t* first, const uint32_t* last) {  // netclu_ng.py:119-126
+        out += "F{ ";
+        for (const uint32_t* m = first; m != last; m++) {
+            if (m != first) out += " ; ";
+            out.append(names[*m]);
+        }
+        out += "}\n";
+    };
     for (uint32_t root = 0; root < S; root++) {
         const uint32_t lo = comp_start[root], hi = comp_start[root + 1];
         if (lo == hi) continue;
         n_comp++;
-        by_genome.clear();
-        for (uint32_t i = lo; i < hi; i++) by_genome.emplace_back(genome[members[i]], members[i]);
-        std::sort(by_genome.begin(), by_genome.end());
-        bool collision = false;
-        for (size_t i = 0; i < by_genome.size() && !collision;) {
-            size_t j = i;
-            while (j < by_genome.size() && by_genome[j].first == by_genome[i].first) j++;
-            for (size_t x = i; x < j && !collision; x++)
-                for (size_t y = x + 1; y < j; y++)
-                    if (!has_edge(by_genome[x].second, by_genome[y].second)) {
-                        collision = true;
-                        break;
-                    }
-            i = j;
-        }
+        const bool collision = has_collision(members.data() + lo, members.data() + hi);
         if (collision) {
             split[root] = 1;
             n_split++;
             continue;
         }
-        out += "F{ ";
-        for (uint32_t i = lo; i < hi; i++) {
-            if (i > lo) out += " ; ";
-            out.append(names[members[i]]);
+        print_family(members.data() + lo, members.data() + hi);
+    }
+
+    // --- -g: the Girvan-Newman split of the others (split_until_max_k, netclu_ng.py:101-117)
+    size_t n_split_families = 0, n_removed = 0;
+    if (native_split && n_split) {
+        pd_host::RootGraph rg;
+        rg.n_nodes = n_nodes;
+        rg.pos = node_pos;
+        rg.dense.assign(S, UINT32_MAX);
+        std::vector<uint32_t> sources;  // per split component, its first node in pnet's order
+        for (uint32_t root = 0; root < S; root++) {
+            if (!split[root]) continue;
+            uint32_t src = members[comp_start[root]];
+            for (uint32_t i = comp_start[root]; i < comp_start[root + 1]; i++) {
+                rg.dense[members[i]] = static_cast<uint32_t>(rg.adj.size());
+                rg.adj.emplace_back();
+                if (node_pos[members[i]] < node_pos[src]) src = members[i];
+            }
+            sources.push_back(src);
         }
-        out += "}\n";
+        std::unordered_map<uint64_t, char> seen_edge;
+        for (const Line& l : lines) {  // add_edge keeps the place of a neighbour it has seen before (:55-56)
+            if (l.a == l.b || !split[dsu.find(l.a)]) continue;
+            if (!seen_edge.emplace(static_cast<uint64_t>(std::min(l.a, l.b)) << 32 | std::max(l.a, l.b), 1).second) continue;
+            rg.adj[rg.dense[l.a]].push_back(l.b);
+            rg.adj[rg.dense[l.b]].push_back(l.a);
+        }
+        pd_host::GirvanNewman gn(rg, [&](const std::vector<uint32_t>& com) { return has_collision(com.data(), com.data() + com.size()); });
+        std::vector<std::vector<uint32_t>> families;
+        // connected_components(pnet) yields the components in the order of their first node (netclu_ng.py:149)
+        std::sort(sources.begin(), sources.end(), [&](uint32_t a, uint32_t b) { return node_pos[a] < node_pos[b]; });
+        for (uint32_t src : sources) gn.split(src, &families);
+        for (const auto& f : families) print_family(f.data(), f.data() + f.size());
+        n_split_families = families.size();
+        n_removed = gn.removed_edges;
     }
     size_t n_single = 0;
     for (uint32_t s = 0; s < S; s++)
@@ -224,5 +276,9 @@ int main(int argc, char** argv) {
     fprintf(stderr, "netclu_cc: %u sequences, %zu genomes, %zu network lines, %zu components: %zu families as they stand, "
                     "%zu left for the split%s, %zu singletons\n",
             S, genome_ids.size(), lines.size(), n_comp, n_comp - n_split, n_split, rest_path.empty() ? "" : " (written to -r)", n_single);
+    if (native_split) {
+        fprintf(stderr, "netclu_cc: -g split them into %zu families, removing %zu edges\n", n_split_families, n_removed);
+        return 0;
+    }
     return n_split ? 3 : 0;
 }

@@ -3,10 +3,15 @@ netclu_ng.py prints for a few (.faa, .net) inputs, digested per connected compon
 connected-component tool (pandelos_b200/csrc/host/netclu_cc_main.cpp).
 
   <case>.faa / <case>.net   inputs (family5 is the Pangenes golden of make_net_golden.py; the others are seeded random
-                            networks over header-only .faa files — netclu_ng.py reads the header lines only)
+                            networks over header-only .faa files — netclu_ng.py reads the header lines only; the
+                            ties* cases are rings, grids, ladders, barbells ...: many edges of EQUAL betweenness, so
+                            the split depends on networkx' iteration orders)
   <case>.json               {"kept": [F-lines of the components printed as they stand], "split": [[ids] of every component
                             that went through girvan_newman], "split_families": [F-lines the split produced],
-                            "singletons": [F-lines of genes outside the network]}
+                            "singletons": [F-lines of genes outside the network],
+                            "gn": [the script's own `gn (..)` lines, one per split, in its order],
+                            "rest_pipeline_differs": true when splitting the components ALONE (netclu_cc -r, then the
+                            script on rest.net) gives other families than the script on the full network}
 
     python tests/golden/make_netclu_golden.py
 """
@@ -44,7 +49,92 @@ def digest(stdout):
         if ln.startswith("F{ ") and ln.endswith(" }"):
             singletons.append(ln)
         i += 1
-    return {"kept": sorted(kept), "split": sorted(split), "split_families": sorted(split_families), "singletons": sorted(singletons)}
+    return {"kept": sorted(kept), "split": sorted(split), "split_families": sorted(split_families), "singletons": sorted(singletons),
+            "gn": [ln for ln in lines if ln.startswith("gn (")]}
+
+
+def tie_case(name, seed):
+    """Components with many edges of equal betweenness, ids shuffled over a gene range of varying size (so that a
+    component is sometimes more, sometimes less than half of the network: the two node orders of a networkx view)."""
+    rng = random.Random(seed)
+    S = rng.choice([40, 120, 400, 3000])
+    G = rng.choice([2, 3, 5, 8])
+    genome = [rng.randrange(G) for _ in range(S)]
+    ids = list(range(S))
+    rng.shuffle(ids)
+    edges = []
+    used = 0
+    for _ in range(rng.choice([1, 1, 2, 5, 20])):
+        size = rng.choice([4, 6, 9, 12, 16, 25, 40]) if S >= 120 else rng.choice([4, 6, 9, 12])
+        if used + size > S:
+            break
+        nodes = ids[used:used + size]
+        used += size
+        kind = rng.choice(["ring", "grid", "barbell", "sparse", "dense", "path", "star2", "ladder"])
+        e = []
+        h = size // 2
+        if kind == "ring":
+            e = [(nodes[i], nodes[(i + 1) % size]) for i in range(size)]
+        elif kind == "path":
+            e = [(nodes[i], nodes[i + 1]) for i in range(size - 1)]
+        elif kind == "grid":
+            w = max(2, int(size ** 0.5))
+            for i in range(size):
+                if (i + 1) % w and i + 1 < size:
+                    e.append((nodes[i], nodes[i + 1]))
+                if i + w < size:
+                    e.append((nodes[i], nodes[i + w]))
+        elif kind == "barbell":
+            for part in (nodes[:h], nodes[h:]):
+                e += [(part[x], part[y]) for x in range(len(part)) for y in range(x + 1, len(part))]
+            e.append((nodes[0], nodes[h]))
+            if rng.random() < 0.5:
+                e.append((nodes[1], nodes[h + 1]))
+        elif kind == "ladder":
+            for i in range(h - 1):
+                e += [(nodes[i], nodes[i + 1]), (nodes[h + i], nodes[h + i + 1])]
+            e += [(nodes[i], nodes[h + i]) for i in range(h)]
+        elif kind == "star2":
+            e += [(nodes[0], nodes[i]) for i in range(1, h)]
+            e += [(nodes[h], nodes[i]) for i in range(h + 1, size)]
+            e.append((nodes[0], nodes[h]))
+        else:
+            p = 0.15 if kind == "sparse" else 0.6
+            e += [(nodes[i], nodes[rng.randrange(i)]) for i in range(1, size)]
+            e += [(nodes[x], nodes[y]) for x in range(size) for y in range(x + 1, size) if rng.random() < p]
+        edges += e
+    rng.shuffle(edges)
+    with open(os.path.join(OUT, name + ".faa"), "w") as f:
+        for s in range(S):
+            f.write("G%d\tn%d\tdesc\nA\n" % (genome[s], s))
+    with open(os.path.join(OUT, name + ".net"), "w") as f:
+        for a, b in edges:
+            if rng.random() < 0.5:
+                a, b = b, a
+            f.write("%d\t%d\t%r\n" % (a, b, round(rng.random(), 3)))
+            if rng.random() < 0.1:
+                f.write("%d\t%d\t0.5\n" % (b, a))
+            if rng.random() < 0.03:
+                f.write("%d\t%d\t1.0\n" % (a, a))
+
+
+def clus(f_lines):
+    return sorted(set(ln.replace("F{ ", "").replace("}", "").replace(" ;", "").strip() for ln in f_lines))
+
+
+def rest_pipeline_differs(name, d):
+    """netclu_cc -r + the script on rest.net, against the script on the full network (digest d)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from pandelos_b200 import build
+    build.build_host()
+    faa, net, rest = (os.path.join(OUT, name + e) for e in (".faa", ".net", ".rest.tmp"))
+    r = subprocess.run([build.NETCLU_BIN, faa, net, "-r", rest], capture_output=True, text=True)
+    lines = r.stdout.splitlines()
+    if r.returncode == 3:
+        s = subprocess.run([sys.executable, SCRIPT, faa, rest], capture_output=True, text=True, check=True)
+        lines += [ln for ln in s.stdout.splitlines() if ln.startswith("F{ ") and not ln.endswith(" }")]
+    os.remove(rest)
+    return clus(lines) != clus(d["kept"] + d["split_families"] + d["singletons"])
 
 
 def random_case(name, genomes, genes, seed):
@@ -95,13 +185,18 @@ def main():
     random_case("random6x30", 6, 30, 11)
     random_case("random12x25", 12, 25, 12)
     random_case("random3x80", 3, 80, 13)
-    for name in ("family5", "random6x30", "random12x25", "random3x80"):
+    ties = {"ties3": 3, "ties21": 21, "ties40": 40, "ties77": 77, "ties105": 105, "ties118": 118}
+    for name, seed in ties.items():
+        tie_case(name, seed)
+    for name in ["family5", "random6x30", "random12x25", "random3x80"] + list(ties):
         r = subprocess.run([sys.executable, SCRIPT, os.path.join(OUT, name + ".faa"), os.path.join(OUT, name + ".net")],
                            capture_output=True, text=True, check=True)
         d = digest(r.stdout)
+        if rest_pipeline_differs(name, d):
+            d["rest_pipeline_differs"] = True
         with open(os.path.join(OUT, name + ".json"), "w") as f:
             json.dump(d, f, indent=0)
-        print(name, dict((k, len(v)) for k, v in d.items()))
+        print(name, dict((k, len(v) if isinstance(v, list) else v) for k, v in d.items()))
 
 
 if __name__ == "__main__":

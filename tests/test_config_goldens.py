@@ -86,14 +86,19 @@ def test_restatement_reproduces_the_reference_goldens_at_config_size():
         o.close()
     text = "".join(ln + "\n" for ln in net.lines())
     assert hashlib.sha256(text.encode()).hexdigest() == gold["net"]["sha256"]
-    if not os.path.exists(SCRIPT):
-        return
+    from pandelos_b200 import build
+    build.build_host()
     with tempfile.TemporaryDirectory() as td:
         faa, netf = os.path.join(td, "in.faa"), os.path.join(td, "in.net")
         w.write_faa(faa)
         with open(netf, "w") as f:
             f.write(text)
-        r = subprocess.run([sys.executable, SCRIPT, faa, netf], capture_output=True, text=True, check=True)
-    fams = sorted(set(ln.replace("F{ ", "").replace("}", "").replace(" ;", "") for ln in r.stdout.splitlines() if "F{ " in ln))
-    ctext = "".join(f + "\n" for f in fams)
-    assert len(fams) == gold["clus"]["lines"] and hashlib.sha256(ctext.encode()).hexdigest() == gold["clus"]["sha256"]
+        # the native netclu (connected components + Girvan-Newman, netclu_cc -g) gives the golden `.clus` everywhere;
+        # the reference's own script re-derives that golden where the reference tree is present
+        runs = [subprocess.run([build.NETCLU_BIN, faa, netf, "-g"], capture_output=True, text=True, check=True)]
+        if os.path.exists(SCRIPT):
+            runs.append(subprocess.run([sys.executable, SCRIPT, faa, netf], capture_output=True, text=True, check=True))
+    for r in runs:
+        fams = sorted(set(ln.replace("F{ ", "").replace("}", "").replace(" ;", "") for ln in r.stdout.splitlines() if "F{ " in ln))
+        ctext = "".join(f + "\n" for f in fams)
+        assert len(fams) == gold["clus"]["lines"] and hashlib.sha256(ctext.encode()).hexdigest() == gold["clus"]["sha256"]

@@ -104,8 +104,15 @@ def test_config_full_size_against_the_unmodified_reference(name, tmp_path):
     assert len(fam_lines) > 0
     if "lines" in gold["clus"]:   # mycoplasma64: the script's Girvan-Newman split does not end in reasonable time (golden says so)
         assert len(fam_lines) <= gold["clus"]["lines"]
-    # .clus itself: golden of the unmodified netclu_ng.py on the identical .net (sha256 in the golden; the script and
-    # /root/reference do not exist on the GPU box — tests/test_config_goldens.py re-derives it in the build container)
+    # .clus itself (pandelos.sh:78-79): the native netclu with its own Girvan-Newman split (netclu_cc -g) against the
+    # golden of the unmodified netclu_ng.py on the identical .net — .faa in, families out, nothing of the reference run
+    if "sha256" in gold["clus"]:
+        r = subprocess.run([build.NETCLU_BIN, faa, out, "-g"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        fams = sorted(set(ln.replace("F{ ", "").replace("}", "").replace(" ;", "") for ln in r.stdout.splitlines() if "F{ " in ln))
+        ctext = "".join(f + "\n" for f in fams)
+        assert len(fams) == gold["clus"]["lines"]
+        assert hashlib.sha256(ctext.encode()).hexdigest() == gold["clus"]["sha256"], ".clus differs from netclu_ng.py's"
 
 
 def _first80():

@@ -1,10 +1,13 @@
-"""netclu_cc (native connected-component half of the reference's netclu_ng.py) against digests of
-the unmodified script's stdout (tests/golden/make_netclu_golden.py): the families it prints as they stand, the
-components it leaves for the Girvan-Newman split, the singletons; and — where the script is present — the whole
-two-step pipeline of INTEGRATION.md against the script run once on the full network.  CPU only."""
+"""netclu_cc (the reference's netclu_ng.py natively) against digests of the unmodified script's
+stdout (tests/golden/make_netclu_golden.py): the families it prints as they stand, the components it leaves for the
+Girvan-Newman split, the singletons; with -g the split itself — the families AND the script's own sequence of `gn (..)`
+lines, on inputs full of edges of equal betweenness, single- and multi-threaded; the CPython set emulation the split
+rests on against the running interpreter; and — where the script is present — fresh random networks and the two-step
+pipeline of INTEGRATION.md against the script run once on the full network.  CPU only."""
 import glob
 import json
 import os
+import random
 import subprocess
 import sys
 
@@ -66,9 +69,86 @@ def test_two_step_pipeline_gives_the_scripts_clus(netclu, name, tmp_path):
     if r.returncode == 3:
         s = subprocess.run([sys.executable, SCRIPT, os.path.join(GOLD, name + ".faa"), rest], capture_output=True, text=True, check=True)
         split_lines = [ln for ln in s.stdout.splitlines() if ln.startswith("F{ ") and not ln.endswith(" }")]
-        assert sorted(split_lines) == want["split_families"]
+        assert (sorted(split_lines) == want["split_families"]) != bool(want.get("rest_pipeline_differs"))
         lines += split_lines
-    assert clus(lines) == clus(want["kept"] + want["split_families"] + want["singletons"])
+    same = clus(lines) == clus(want["kept"] + want["split_families"] + want["singletons"])
+    # a component split alone can fall differently (node order of a networkx view depends on the share of the graph the
+    # component is; ties between edges follow it): the golden records where it does — netclu_cc -g has no such cases
+    assert same != bool(want.get("rest_pipeline_differs"))
+
+
+def run_native_split(binary, name, env=None):
+    e = dict(os.environ, PD_NETCLU_TRACE="1")
+    e.update(env or {})
+    r = subprocess.run([binary, os.path.join(GOLD, name + ".faa"), os.path.join(GOLD, name + ".net"), "-g"],
+                       capture_output=True, text=True, timeout=300, env=e)
+    assert r.returncode == 0, r.stderr
+    return r.stdout.splitlines(), [ln for ln in r.stderr.splitlines() if ln.startswith("gn (")]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_native_split_makes_the_scripts_families_split_by_split(netclu, name):
+    want = json.load(open(os.path.join(GOLD, name + ".json")))
+    out, gn = run_native_split(netclu, name)
+    assert all(ln.startswith("F{ ") for ln in out)
+    assert sorted(ln for ln in out if ln.endswith(" }")) == want["singletons"]
+    assert sorted(ln for ln in out if not ln.endswith(" }")) == sorted(want["kept"] + want["split_families"])
+    assert gn == want["gn"]          # every split of the script, in its order, with both halves
+
+
+@pytest.mark.parametrize("threads", ["1", "3", "8"])
+def test_native_split_does_not_depend_on_the_thread_count(netclu, threads):
+    # PD_NETCLU_PAR_MIN=0 sends even small components through the blocked (multi-threaded) betweenness sums
+    for name in ("ties40", "random3x80", "ties118"):
+        want = json.load(open(os.path.join(GOLD, name + ".json")))
+        out, gn = run_native_split(netclu, name, {"PD_NETCLU_THREADS": threads, "PD_NETCLU_PAR_MIN": "0"})
+        assert gn == want["gn"]
+        assert sorted(ln for ln in out if not ln.endswith(" }")) == sorted(want["kept"] + want["split_families"])
+
+
+def test_some_cases_need_the_exact_tie_breaking():
+    assert sum(1 for n in CASES if json.load(open(os.path.join(GOLD, n + ".json"))).get("rest_pipeline_differs")) >= 2
+
+
+def test_int_set_iteration_order_is_cpythons(tmp_path):
+    """PyIntSet (girvan_newman.h) against the `set` of the interpreter running the test: small and large ints, runs,
+    multiples of the table size (collision chains), sizes across several resizes including the > 50000 growth rule."""
+    exe = str(tmp_path / "pyset")
+    host = os.path.join(os.path.dirname(build.NETCLU_BIN), "csrc", "host")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-pthread", "-I", host, "-o", exe,
+                    os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "pyset_main.cpp")], check=True)
+    rng = random.Random(5)
+    cases = [[], [0], list(range(40)), list(range(39, -1, -1)), [8 * i for i in range(100)], [1024 * i + 3 for i in range(300)],
+             [rng.randrange(1 << 22) for _ in range(5000)], [rng.randrange(200) for _ in range(1000)],
+             [rng.randrange(1 << 31) for _ in range(3000)], [(i * 7919) % 200003 for i in range(120000)]]
+    for n in (5, 6, 21, 22, 85, 86, 341, 342):      # around the fill thresholds
+        cases.append([rng.randrange(100000) for _ in range(n)])
+    for keys in cases:
+        want = set()
+        for k in keys:
+            want.add(k)
+        r = subprocess.run([exe], input="".join("%d\n" % k for k in keys), capture_output=True, text=True, check=True)
+        assert [int(x) for x in r.stdout.split()] == list(want), keys[:10]
+
+
+@pytest.mark.skipif(not os.path.exists(SCRIPT), reason="the reference's netclu_ng.py is only in the build container")
+def test_native_split_against_the_script_on_fresh_networks(netclu, tmp_path):
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLD)))
+    import make_netclu_golden as gen
+    old = gen.OUT
+    gen.OUT = str(tmp_path)
+    try:
+        for seed in range(1000, 1008):
+            gen.tie_case("c", seed)
+            faa, net = str(tmp_path / "c.faa"), str(tmp_path / "c.net")
+            s = subprocess.run([sys.executable, SCRIPT, faa, net], capture_output=True, text=True, check=True).stdout.splitlines()
+            e = dict(os.environ, PD_NETCLU_TRACE="1")
+            r = subprocess.run([netclu, faa, net, "-g"], capture_output=True, text=True, env=e)
+            assert r.returncode == 0
+            assert [ln for ln in r.stderr.splitlines() if ln.startswith("gn (")] == [ln for ln in s if ln.startswith("gn (")], seed
+            assert clus(r.stdout.splitlines()) == clus([ln for ln in s if "F{ " in ln]), seed
+    finally:
+        gen.OUT = old
 
 
 def test_family5_clus_is_the_pangenes_golden(netclu, tmp_path):
