@@ -195,7 +195,7 @@ class GirvanNewman {
     std::vector<Scratch> scratch_;
     std::vector<double> bet_, block_;
     Workers workers_;
-    bool trace_ = false;
+    int trace_ = 0;
     uint64_t par_min_ = 1u << 22;  // nodes x edges from which the blocks pay for their barriers (PD_NETCLU_PAR_MIN)
 
     // g = snet.copy().to_undirected(): Graph.copy / to_undirected add the nodes in the view's order, then the edges as
@@ -372,12 +372,13 @@ public:
     size_t removed_edges = 0, splits = 0;
 
     // threads: 0 = PD_NETCLU_THREADS or the hardware's (at most 32); the result does not depend on it.  PD_NETCLU_TRACE=1 prints the script's own
-    // `gn ([..], [..])` line (netclu_ng.py:107) for every split on stderr, in the script's order.
+    // `gn ([..], [..])` line (netclu_ng.py:107) for every split on stderr, in the script's order; =2 also `rm a b` for
+    // every removed edge (a, b as networkx' edge tuple has them).
     GirvanNewman(const RootGraph& root, std::function<bool(const std::vector<uint32_t>&)> collision, unsigned threads = 0)
         : root_(root), collision_(std::move(collision)), workers_(pick_threads(threads)) {
         scratch_.resize(workers_.size());
         const char* t = getenv("PD_NETCLU_TRACE");
-        trace_ = t && *t && *t != '0';
+        trace_ = t ? atoi(t) : 0;
         if (const char* pm = getenv("PD_NETCLU_PAR_MIN")) par_min_ = strtoull(pm, nullptr, 10);
     }
     static unsigned pick_threads(unsigned asked) {
@@ -424,7 +425,9 @@ public:
             build_copy(nodes, node_set);
             std::vector<uint8_t> first;
             for (;;) {  // _without_most_central_edges: g is connected, so one more component ends it
-                remove_edge(most_central_edge());
+                const uint32_t e = most_central_edge();
+                if (trace_ >= 2) fprintf(stderr, "rm %u %u\n", nodes[edge_[e].first], nodes[edge_[e].second]);
+                remove_edge(e);
                 removed_edges++;
                 first = reach_first();
                 if (std::find(first.begin(), first.end(), 0) != first.end()) break;

@@ -113,6 +113,13 @@ def test_config_full_size_against_the_unmodified_reference(name, tmp_path):
         ctext = "".join(f + "\n" for f in fams)
         assert len(fams) == gold["clus"]["lines"]
         assert hashlib.sha256(ctext.encode()).hexdigest() == gold["clus"]["sha256"], ".clus differs from netclu_ng.py's"
+    if name == "salmonella7":
+        # and the whole of pandelos.sh (:46-79) through the package's own pipeline script: dataset.faa in, out_prefix.clus out
+        script = os.path.join(os.path.dirname(build.NETCLU_BIN), "pandelos.sh")
+        r = subprocess.run(["bash", script, faa, str(tmp_path / "fam")], capture_output=True, text=True, cwd=str(tmp_path))
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "k = %d" % k in r.stdout
+        assert hashlib.sha256(open(str(tmp_path / "fam.clus"), "rb").read()).hexdigest() == gold["clus"]["sha256"]
 
 
 def _first80():

@@ -173,3 +173,28 @@ def test_errors(netclu, tmp_path):
     assert subprocess.run([netclu, str(tmp_path / "missing.faa"), str(net)], capture_output=True).returncode == 1
     faa.write_text("G0\ta\nAAA\n")                      # two columns: the script raises IndexError
     assert subprocess.run([netclu, str(faa), str(net)], capture_output=True).returncode == 1
+
+
+def test_pipeline_script_with_a_stand_in_for_the_similarity_stage(netclu, tmp_path):
+    """pandelos_b200/pandelos.sh (the reference's pandelos.sh:46-79 over the native programs): k from calculate_k, the
+    `.net` from the program named by PD_PANGENES (here a stub that hands out the golden family5 network — the real one
+    needs a GPU, tests/test_gpu_configs.py), netclu_cc -g, and the reference's grep/sed/sort: the golden `.clus`."""
+    script = os.path.join(os.path.dirname(build.NETCLU_BIN), "pandelos.sh")
+    net_dir = os.path.join(os.path.dirname(GOLD), "net")
+    stub = tmp_path / "stub.sh"
+    stub.write_text('#!/bin/bash\nwhile [ $# -gt 0 ]; do case "$1" in -o) out="$2"; shift;; -k) echo "k $2" > "%s";; esac; shift; done\ncp "%s" "$out"\n'
+                    % (tmp_path / "k_seen", os.path.join(net_dir, "family5.net")))
+    stub.chmod(0o755)
+    env = dict(os.environ, PD_PANGENES=str(stub))
+    r = subprocess.run(["bash", script, os.path.join(net_dir, "family5.faa"), str(tmp_path / "fam")], capture_output=True, text=True,
+                       cwd=str(tmp_path), env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # (the reference's sed chain leaves "name " for a singleton's "F{ name }"; the committed golden has the lines stripped)
+    got = open(tmp_path / "fam.clus").read().splitlines()
+    assert got == sorted(got) and sorted(ln.strip() for ln in got) == open(os.path.join(net_dir, "family5.clus")).read().splitlines()
+    k_line = [ln for ln in r.stdout.splitlines() if ln.startswith("k = ")]
+    assert k_line and open(tmp_path / "k_seen").read().split() == ["k", k_line[0][4:]]
+    assert [p for p in os.listdir(tmp_path) if p.startswith("family5.")] == []      # the working directory is removed
+    # usage errors
+    assert subprocess.run(["bash", script, str(tmp_path / "missing.faa"), "x"], capture_output=True, cwd=str(tmp_path)).returncode == 1
+    assert subprocess.run(["bash", script, os.path.join(net_dir, "family5.faa")], capture_output=True, cwd=str(tmp_path)).returncode == 1
