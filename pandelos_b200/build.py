@@ -28,6 +28,7 @@ JNI_LIB = os.path.join(HERE, "libnative.so")
 CLI_BIN = os.path.join(HERE, "pangenes")
 CALCK_BIN = os.path.join(HERE, "calculate_k")
 NETCLU_BIN = os.path.join(HERE, "netclu_cc")
+NETCHECK_BIN = os.path.join(HERE, "net_check")
 SYNTH_LIB = os.path.join(HERE, "libpdsynth.so")
 
 
@@ -102,7 +103,7 @@ def build_jni(force=False):
 
 
 def build_host(force=False):
-    """The native hosts: `pangenes` (links the engine); `calculate_k` and `netclu_cc` (CPU only, no engine)."""
+    """The native hosts: `pangenes` (links the engine); `calculate_k`, `netclu_cc` and `net_check` (CPU only, no engine)."""
     build_engine(force=False)
     hdir = os.path.join(CSRC, "host")
     if not os.path.isdir(hdir):
@@ -119,6 +120,9 @@ def build_host(force=False):
     if force or _stale(NETCLU_BIN, [src] + headers):
         # -ffp-contract=off: girvan_newman.h repeats networkx' float sums operation by operation
         _run([CXX, "-std=c++17", "-O2", "-Wall", "-ffp-contract=off", "-pthread", "-I", hdir, "-o", NETCLU_BIN, src])
+    src = os.path.join(hdir, "net_check_main.cpp")
+    if force or _stale(NETCHECK_BIN, [src] + headers):
+        _run([CXX, "-std=c++17", "-O2", "-Wall", "-I", hdir, "-o", NETCHECK_BIN, src])
     return CLI_BIN
 
 
