@@ -111,7 +111,7 @@ def build_host(force=False):
     headers = _sources(hdir, INCLUDE, exts=(".h", ".hpp"))
     src = os.path.join(hdir, "pangenes_main.cpp")
     if force or _stale(CLI_BIN, [src] + headers + [ENGINE_LIB]):
-        _run([CXX, "-std=c++17", "-O2", "-Wall", "-I", INCLUDE, "-I", hdir, "-o", CLI_BIN, src,
+        _run([CXX, "-std=c++17", "-O2", "-Wall", "-ffp-contract=off", "-I", INCLUDE, "-I", hdir, "-o", CLI_BIN, src,
               "-L", HERE, "-lpandelos_b200", "-Wl,-rpath,$ORIGIN", "-pthread"])
     src = os.path.join(hdir, "calculate_k_main.cpp")
     if force or _stale(CALCK_BIN, [src] + headers):

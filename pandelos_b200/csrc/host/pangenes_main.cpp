@@ -12,6 +12,10 @@
 //                    per undirected edge with src <= dst, score = the float widened to double and printed the way
 //                    Java's Double.toString prints it.  Line ORDER: the reference iterates a HashMap; here lines are
 //                    sorted by (src, dst) — netclu_ng.py reads the file into a graph, the order carries no meaning.
+//   --clus <file>    (not in the reference's CLI) also cluster that network here, as `netclu_ng.py in.faa out.net` +
+//                    pandelos.sh:79 would (netclu.h: components, collision test, Girvan-Newman split), and write the
+//                    gene families: the network goes from memory to the clustering without being parsed back from text.
+//                    Gene names = second header field.
 #include <algorithm>
 #include <atomic>
 #include <charconv>
@@ -27,6 +31,7 @@
 #include <vector>
 
 #include "faa.h"
+#include "netclu.h"
 #include "pandelos_b200.h"
 
 namespace {
@@ -96,13 +101,14 @@ void usage() {
            " -i,--input <arg>    Input file (.faa) to process\n"
            " -j,--threads <arg>  Upper bound on the host threads issuing per-genome calls (1 to 4 are used, by genome count)\n"
            " -k,--kvalue <arg>   Length of the kmers used by the algorithm\n"
-           " -o,--output <arg>   Output file for the network\n");
+           " -o,--output <arg>   Output file for the network\n"
+           "    --clus <arg>     Also write the gene families of that network (what netclu_ng.py + pandelos.sh make of it)\n");
 }
 
 }  // namespace
 
 int main(int argc, char** argv) {
-    std::string in, out;
+    std::string in, out, clus;
     int k = 0, threads = 0;
     bool complexity = false;
     for (int i = 1; i < argc; i++) {
@@ -119,6 +125,7 @@ int main(int argc, char** argv) {
         else if (a == "-k" || a == "--kvalue") k = atoi(need("k"));
         else if (a == "-j" || a == "--threads") threads = atoi(need("j"));
         else if (a == "-c" || a == "--complexity") complexity = true;
+        else if (a == "--clus") clus = need("clus");
         else if (a == "--selftest-format") {
             // the fast writer against the reference formatter on float32 patterns in (0, 1] and around the notation
             // switches (tests/test_network_filter.py; no GPU involved)
@@ -165,6 +172,8 @@ int main(int argc, char** argv) {
     residues.reserve(f.size());
     std::vector<uint64_t> offsets(1, 0);
     std::vector<uint32_t> genome_of;
+    std::vector<std::string_view> gene_name;  // second header field (netclu_ng.py:22), views into the mapped file
+    std::string_view name_field;
     std::unordered_map<std::string, uint32_t> genome_id;
     std::string genome_name, bad_header;
     bool name_line = true;
@@ -180,12 +189,14 @@ int main(int argc, char** argv) {
                 return;
             }
             genome_name.assign(b, tab);
+            name_field = std::string_view(tab + 1, (size_t)(static_cast<const char*>(memchr(tab + 1, '\t', (size_t)(e - tab - 1))) - tab - 1));
         } else {
             residues.insert(residues.end(), reinterpret_cast<const uint8_t*>(b), reinterpret_cast<const uint8_t*>(e));
             offsets.push_back(residues.size());
             auto it = genome_id.find(genome_name);
             if (it == genome_id.end()) it = genome_id.emplace(genome_name, (uint32_t)genome_id.size()).first;
             genome_of.push_back(it->second);
+            gene_name.push_back(name_field);
         }
         name_line = !name_line;
     });
@@ -329,5 +340,23 @@ int main(int argc, char** argv) {
     fclose(o);
     timer.lap("write .net");
     printf("Network: %llu undirected edges written to %s\n", (unsigned long long)lines, out.c_str());
+
+    // ---- --clus: netclu_ng.py on that network, from memory (the .net lines in their written order)
+    if (!clus.empty()) {
+        std::vector<pd_host::NetEdge> net_lines;
+        net_lines.reserve(lines);
+        for (size_t i = 0; i < net.size(); i++)
+            if (!i || net[i].key != net[i - 1].key) net_lines.push_back({(uint32_t)(net[i].key >> 32), (uint32_t)net[i].key});
+        const pd_host::NetcluResult fam = pd_host::netclu(gene_name, genome_of, net_lines, true);
+        const std::string text = pd_host::clus_text(fam.f_lines);
+        FILE* c = fopen(clus.c_str(), "w");
+        if (!c || fwrite(text.data(), 1, text.size(), c) != text.size() || fclose(c) != 0) {
+            fprintf(stderr, "cannot write %s\n", clus.c_str());
+            return 1;
+        }
+        timer.lap("families");
+        printf("Families: %zu components (%zu split into %zu by Girvan-Newman, %zu edges removed), %zu genes outside the network; written to %s\n",
+               fam.n_comp, fam.n_split, fam.n_split_families, fam.n_removed, fam.n_single, clus.c_str());
+    }
     return 0;
 }

@@ -151,3 +151,30 @@ def test_native_cli_on_the_golden_input(engine_lib, tmp_path):
     r = subprocess.run([build.build_host(), "-i", os.path.join(GOLD, "family5.faa"), "-k", "4", "-o", out], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(out).read() == open(os.path.join(GOLD, "family5.net")).read()
+    # --clus: the families netclu_ng.py + pandelos.sh:79 make of that network (the reference chain leaves "name " for a
+    # gene outside the network; the committed golden has the lines stripped)
+    clus = str(tmp_path / "family5.clus")
+    r = subprocess.run([build.CLI_BIN, "-i", os.path.join(GOLD, "family5.faa"), "-k", "4", "-o", out, "--clus", clus], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = open(clus).read().splitlines()
+    assert got == sorted(got) and sorted(ln.strip() for ln in got) == open(os.path.join(GOLD, "family5.clus")).read().splitlines()
+
+
+def test_native_cli_over_the_emulated_engine(emu_lib, tmp_path):
+    """csrc/host/pangenes_main.cpp linked with the emulator build of the engine (same C ABI): the CLI's .faa reader, its
+    genome tasks, edge bookkeeping, .net writer and --clus clustering run on the CPU against the reference-made goldens."""
+    import subprocess
+    import build_emu
+    from pandelos_b200 import build
+    lib = build_emu.build()
+    exe = str(tmp_path / "pangenes_emu")
+    host = os.path.join(build.CSRC, "host")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-I", build.INCLUDE, "-I", host, "-o", exe,
+                    os.path.join(host, "pangenes_main.cpp"), lib, "-Wl,-rpath," + os.path.dirname(lib), "-pthread"], check=True)
+    out, clus = str(tmp_path / "family5.net"), str(tmp_path / "family5.clus")
+    r = subprocess.run([exe, "-i", os.path.join(GOLD, "family5.faa"), "-k", "4", "-o", out, "--clus", clus], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert open(out).read() == open(os.path.join(GOLD, "family5.net")).read()
+    got = open(clus).read().splitlines()
+    assert got == sorted(got) and sorted(ln.strip() for ln in got) == open(os.path.join(GOLD, "family5.clus")).read().splitlines()
+    assert "Families: " in r.stdout and "Girvan-Newman" in r.stdout
