@@ -1267,7 +1267,10 @@ inline bool small_index(const Index& ix) { return ix.info.S <= (1u << 18); }
 inline void levels_of(const Index& ix, Level lv[kLevels]) {
     lv[0] = {512, 9, 128, 256, 256};
     lv[1] = {2048, 11, 256, 512, 1536};
-    lv[2] = {4096, 11, 512, 1024, ~0ull};
+    // 4992 tier-1 slots: what two CTAs per SM leave room for (112.9 KB each).  Against 4096 it halves the rows that
+    // overflow and are scored a second time (21 K -> 10 K of 3.8 M on the 1,000-genome input) and takes the whole job's
+    // scoring from 749 to 729 ms; the landscape around it is bumpy (tools/levels_sweep.py, profiles/r02_levels_sweep.txt).
+    lv[2] = {4992, 11, 512, 1024, ~0ull};
     lv[3] = {2048, 14, 1024, 1024, 0};  // few, heavy rows, one CTA per SM: twice the warps per row shortens the tail
     // Small indices (tens of genomes, k = 4..5): a row shares random k-mers with thousands of the few ten thousand
     // genes, so its columns are many relative to S and the tier-1 slots (S / T1 genes each) collide.  A larger table
