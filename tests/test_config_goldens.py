@@ -102,3 +102,37 @@ def test_restatement_reproduces_the_reference_goldens_at_config_size():
         fams = sorted(set(ln.replace("F{ ", "").replace("}", "").replace(" ;", "") for ln in r.stdout.splitlines() if "F{ " in ln))
         ctext = "".join(f + "\n" for f in fams)
         assert len(fams) == gold["clus"]["lines"] and hashlib.sha256(ctext.encode()).hexdigest() == gold["clus"]["sha256"]
+
+
+def test_first_girvan_newman_step_on_the_component_the_script_cannot_finish(tmp_path):
+    """mycoplasma64: the `.net` (made here from the C restatement's scores, sha256 = the golden of the reference's) has
+    one component of 11,325 genes that netclu_ng.py does not split in any reasonable time.  One networkx betweenness pass
+    on it was run once (tests/golden/make_netclu_first_edge.py, ~40 minutes): the edge it removes first is the edge the
+    native split removes first (netclu_cc -g, PD_NETCLU_TRACE=2; stopped after that line)."""
+    gold = load("mycoplasma64")
+    first = json.load(open(os.path.join(HERE, "golden", "netclu_first_edge_mycoplasma64.json")))
+    w = synth.shape("mycoplasma64")
+    k = synth.calculate_k(w)
+    o = cport.OracleIndex(w.residues, w.offsets, w.genome_of, k)
+    try:
+        net = pangenes_java.PangeneNet()
+        for g in range(w.G):
+            for src, dst, sc in pangenes_java.genome_task(o.compute_scores(g), g, w.G):
+                net.add_connection(src, dst, sc)
+    finally:
+        o.close()
+    text = "".join(ln + "\n" for ln in net.lines())
+    assert hashlib.sha256(text.encode()).hexdigest() == gold["net"]["sha256"]
+    from pandelos_b200 import build
+    build.build_host()
+    faa, netf = str(tmp_path / "in.faa"), str(tmp_path / "in.net")
+    w.write_faa(faa)
+    open(netf, "w").write(text)
+    p = subprocess.Popen([build.NETCLU_BIN, faa, netf, "-g"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True,
+                         env=dict(os.environ, PD_NETCLU_TRACE="2"))
+    try:
+        line = p.stderr.readline()       # the large component is the first in the network's node order
+    finally:
+        p.kill()
+        p.wait()
+    assert line.split() == ["rm", str(first["first_removed_edge"][0]), str(first["first_removed_edge"][1])]
