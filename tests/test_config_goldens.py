@@ -110,7 +110,7 @@ def test_first_girvan_newman_step_on_the_component_the_script_cannot_finish(tmp_
     on it was run once (tests/golden/make_netclu_first_edge.py, ~40 minutes): the edge it removes first is the edge the
     native split removes first (netclu_cc -g, PD_NETCLU_TRACE=2; stopped after that line)."""
     gold = load("mycoplasma64")
-    first = json.load(open(os.path.join(HERE, "golden", "netclu_first_edge_mycoplasma64.json")))
+    first = json.load(open(os.path.join(DIGESTS, "mycoplasma64_first_removed_edge.json")))
     w = synth.shape("mycoplasma64")
     k = synth.calculate_k(w)
     o = cport.OracleIndex(w.residues, w.offsets, w.genome_of, k)
