@@ -198,3 +198,16 @@ def test_pipeline_script_with_a_stand_in_for_the_similarity_stage(netclu, tmp_pa
     # usage errors
     assert subprocess.run(["bash", script, str(tmp_path / "missing.faa"), "x"], capture_output=True, cwd=str(tmp_path)).returncode == 1
     assert subprocess.run(["bash", script, os.path.join(net_dir, "family5.faa")], capture_output=True, cwd=str(tmp_path)).returncode == 1
+
+
+@pytest.mark.parametrize("name", ["family5", "ties40", "random12x25"])
+def test_clus_file_is_what_the_reference_shell_chain_makes_of_the_lines(netclu, name, tmp_path):
+    # netclu_cc -g -o out.clus against pandelos.sh:79 (grep | sed | sed | sed | sort | uniq) run on the tool's stdout
+    out = str(tmp_path / "out.clus")
+    r = subprocess.run([netclu, os.path.join(GOLD, name + ".faa"), os.path.join(GOLD, name + ".net"), "-g", "-o", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    chain = r'grep "F{ " | sed s/F{\ //g | sed s/}//g | sed s/\ \;//g | LC_ALL=C sort | uniq'
+    want = subprocess.run(["bash", "-c", chain], input=r.stdout, capture_output=True, text=True, check=True).stdout
+    assert open(out).read() == want and want.count("\n") > 10
+    # -o without -g: the families would be incomplete
+    assert subprocess.run([netclu, os.path.join(GOLD, name + ".faa"), os.path.join(GOLD, name + ".net"), "-o", out], capture_output=True).returncode == 1
