@@ -71,6 +71,18 @@ def test_overflow_levels_and_dense_path(monkeypatch):
     assert st["fallback_rows"] > 0
 
 
+def test_table_sizes_that_are_not_powers_of_two(monkeypatch):
+    """The level tables' tier-1 size is any multiple of 32 (the default top level has 4992 slots): the slot function
+    floor(c * T1 / S), the clearing and the finalize scan on small odd sizes, with and without overflow into the retry level."""
+    w = synth.generate(4, 70, 85.0, 0.1, 53)
+    for levels in ("96:5:128:64:40,160:6:128:96:200,224:6:128:96:0,352:8:128:128:0",
+                   "32:5:128:32:8,96:5:128:64:64,160:5:128:64:0,480:7:256:128:0"):
+        monkeypatch.setenv("PD_LEVELS", levels)
+        st = check_workload(w, 3)
+        assert st["cells"] > 0
+    monkeypatch.delenv("PD_LEVELS")
+
+
 def test_cell_buffer_regrow():
     w, k = fixtures.random_workload(54, genes=60, genomes=3, max_len=40)
     st = check_workload(w, k, cell_capacity=7)
