@@ -14,6 +14,9 @@ connected-component tool (pandelos_b200/csrc/host/netclu_cc_main.cpp).
                             script on rest.net) gives other families than the script on the full network}
 
     python tests/golden/make_netclu_golden.py
+    python tests/golden/make_netclu_golden.py --fuzz LO HI     no files: tie_case(seed) for LO <= seed < HI, netclu_cc -g against
+                                                               the script (families and every `gn (..)` line); run for seeds
+                                                               0..500 in round 2: 10,757 splits, no difference
 """
 import json
 import os
@@ -199,5 +202,35 @@ def main():
         print(name, dict((k, len(v) if isinstance(v, list) else v) for k, v in d.items()))
 
 
+def fuzz(lo, hi):
+    import tempfile
+    global OUT
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from pandelos_b200 import build
+    build.build_host()
+    keep, bad, splits = OUT, 0, 0
+    with tempfile.TemporaryDirectory() as td:
+        OUT = td
+        try:
+            for seed in range(lo, hi):
+                tie_case("c", seed)
+                faa, net = os.path.join(td, "c.faa"), os.path.join(td, "c.net")
+                a = subprocess.run([sys.executable, SCRIPT, faa, net], capture_output=True, text=True, check=True).stdout.splitlines()
+                b = subprocess.run([build.NETCLU_BIN, faa, net, "-g"], capture_output=True, text=True, check=True,
+                                   env=dict(os.environ, PD_NETCLU_TRACE="1"))
+                gn = [ln for ln in a if ln.startswith("gn (")]
+                splits += len(gn)
+                if gn != [ln for ln in b.stderr.splitlines() if ln.startswith("gn (")] or \
+                        clus([ln for ln in a if "F{ " in ln]) != clus(b.stdout.splitlines()):
+                    bad += 1
+                    print("MISMATCH seed", seed, flush=True)
+        finally:
+            OUT = keep
+    print("seeds %d..%d: %d mismatches, %d splits" % (lo, hi, bad, splits))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) == 4 and sys.argv[1] == "--fuzz":
+        fuzz(int(sys.argv[2]), int(sys.argv[3]))
+    else:
+        main()

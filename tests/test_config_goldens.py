@@ -107,8 +107,8 @@ def test_restatement_reproduces_the_reference_goldens_at_config_size():
 def test_first_girvan_newman_step_on_the_component_the_script_cannot_finish(tmp_path):
     """mycoplasma64: the `.net` (made here from the C restatement's scores, sha256 = the golden of the reference's) has
     one component of 11,325 genes that netclu_ng.py does not split in any reasonable time.  One networkx betweenness pass
-    on it was run once (tests/golden/make_netclu_first_edge.py, ~40 minutes): the edge it removes first is the edge the
-    native split removes first (netclu_cc -g, PD_NETCLU_TRACE=2; stopped after that line)."""
+    on it was run once (tests/golden/make_netclu_first_edge.py, ~40 minutes), and the script itself until its first `gn`
+    line: the edge removed first and the first split are those of the native split (netclu_cc -g, PD_NETCLU_TRACE=2; stopped there)."""
     gold = load("mycoplasma64")
     first = json.load(open(os.path.join(DIGESTS, "mycoplasma64_first_removed_edge.json")))
     w = synth.shape("mycoplasma64")
@@ -130,9 +130,15 @@ def test_first_girvan_newman_step_on_the_component_the_script_cannot_finish(tmp_
     open(netf, "w").write(text)
     p = subprocess.Popen([build.NETCLU_BIN, faa, netf, "-g"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True,
                          env=dict(os.environ, PD_NETCLU_TRACE="2"))
+    lines = []
     try:
-        line = p.stderr.readline()       # the large component is the first in the network's node order
+        while not lines or not lines[-1].startswith("gn ("):   # the large component is the first in the network's node order
+            lines.append(p.stderr.readline().rstrip("\n"))
+            assert lines[-1] and len(lines) < 10
     finally:
         p.kill()
         p.wait()
-    assert line.split() == ["rm", str(first["first_removed_edge"][0]), str(first["first_removed_edge"][1])]
+    assert lines[0].split() == ["rm", str(first["first_removed_edge"][0]), str(first["first_removed_edge"][1])]
+    # ... and the first split is the one the unmodified script prints after 67 minutes: 10,635 + 690 genes, two edges removed
+    assert len(lines) == 1 + first["first_split"]["removed_edges_before"]
+    assert hashlib.sha256(lines[-1].encode()).hexdigest() == first["first_split"]["gn_line_sha256"]
