@@ -107,7 +107,7 @@ def test_restatement_reproduces_the_reference_goldens_at_config_size():
 def test_first_girvan_newman_step_on_the_component_the_script_cannot_finish(tmp_path):
     """mycoplasma64: the `.net` (made here from the C restatement's scores, sha256 = the golden of the reference's) has
     one component of 11,325 genes that netclu_ng.py does not split in any reasonable time.  One networkx betweenness pass
-    on it was run once (tests/golden/make_netclu_first_edge.py, ~40 minutes), and the script itself until its first `gn`
+    on it was run once (tests/golden/verify_netclu_splits.py --first-edge, ~40 minutes), and the script itself until its first `gn`
     line: the edge removed first and the first split are those of the native split (netclu_cc -g, PD_NETCLU_TRACE=2; stopped there)."""
     gold = load("mycoplasma64")
     first = json.load(open(os.path.join(DIGESTS, "mycoplasma64_first_removed_edge.json")))
