@@ -10,6 +10,8 @@ where neither /root/reference nor a JVM exists — can check the engine on the v
       net        : sha256 / line count of the .net text made from the reference's scores by the restated Java host
                    (oracle/pangenes_java.py: Pangenes.java:98-176, PangeneNet.java:159-179; no JVM here)
       clus       : sha256 / line count of the .clus the reference's own netclu_ng.py + pandelos.sh:79 make of that .net
+                   (mycoplasma64: the script does not finish; the .clus of the native split, verified level by level
+                   against networkx — <config>_clus_verified.json, tests/golden/verify_netclu_splits.py)
   scaleout1000_first80.json   the first 80 genomes of the scale-out config (S > 2^18 genes, k = 7: the engine's
                    large-index configuration), same content for a sample of genomes, no .net / .clus
   scaleout1000_sample.json    (--scaleout-full; ~35 GB of RAM, ~30 min) the FULL 1,000-genome index, genomes
@@ -117,7 +119,11 @@ def config_doc(name, w, k, genomes, with_net):
             except subprocess.TimeoutExpired:
                 # Girvan-Newman (networkx edge betweenness, recomputed per removed edge) on the large mixed components of
                 # the many-genome config does not end in reasonable time; the .net golden above still pins the input to it
-                doc["clus"] = {"unavailable": "the reference's netclu_ng.py did not finish its Girvan-Newman split within %d s" % NETCLU_TIMEOUT_S}
+                why = "the reference's netclu_ng.py did not finish its Girvan-Newman split within %d s" % NETCLU_TIMEOUT_S
+                # <config>_clus_verified.json: the native split's .clus, checked level by level against networkx
+                # (tests/golden/verify_netclu_splits.py; hours of CPU, done once and committed with its evidence)
+                ver = os.path.join(OUT, name + "_clus_verified.json")
+                doc["clus"] = dict(json.load(open(ver)), script_unavailable=why) if os.path.exists(ver) else {"unavailable": why}
                 o.close()
                 return doc
         # pandelos.sh:79: grep "F{ " | sed s/F{\ //g | sed s/}//g | sed s/\ \;//g | sort | uniq   (byte order, LC_ALL=C)

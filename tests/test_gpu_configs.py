@@ -89,8 +89,9 @@ def test_config_full_size_against_the_unmodified_reference(name, tmp_path):
     cli = build.build_host()
     faa, out = str(tmp_path / "in.faa"), str(tmp_path / "out.net")
     w.write_faa(faa)
-    # --clus: the families too, clustered from the network in memory (not for mycoplasma64, whose Girvan-Newman split the
-    # reference's script cannot finish: there is no golden to compare with)
+    # --clus: the families too, clustered from the network in memory (mycoplasma64, whose Girvan-Newman split the
+    # reference's script cannot finish: the golden is the native split verified level by level against networkx,
+    # tests/golden/digests/mycoplasma64_clus_verified.json; its 11,325-gene component takes about a minute of host time)
     clus_file = str(tmp_path / "out.clus")
     r = subprocess.run([cli, "-i", faa, "-k", str(k), "-o", out] + (["--clus", clus_file] if "sha256" in gold["clus"] else []),
                        capture_output=True, text=True)
@@ -112,7 +113,7 @@ def test_config_full_size_against_the_unmodified_reference(name, tmp_path):
         assert len(fam_lines) <= gold["clus"]["lines"]
     # .clus itself (pandelos.sh:78-79): the native netclu with its own Girvan-Newman split (netclu_cc -g) against the
     # golden of the unmodified netclu_ng.py on the identical .net — .faa in, families out, nothing of the reference run
-    if "sha256" in gold["clus"]:
+    if "sha256" in gold["clus"] and name != "mycoplasma64":     # (mycoplasma64: pangenes --clus above ran the same code)
         r = subprocess.run([build.NETCLU_BIN, faa, out, "-g"], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         fams = sorted(set(ln.replace("F{ ", "").replace("}", "").replace(" ;", "") for ln in r.stdout.splitlines() if "F{ " in ln))
