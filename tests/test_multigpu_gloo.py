@@ -136,7 +136,7 @@ def _shard_worker(rank, world, port, emu_path, out_dir, low_complexity):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,low", [(2, 0.0), (3, 0.3)])
+@pytest.mark.parametrize("world,low", [(2, 0.0), (3, 0.3), (4, 0.1), (8, 0.0)])
 def test_sharded_build_matches_the_single_process_index(tmp_path, world, low):
     import build_emu
     import torch.multiprocessing as mp
